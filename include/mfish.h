@@ -1,0 +1,219 @@
+/* libmfish_sm100 -- C ABI of the B200-native muscle-FISH spot-analysis path.
+ *
+ * The reference (cpkelley94/muscle-FISH) has no FFI layer: its boundary is the
+ * Python function surface of modules/muscle_fish.py and modules/scope_utils3.py
+ * plus two direct scipy calls.  Each entry point below names the reference
+ * call (file:line, relative to the upstream repository root) whose arithmetic
+ * it replaces; INTEGRATION.md shows the ctypes binding the Python host side
+ * uses.
+ *
+ * Conventions
+ *  - plain C: pointers + sizes only, no torch / C++ types.
+ *  - every function returns an int status (MFISH_OK == 0, < 0 on error);
+ *    mfish_last_error() gives a thread-local message for the last failure.
+ *  - pointers named *_dev are DEVICE pointers owned by the caller; pointers
+ *    named *_host are host pointers read before the call returns.
+ *  - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it.
+ *  - device volumes are laid out [nz][nx][ny], y contiguous ("zxy").  The
+ *    reference's logical order is (x, y, z) with z fastest ("xyz",
+ *    modules/muscle_fish.py:60-71); mfish_ingest() converts.  Spot indices
+ *    returned by the library are REFERENCE raster indices
+ *    ((x*ny + y)*nz + z)*ns + s so that ordering matches np.nonzero().
+ */
+#ifndef MFISH_H_
+#define MFISH_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MFISH_ABI_VERSION 2
+
+#define MFISH_OK 0
+#define MFISH_ERR_INVALID (-1)
+#define MFISH_ERR_CUDA (-2)
+#define MFISH_ERR_CAPACITY (-3)
+#define MFISH_ERR_UNSUPPORTED (-4)
+
+/* element types accepted by mfish_ingest */
+#define MFISH_U8 0
+#define MFISH_U16 1
+#define MFISH_I16 2
+#define MFISH_I32 3
+#define MFISH_I64 4
+#define MFISH_F32 5
+#define MFISH_F64 6
+
+#define MFISH_LAYOUT_XYZ 0 /* reference order, z fastest */
+#define MFISH_LAYOUT_ZXY 1 /* device order, y fastest  */
+
+#define MFISH_DST_F32 0     /* numeric value as float32              */
+#define MFISH_DST_NONZERO 1 /* uint8: 1 where src != 0 else 0 (masks) */
+#define MFISH_DST_ISZERO 2  /* uint8: 1 where src == 0 else 0 (np.logical_not(mask),
+                               nocodazole/fish_analysis_noco.py:218)   */
+
+#define MFISH_BOUNDARY_REFLECT 0 /* scipy 'reflect'  (gaussian_laplace default) */
+#define MFISH_BOUNDARY_NEAREST 1 /* scipy 'nearest'  (skimage.filters.gaussian) */
+
+#define MFISH_AXIS_Z 0
+#define MFISH_AXIS_X 1
+#define MFISH_AXIS_Y 2
+
+/* one separable pass: G = order-0 taps, D = order-2 taps */
+#define MFISH_CONV_G 0    /* out0 = G*in0                               */
+#define MFISH_CONV_GD 1   /* out0 = G*in0, out1 = D*in0                 */
+#define MFISH_CONV_MID 2  /* out0 = G*in0, out1 = D*in0 + G*in1         */
+#define MFISH_CONV_LAST 3 /* out0 = out_scale * (D*in0 + G*in1)         */
+
+#define MFISH_MAX_RADIUS 128
+
+int mfish_abi_version(void);
+const char* mfish_last_error(void);
+/* number of kernels this library has launched in the calling process */
+int64_t mfish_launch_count(void);
+
+/* ---- ingest / normalisation ------------------------------------------- *
+ * replaces the float64 copies made by su.normalize_image
+ * (modules/scope_utils3.py:381-386) and open_image's transposed view
+ * (modules/muscle_fish.py:60-71).  Converts `src_dev` (dtype/layout given)
+ * into the device layout; when minmax_dev != NULL also reduces min and max of
+ * the converted values into minmax_dev[0..1] (float).                      */
+int mfish_ingest(const void* src_dev, int src_dtype, int src_layout, int64_t nx, int64_t ny,
+                 int64_t nz, void* dst_dev, int dst_kind, float* minmax_dev, void* stream);
+
+/* global min / max (np.min, np.max inside np.interp, scope_utils3.py:386) */
+int mfish_minmax_f32(const float* vol_dev, int64_t n, float* minmax_dev, void* stream);
+
+/* su.normalize_image as a stand-alone call (modules/scope_utils3.py:381-386):
+ * out = np.interp(src, (min, max), (vmin, vmax)) in float64, same element
+ * order as src (n elements of src_dtype).  ws16_dev: 16 bytes of scratch.     */
+int mfish_normalize_f64(const void* src_dev, int src_dtype, int64_t n, double vmin, double vmax,
+                        double* out_dev, void* ws16_dev, void* stream);
+
+/* device [z][x][y] float32 -> float64 in dst_layout (MFISH_LAYOUT_XYZ: the
+ * reference order its callers index as arr[x, y, z]): the dense outputs handed
+ * back to the reference's scripts (the distance map of
+ * nocodazole/fish_analysis_noco.py:218-221, fix_bleaching's corrected image,
+ * filtered volumes).                                                          */
+int mfish_export_f64(const float* vol_zxy_dev, int64_t nx, int64_t ny, int64_t nz, int dst_layout,
+                     double* out_dev, void* stream);
+
+/* ---- separable filtering ---------------------------------------------- *
+ * replaces scipy.ndimage.correlate1d as driven by gaussian_filter /
+ * gaussian_laplace (call sites modules/muscle_fish.py:333,357,661 through
+ * skimage.feature.blob_log / skimage.filters.gaussian).  `taps_*_host` hold
+ * radius+1 half taps (offset 0..radius; the kernels are symmetric).  When
+ * norm_minmax_dev != NULL, in0 is mapped (v-min)/(max-min) on load
+ * (ops G / GD only).                                                       */
+int mfish_sepconv_f32(const float* in0_dev, const float* in1_dev, float* out0_dev, float* out1_dev,
+                      int64_t nz, int64_t nx, int64_t ny, int axis, const double* taps_g_host,
+                      const double* taps_d_host, int radius, int boundary, int op, float out_scale,
+                      const float* norm_minmax_dev, void* stream);
+
+/* skimage.filters.gaussian(img, sigma) == gaussian_filter(mode, truncate=4)
+ * (modules/muscle_fish.py:166,239,357; nocodazole/fish_analysis_noco.py:235).
+ * sigma_zxy_host[3] in device axis order; tmp_dev is one scratch volume.   */
+int mfish_gaussian3d_f32(const float* in_dev, float* out_dev, float* tmp_dev, int64_t nz, int64_t nx,
+                         int64_t ny, const double* sigma_zxy_host, int boundary,
+                         const float* norm_minmax_dev, void* stream);
+
+/* -sigma^2 * scipy.ndimage.gaussian_laplace(normalize(img), sigma), the
+ * per-scale volume of skimage.feature.blob_log (modules/muscle_fish.py:333,
+ * 661; modules/scope_utils3.py:403).  Three fused passes (y: G,D; z: MID;
+ * x: LAST).  tmp1..3 are scratch volumes; out_dev is also used as scratch.  */
+int mfish_log3d_f32(const float* in_dev, float* out_dev, float* tmp1_dev, float* tmp2_dev,
+                    float* tmp3_dev, int64_t nz, int64_t nx, int64_t ny, double sigma,
+                    const float* norm_minmax_dev, void* stream);
+
+/* ---- spot detection --------------------------------------------------- *
+ * skimage.feature.peak_local_max(cube, threshold_abs=t, footprint=ones(3^4))
+ * as blob_log calls it: v > t and v >= every in-volume neighbour in
+ * (scale, z, x, y); ties kept.  cube_dev is [ns][nz][nx][ny].  Writes up to
+ * `capacity` (index, value) pairs in arbitrary order and the total number of
+ * peaks found into *count_dev (which may exceed capacity: re-run larger).   */
+int mfish_nms_compact_f32(const float* cube_dev, int64_t ns, int64_t nz, int64_t nx, int64_t ny,
+                          float threshold, int64_t* out_idx_dev, float* out_val_dev,
+                          uint32_t* count_dev, int64_t capacity, void* stream);
+
+/* order peaks like peak_local_max (descending value, ties by ascending
+ * raster index) and apply blob_log's _prune_blobs for equal sigma: with
+ * integer coordinates, peak r is dropped iff some peak of lower rank-order
+ * priority (index > r) lies within squared voxel distance cutoff_sq.
+ * n is the number of valid entries.  alive_dev[r] in {0,1}.                */
+int mfish_rank_prune(const int64_t* idx_dev, const float* val_dev, int64_t n, int64_t ns,
+                     int64_t nz, int64_t nx, int64_t ny, int64_t cutoff_sq, int64_t* idx_out_dev,
+                     float* val_out_dev, uint8_t* alive_out_dev, void* stream);
+
+/* candidate pairs for the unequal-sigma prune (multi-scale blob_log,
+ * modules/scope_utils3.py:403): all i<j (rank order) whose squared voxel
+ * distance is <= cutoff_sq_host[si*ns+sj].  Pairs are written unordered.   */
+int mfish_overlap_pairs(const int64_t* idx_ranked_dev, int64_t n, int64_t ns, int64_t nz, int64_t nx,
+                        int64_t ny, const int64_t* cutoff_sq_host, int32_t* pairs_dev,
+                        uint32_t* count_dev, int64_t capacity, void* stream);
+
+/* ---- statistics used by find_spots_snrfilter / fix_bleaching ----------- */
+#define MFISH_QUANTILE_WS_BYTES (64 * 1024)
+/* np.percentile(img[mask], q) order statistics (modules/muscle_fish.py:355-356):
+ * out_dev = {value[k], value[k+1]} of the masked RAW values, k = floor of
+ * numpy's 'linear' virtual index; info_dev = {gamma, n_masked}.            */
+int mfish_masked_quantile_f32(const float* vol_dev, const uint8_t* mask_dev, int64_t n, double q,
+                              void* ws_dev, float* out_dev, double* info_dev, void* stream);
+
+/* img_blur[pos] of skimage.filters.gaussian(normalize(img), sigma)
+ * (modules/muscle_fish.py:357-365,385-388), evaluated only at the given
+ * points in float64.  pts_dev is npts x 3 int32 (z, x, y).                 */
+int mfish_blur_at_points(const float* vol_dev, int64_t nz, int64_t nx, int64_t ny,
+                         const int32_t* pts_dev, int64_t npts, const double* taps_z_host, int rz,
+                         const double* taps_x_host, int rx, const double* taps_y_host, int ry,
+                         int boundary, const float* norm_minmax_dev, double* out_dev, void* stream);
+
+/* value lookups at integer voxel positions: mask[spot] tests
+ * (modules/muscle_fish.py:335-343,663-670) and the interpn gather of the
+ * distance map (nocodazole/fish_analysis_noco.py:297-298).                 */
+int mfish_gather_f32(const float* vol_dev, int64_t nz, int64_t nx, int64_t ny, const int32_t* pts_dev,
+                     int64_t npts, float* out_dev, void* stream);
+int mfish_gather_u8(const uint8_t* vol_dev, int64_t nz, int64_t nx, int64_t ny, const int32_t* pts_dev,
+                    int64_t npts, uint8_t* out_dev, void* stream);
+
+/* per-z-plane masked sum and count (fix_bleaching, modules/muscle_fish.py:
+ * 456-461).  sums_dev / counts_dev are double[nz]; mask_dev may be NULL.   */
+int mfish_plane_sums_f32(const float* vol_dev, const uint8_t* mask_dev, int64_t nz, int64_t nx,
+                         int64_t ny, double* sums_dev, double* counts_dev, void* stream);
+/* out = in * factor[z] (modules/muscle_fish.py:506-507)                    */
+int mfish_scale_planes_f32(const float* in_dev, float* out_dev, int64_t nz, int64_t nx, int64_t ny,
+                           const float* factor_dev, void* stream);
+
+/* ---- Euclidean distance transform ------------------------------------- *
+ * scipy.ndimage.distance_transform_edt(mask, sampling)
+ * (nocodazole/fish_analysis_noco.py:218; simulation/analyze_simulation.py:101):
+ * distance from every voxel to the nearest ZERO voxel of mask_dev.  Exact,
+ * separable: one scan pass (y) + two lower-envelope passes (x, z).
+ * spacing_zxy_host[3] in device axis order.  out_dist_dev (float32) and/or
+ * out_sq_dev (int32 squared voxel distance; isotropic spacing only) may be
+ * NULL.  A mask with no zero voxel yields +inf (scipy returns garbage).    */
+int64_t mfish_edt_workspace_bytes(int64_t nz, int64_t nx, int64_t ny);
+int mfish_edt3d_u8(const uint8_t* mask_dev, int64_t nz, int64_t nx, int64_t ny,
+                   const double* spacing_zxy_host, float* out_dist_dev, int32_t* out_sq_dev,
+                   void* workspace_dev, void* stream);
+
+/* The same transform in two halves, for a z-slab decomposed mosaic: the y and
+ * x passes are local to a z-slab; the z pass runs after the slabs have been
+ * re-partitioned into x-slabs (all-to-all).  f2 is the squared in-plane
+ * distance, 4 bytes per voxel, encoded as *f2_kind_host says.
+ * mfish_edt_inplane_u8 needs mfish_edt_workspace_bytes() of scratch,
+ * mfish_edt_zpass needs nz*nx*ny*4 bytes.                                    */
+#define MFISH_EDT_F2_I32 0 /* exact integer voxel^2 (x spacing == y spacing) */
+#define MFISH_EDT_F2_F32 1 /* float32 physical units^2                       */
+int mfish_edt_inplane_u8(const uint8_t* mask_dev, int64_t nz, int64_t nx, int64_t ny,
+                         const double* spacing_zxy_host, void* f2_out_dev, int* f2_kind_host,
+                         void* workspace_dev, void* stream);
+int mfish_edt_zpass(const void* f2_dev, int f2_kind, int64_t nz, int64_t nx, int64_t ny,
+                    const double* spacing_zxy_host, float* out_dist_dev, int32_t* out_sq_dev,
+                    void* link_ws_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MFISH_H_ */

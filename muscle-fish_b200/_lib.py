@@ -1,0 +1,103 @@
+"""ctypes binding of ``libmfish_sm100.so`` (the C ABI declared in ``include/mfish.h``).
+
+There is NO fallback: if the shared library is missing the first use raises.
+Build it with ``python __graft_entry__.py build`` (or ``make -C muscle-fish_b200/csrc``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmfish_sm100.so")
+
+# constants mirrored from include/mfish.h
+ABI_VERSION = 2
+OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_UNSUPPORTED = 0, -1, -2, -3, -4
+U8, U16, I16, I32, I64, F32, F64 = range(7)
+LAYOUT_XYZ, LAYOUT_ZXY = 0, 1
+DST_F32, DST_NONZERO, DST_ISZERO = 0, 1, 2
+BOUNDARY_REFLECT, BOUNDARY_NEAREST = 0, 1
+AXIS_Z, AXIS_X, AXIS_Y = 0, 1, 2
+CONV_G, CONV_GD, CONV_MID, CONV_LAST = 0, 1, 2, 3
+QUANTILE_WS_BYTES = 64 * 1024
+EDT_F2_I32, EDT_F2_F32 = 0, 1
+
+
+class MfishError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libmfish_sm100 error {code}: {msg}")
+        self.code = code
+
+
+_p, _i, _i64, _f, _d = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
+
+# name -> (restype, argtypes); every entry point of include/mfish.h
+SIGNATURES = {
+    "mfish_abi_version": (_i, []),
+    "mfish_last_error": (C.c_char_p, []),
+    "mfish_launch_count": (_i64, []),
+    "mfish_ingest": (_i, [_p, _i, _i, _i64, _i64, _i64, _p, _i, _p, _p]),
+    "mfish_minmax_f32": (_i, [_p, _i64, _p, _p]),
+    "mfish_normalize_f64": (_i, [_p, _i, _i64, _d, _d, _p, _p, _p]),
+    "mfish_sepconv_f32": (_i, [_p, _p, _p, _p, _i64, _i64, _i64, _i, _p, _p, _i, _i, _i, _f, _p, _p]),
+    "mfish_gaussian3d_f32": (_i, [_p, _p, _p, _i64, _i64, _i64, _p, _i, _p, _p]),
+    "mfish_log3d_f32": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _d, _p, _p]),
+    "mfish_nms_compact_f32": (_i, [_p, _i64, _i64, _i64, _i64, _f, _p, _p, _p, _i64, _p]),
+    "mfish_rank_prune": (_i, [_p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p, _p, _p]),
+    "mfish_overlap_pairs": (_i, [_p, _i64, _i64, _i64, _i64, _i64, _p, _p, _p, _i64, _p]),
+    "mfish_masked_quantile_f32": (_i, [_p, _p, _i64, _d, _p, _p, _p, _p]),
+    "mfish_blur_at_points": (_i, [_p, _i64, _i64, _i64, _p, _i64, _p, _i, _p, _i, _p, _i, _i, _p, _p, _p]),
+    "mfish_gather_f32": (_i, [_p, _i64, _i64, _i64, _p, _i64, _p, _p]),
+    "mfish_gather_u8": (_i, [_p, _i64, _i64, _i64, _p, _i64, _p, _p]),
+    "mfish_plane_sums_f32": (_i, [_p, _p, _i64, _i64, _i64, _p, _p, _p]),
+    "mfish_scale_planes_f32": (_i, [_p, _p, _i64, _i64, _i64, _p, _p]),
+    "mfish_edt_workspace_bytes": (_i64, [_i64, _i64, _i64]),
+    "mfish_edt3d_u8": (_i, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p]),
+    "mfish_edt_inplane_u8": (_i, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p]),
+    "mfish_edt_zpass": (_i, [_p, _i, _i64, _i64, _i64, _p, _p, _p, _p, _p]),
+    "mfish_export_f64": (_i, [_p, _i64, _i64, _i64, _i, _p, _p]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: the CUDA extension is not built and this package has no CPU "
+            "fallback.  Run `python __graft_entry__.py build` (nvcc, sm_100a)."
+        )
+    handle = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(handle, name)  # AttributeError if the .so is stale: loud by design
+        fn.restype = res
+        fn.argtypes = args
+    ver = handle.mfish_abi_version()
+    if ver != ABI_VERSION:
+        raise RuntimeError(f"libmfish_sm100 ABI {ver} != expected {ABI_VERSION}: rebuild the extension")
+    _lib = handle
+    return _lib
+
+
+def check(code):
+    if code != OK:
+        raise MfishError(code, lib().mfish_last_error().decode("utf-8", "replace"))
+
+
+def launch_count() -> int:
+    return int(lib().mfish_launch_count())
+
+
+def darray(values):
+    """float64 host array argument (kept alive by the caller for the call's duration)."""
+    arr = (C.c_double * len(values))(*[float(v) for v in values])
+    return arr
+
+
+def i64array(values):
+    return (C.c_int64 * len(values))(*[int(v) for v in values])

@@ -1,0 +1,113 @@
+// Shared helpers for libmfish_sm100 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+#include <vector>
+
+#include "../../include/mfish.h"
+
+namespace mfish {
+
+void set_error(const char* fmt, ...);
+
+inline int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return MFISH_ERR_CUDA;
+  }
+  return MFISH_OK;
+}
+
+#define MFISH_REQUIRE(cond, ...)            \
+  do {                                      \
+    if (!(cond)) {                          \
+      mfish::set_error(__VA_ARGS__);        \
+      return MFISH_ERR_INVALID;             \
+    }                                       \
+  } while (0)
+
+#define MFISH_CUDA(call)                                              \
+  do {                                                                \
+    cudaError_t e__ = (call);                                         \
+    if (e__ != cudaSuccess) {                                         \
+      mfish::set_error("%s: %s", #call, cudaGetErrorString(e__));     \
+      return MFISH_ERR_CUDA;                                          \
+    }                                                                 \
+  } while (0)
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+__device__ __forceinline__ bool aligned16_dev(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// Number of SMs on the current device (cached).
+int num_sms();
+// launch accounting (mfish_launch_count)
+void count_launch(int k);
+
+// ---- device helpers -------------------------------------------------------
+
+// Monotone float <-> uint32 key (total order, -0 < +0, NaNs at the ends).
+__host__ __device__ __forceinline__ uint32_t f32_to_key(float f) {
+#ifdef __CUDA_ARCH__
+  uint32_t u = __float_as_uint(f);
+#else
+  uint32_t u;
+  memcpy(&u, &f, 4);
+#endif
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float key_to_f32(uint32_t k) {
+  uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(u);
+#else
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+#endif
+}
+
+// Boundary extension of an index into [0, n): MFISH_BOUNDARY_REFLECT is
+// scipy 'reflect' (d c b a | a b c d | d c b a, period 2n), NEAREST clamps.
+template <int BMODE>
+__device__ __forceinline__ int bmap(int i, int n) {
+  if (BMODE == MFISH_BOUNDARY_NEAREST) {
+    return i < 0 ? 0 : (i >= n ? n - 1 : i);
+  } else {
+    if (i >= 0 && i < n) return i;
+    int p = 2 * n;
+    int m = i % p;
+    if (m < 0) m += p;
+    return m < n ? m : p - 1 - m;
+  }
+}
+
+// Single-fold variant, valid for -n <= i <= 2n-1 (no modulo: used in the hot loops).
+template <int BMODE>
+__device__ __forceinline__ int bmap1(int i, int n) {
+  if (BMODE == MFISH_BOUNDARY_NEAREST) {
+    return min(max(i, 0), n - 1);
+  } else {
+    if (i < 0) i = -i - 1;
+    if (i >= n) i = 2 * n - 1 - i;
+    return i;
+  }
+}
+
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+}  // namespace mfish

@@ -1,0 +1,706 @@
+// Separable 1-D correlation passes (orders 0 and 2 of the sampled Gaussian), the arithmetic
+// behind scipy.ndimage.gaussian_filter / gaussian_laplace as skimage.feature.blob_log and
+// skimage.filters.gaussian drive them (modules/muscle_fish.py:333,357,661).
+//
+// Device layout [z][x][y], y contiguous.
+//  * conv_y_kernel      : contiguous axis.  A 512-voxel row segment + halo is staged in shared
+//                         memory with 128-bit loads; each thread produces 4 consecutive outputs
+//                         from a register window.            R4 + W4 (G) or R4 + W8 (G,D) B/voxel.
+//  * conv_strided_kernel: z or x axis.  One thread per contiguous-axis position walks the strided
+//                         axis with a (2R+1+D)-deep register ring (D planes of load lookahead), so
+//                         every voxel is read once and written once.  8 / 12 / 16 / 12 B/voxel for
+//                         ops G / GD / MID / LAST.
+// Taps live in the kernel parameter block (constant bank) so every FFMA has two register sources.
+#include <algorithm>
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace mfish {
+void count_launch(int k);
+
+template <int R>
+struct Taps {
+  float g[R + 1];
+  float d[R + 1];
+};
+
+struct NormSrc {
+  const float* mm;  // device {min, max} or nullptr
+};
+
+__device__ __forceinline__ void load_norm(const float* mm, float& mn, float& sc, bool& degenerate) {
+  mn = 0.f;
+  sc = 1.f;
+  degenerate = false;
+  if (mm != nullptr) {
+    float lo = __ldg(mm), hi = __ldg(mm + 1);
+    mn = lo;
+    if (hi > lo)
+      sc = (float)(1.0 / ((double)hi - (double)lo));
+    else
+      degenerate = true;
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// contiguous (y) axis
+// --------------------------------------------------------------------------------------------
+constexpr int YSEG = 512;     // outputs per block
+constexpr int YTHREADS = 128;  // 4 outputs per thread
+
+template <int R>
+struct YArgs {
+  const float* in;
+  float* out0;
+  float* out1;
+  int64_t nrows;  // nz*nx
+  int ny;
+  int nseg;
+  int bmode;
+  const float* mm;
+  Taps<R> t;
+};
+
+template <int R, int OP>
+__global__ void __launch_bounds__(YTHREADS) conv_y_kernel(const YArgs<R> a) {
+  constexpr int RP = (R + 3) & ~3;  // halo rounded up to a float4
+  constexpr int NW = 4 + 2 * RP;    // register window per thread
+  __shared__ __align__(16) float buf[YSEG + 2 * RP];
+
+  const int64_t row = blockIdx.x / a.nseg;
+  const int seg0 = (int)(blockIdx.x - row * a.nseg) * YSEG;
+  const int ny = a.ny;
+  const float* __restrict__ src = a.in + row * ny;
+  const int t = threadIdx.x;
+
+  float mn, sc;
+  bool degen;
+  load_norm(a.mm, mn, sc, degen);
+
+  const bool vec = ((ny & 3) == 0) && aligned16_dev(a.in);
+  const bool interior = vec && (seg0 - RP >= 0) && (seg0 + YSEG + RP <= ny);
+  if (interior) {
+    const float4* s4 = reinterpret_cast<const float4*>(src + seg0 - RP);
+    float4* b4 = reinterpret_cast<float4*>(buf);
+    constexpr int N4 = (YSEG + 2 * RP) / 4;
+    for (int j = t; j < N4; j += YTHREADS) {
+      float4 v = __ldg(&s4[j]);
+      v.x = (v.x - mn) * sc;
+      v.y = (v.y - mn) * sc;
+      v.z = (v.z - mn) * sc;
+      v.w = (v.w - mn) * sc;
+      b4[j] = v;
+    }
+  } else {
+    for (int j = t; j < YSEG + 2 * RP; j += YTHREADS) {
+      int y = seg0 - RP + j;
+      float v = 0.f;
+      // positions further than R outside the row are never read by a valid output
+      if (y >= -R && y < ny + R) {
+        int yy = a.bmode == MFISH_BOUNDARY_NEAREST ? bmap<MFISH_BOUNDARY_NEAREST>(y, ny)
+                                                   : bmap<MFISH_BOUNDARY_REFLECT>(y, ny);
+        v = (__ldg(&src[yy]) - mn) * sc;
+      }
+      buf[j] = v;
+    }
+  }
+  __syncthreads();
+
+  const int y0 = seg0 + 4 * t;
+  if (y0 >= ny) return;
+
+  float w[NW];
+  {
+    const float4* b4 = reinterpret_cast<const float4*>(buf + 4 * t);
+#pragma unroll
+    for (int j = 0; j < NW / 4; ++j) {
+      float4 v = b4[j];
+      w[4 * j + 0] = v.x;
+      w[4 * j + 1] = v.y;
+      w[4 * j + 2] = v.z;
+      w[4 * j + 3] = v.w;
+    }
+  }
+  if (degen) {
+#pragma unroll
+    for (int j = 0; j < NW; ++j) w[j] = 1.0f;
+  }
+  float o0[4], o1[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = i + RP;
+    float acc0 = a.t.g[0] * w[c];
+    float acc1 = (OP == MFISH_CONV_GD) ? a.t.d[0] * w[c] : 0.f;
+#pragma unroll
+    for (int k = 1; k <= R; ++k) {
+      float s = w[c - k] + w[c + k];
+      acc0 = fmaf(a.t.g[k], s, acc0);
+      if (OP == MFISH_CONV_GD) acc1 = fmaf(a.t.d[k], s, acc1);
+    }
+    o0[i] = acc0;
+    o1[i] = acc1;
+  }
+  float* __restrict__ d0 = a.out0 + row * ny + y0;
+  const bool vst = vec && aligned16_dev(a.out0) && (OP != MFISH_CONV_GD || aligned16_dev(a.out1));
+  if (vst && y0 + 3 < ny) {
+    *reinterpret_cast<float4*>(d0) = make_float4(o0[0], o0[1], o0[2], o0[3]);
+    if (OP == MFISH_CONV_GD)
+      *reinterpret_cast<float4*>(a.out1 + row * ny + y0) = make_float4(o1[0], o1[1], o1[2], o1[3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (y0 + i < ny) {
+        d0[i] = o0[i];
+        if (OP == MFISH_CONV_GD) a.out1[row * ny + y0 + i] = o1[i];
+      }
+    }
+  }
+}
+
+// runtime-radius fallback (large sigma: segmentation blurs, FMA-bound by construction)
+struct YGenArgs {
+  const float* in;
+  float* out0;
+  float* out1;
+  int64_t nrows;
+  int ny, nseg, bmode, radius, op;
+  const float* mm;
+  const float* taps_g;  // device, radius+1
+  const float* taps_d;
+};
+
+__global__ void __launch_bounds__(YTHREADS) conv_y_generic_kernel(const YGenArgs a) {
+  extern __shared__ float gbuf[];
+  const int R = a.radius;
+  float* tg = gbuf;               // R+1
+  float* td = gbuf + (R + 1);     // R+1
+  float* buf = gbuf + 2 * (R + 1);  // YSEG + 2R
+  const int64_t row = blockIdx.x / a.nseg;
+  const int seg0 = (int)(blockIdx.x - row * a.nseg) * YSEG;
+  const int ny = a.ny;
+  const float* __restrict__ src = a.in + row * ny;
+  float mn, sc;
+  bool degen;
+  load_norm(a.mm, mn, sc, degen);
+  for (int j = threadIdx.x; j <= R; j += YTHREADS) {
+    tg[j] = a.taps_g[j];
+    td[j] = a.op == MFISH_CONV_GD ? a.taps_d[j] : 0.f;
+  }
+  for (int j = threadIdx.x; j < YSEG + 2 * R; j += YTHREADS) {
+    int y = seg0 - R + j;
+    float v = 0.f;
+    if (y < ny + R) {
+      int yy = a.bmode == MFISH_BOUNDARY_NEAREST ? bmap<MFISH_BOUNDARY_NEAREST>(y, ny)
+                                                 : bmap<MFISH_BOUNDARY_REFLECT>(y, ny);
+      v = degen ? 1.0f : (__ldg(&src[yy]) - mn) * sc;
+    }
+    buf[j] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < YSEG; i += YTHREADS) {
+    int y = seg0 + i;
+    if (y >= ny) break;
+    const float* c = buf + i + R;
+    float acc0 = tg[0] * c[0], acc1 = td[0] * c[0];
+    for (int k = 1; k <= R; ++k) {
+      float s = c[-k] + c[k];
+      acc0 = fmaf(tg[k], s, acc0);
+      acc1 = fmaf(td[k], s, acc1);
+    }
+    a.out0[row * ny + y] = acc0;
+    if (a.op == MFISH_CONV_GD) a.out1[row * ny + y] = acc1;
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// strided (z or x) axis: register-ring walker
+// --------------------------------------------------------------------------------------------
+constexpr int LOOKAHEAD = 6;
+constexpr int STHREADS = 128;
+
+template <int R>
+struct SArgs {
+  const float* in0;
+  const float* in1;
+  float* out0;
+  float* out1;
+  int64_t inner;         // contiguous positions per line bundle
+  int64_t outer_stride;  // elements between bundles
+  int stride;            // elements between successive samples along the axis (< 2^31)
+  int L;                 // samples along the axis (>= R)
+  int chunk_len;         // samples handled per blockIdx.z
+  int bmode;
+  float scale;
+  Taps<R> t;
+};
+
+// All four volumes are addressed with one 32-bit element offset (volume < 2^32 elements), so an
+// access costs a single IMAD.WIDE.U32 on top of the load/store.
+__device__ __forceinline__ int bmap1_rt(int i, int n, int bmode) {
+  return bmode == MFISH_BOUNDARY_NEAREST ? bmap1<MFISH_BOUNDARY_NEAREST>(i, n)
+                                         : bmap1<MFISH_BOUNDARY_REFLECT>(i, n);
+}
+
+template <int R, int OP>
+__global__ void __launch_bounds__(STHREADS) conv_strided_kernel(const SArgs<R> a) {
+  constexpr int W = 2 * R + 1;
+  constexpr int RS = W + LOOKAHEAD;
+  constexpr bool TWO_IN = (OP == MFISH_CONV_MID || OP == MFISH_CONV_LAST);
+
+  const int64_t i = (int64_t)blockIdx.x * STHREADS + threadIdx.x;
+  if (i >= a.inner) return;
+  const unsigned i0 = (unsigned)((int64_t)blockIdx.y * a.outer_stride + i);
+  const int kb = blockIdx.z * a.chunk_len;
+  const int ke = min(a.L, kb + a.chunk_len);
+  if (kb >= ke) return;
+  const int L = a.L;
+  const int st = a.stride;
+  const int bmode = a.bmode;
+  const float* __restrict__ p0 = a.in0;
+  const float* __restrict__ p1 = a.in1;
+  float* __restrict__ q0 = a.out0;
+  float* __restrict__ q1 = a.out1;
+  const int klast = ke - 1 + R;  // last plane any output of this chunk needs
+
+  float r0[RS];
+  float r1[TWO_IN ? RS : 1];
+#pragma unroll
+  for (int s = 0; s < RS - 1; ++s) {
+    int k = kb - R + s;
+    r0[s] = 0.f;
+    if (TWO_IN) r1[s] = 0.f;
+    if (k <= klast) {
+      const unsigned on = i0 + (unsigned)(bmap1_rt(k, L, bmode) * st);
+      r0[s] = __ldg(p0 + on);
+      if (TWO_IN) r1[s] = __ldg(p1 + on);
+    }
+  }
+  r0[RS - 1] = 0.f;
+  if (TWO_IN) r1[RS - 1] = 0.f;
+
+  // one unrolled sweep of RS outputs; FAST = every output and every look-ahead plane is interior
+  auto sweep = [&](auto fast_tag, int k0, unsigned off_k) {
+    constexpr bool FAST = decltype(fast_tag)::value;
+    const float* __restrict__ p0n = p0 + (unsigned)((R + LOOKAHEAD) * st);
+    const float* __restrict__ p1n = TWO_IN ? p1 + (unsigned)((R + LOOKAHEAD) * st) : nullptr;
+#pragma unroll
+    for (int u = 0; u < RS; ++u) {
+      const int k = k0 + u;
+      if (FAST || k < ke) {
+        if (FAST) {
+          r0[(u + RS - 1) % RS] = __ldg(p0n + off_k);
+          if (TWO_IN) r1[(u + RS - 1) % RS] = __ldg(p1n + off_k);
+        } else {
+          const int kn = k + R + LOOKAHEAD;
+          if (kn <= klast) {
+            const unsigned on = i0 + (unsigned)(bmap1_rt(kn, L, bmode) * st);
+            r0[(u + RS - 1) % RS] = __ldg(p0 + on);
+            if (TWO_IN) r1[(u + RS - 1) % RS] = __ldg(p1 + on);
+          }
+        }
+        const float c0 = r0[(u + R) % RS];
+        float accG0 = a.t.g[0] * c0;  // G * in0
+        float accD0 = a.t.d[0] * c0;  // D * in0
+        float accG1 = 0.f;            // G * in1
+        if (TWO_IN) accG1 = a.t.g[0] * r1[(u + R) % RS];
+#pragma unroll
+        for (int j = 1; j <= R; ++j) {
+          const float s0 = r0[(u + R - j + RS) % RS] + r0[(u + R + j) % RS];
+          if (OP != MFISH_CONV_LAST) accG0 = fmaf(a.t.g[j], s0, accG0);
+          if (OP != MFISH_CONV_G) accD0 = fmaf(a.t.d[j], s0, accD0);
+          if (TWO_IN) {
+            const float s1 = r1[(u + R - j + RS) % RS] + r1[(u + R + j) % RS];
+            accG1 = fmaf(a.t.g[j], s1, accG1);
+          }
+        }
+        if (OP == MFISH_CONV_G) {
+          q0[off_k] = accG0;
+        } else if (OP == MFISH_CONV_GD) {
+          q0[off_k] = accG0;
+          q1[off_k] = accD0;
+        } else if (OP == MFISH_CONV_MID) {
+          q0[off_k] = accG0;
+          q1[off_k] = accD0 + accG1;
+        } else {
+          q0[off_k] = a.scale * (accD0 + accG1);
+        }
+        off_k += (unsigned)st;
+      }
+    }
+  };
+
+  unsigned off_k = i0 + (unsigned)(kb * st);
+  for (int k0 = kb; k0 < ke; k0 += RS) {
+    const bool fast = (k0 + RS <= ke) && (k0 + RS - 1 + R + LOOKAHEAD < L);
+    if (fast)
+      sweep(std::true_type{}, k0, off_k);
+    else
+      sweep(std::false_type{}, k0, off_k);
+    off_k += (unsigned)(RS * st);
+  }
+}
+
+struct SGenArgs {
+  const float* in0;
+  const float* in1;
+  float* out0;
+  float* out1;
+  int64_t inner, stride, outer_stride;
+  int L, bmode, radius, op;
+  float scale;
+  const float* taps_g;
+  const float* taps_d;
+};
+
+// runtime-radius fallback: direct gather through L1/L2.
+__global__ void __launch_bounds__(STHREADS) conv_strided_generic_kernel(const SGenArgs a) {
+  extern __shared__ float tapbuf[];
+  const int R = a.radius;
+  float* tg = tapbuf;
+  float* td = tapbuf + (R + 1);
+  for (int j = threadIdx.x; j <= R; j += STHREADS) {
+    tg[j] = a.taps_g[j];
+    td[j] = a.taps_d ? a.taps_d[j] : 0.f;
+  }
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * STHREADS + threadIdx.x;
+  if (i >= a.inner) return;
+  const int k = blockIdx.z;
+  const int64_t base = (int64_t)blockIdx.y * a.outer_stride + i;
+  const float* __restrict__ p0 = a.in0 + base;
+  const float* __restrict__ p1 = a.in1 ? a.in1 + base : nullptr;
+  const bool two_in = (a.op == MFISH_CONV_MID || a.op == MFISH_CONV_LAST);
+  float accG0 = 0.f, accD0 = 0.f, accG1 = 0.f;
+  for (int j = -R; j <= R; ++j) {
+    int kk = a.bmode == MFISH_BOUNDARY_NEAREST ? bmap<MFISH_BOUNDARY_NEAREST>(k + j, a.L)
+                                               : bmap<MFISH_BOUNDARY_REFLECT>(k + j, a.L);
+    int aj = j < 0 ? -j : j;
+    float v0 = __ldg(p0 + (int64_t)kk * a.stride);
+    accG0 = fmaf(tg[aj], v0, accG0);
+    accD0 = fmaf(td[aj], v0, accD0);
+    if (two_in) accG1 = fmaf(tg[aj], __ldg(p1 + (int64_t)kk * a.stride), accG1);
+  }
+  const int64_t o = base + (int64_t)k * a.stride;
+  switch (a.op) {
+    case MFISH_CONV_G: a.out0[o] = accG0; break;
+    case MFISH_CONV_GD: a.out0[o] = accG0; a.out1[o] = accD0; break;
+    case MFISH_CONV_MID: a.out0[o] = accG0; a.out1[o] = accD0 + accG1; break;
+    default: a.out0[o] = a.scale * (accD0 + accG1); break;
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// host-side dispatch
+// --------------------------------------------------------------------------------------------
+template <int R>
+static void fill_taps(Taps<R>& t, const double* g, const double* d, int radius) {
+  for (int k = 0; k <= R; ++k) {
+    t.g[k] = (k <= radius && g) ? (float)g[k] : 0.f;
+    t.d[k] = (k <= radius && d) ? (float)d[k] : 0.f;
+  }
+}
+
+struct PassDesc {
+  const float* in0;
+  const float* in1;
+  float* out0;
+  float* out1;
+  int64_t nz, nx, ny;
+  int axis;
+  const double* g;
+  const double* d;
+  int radius, boundary, op;
+  float scale;
+  const float* mm;
+  cudaStream_t st;
+};
+
+static int upload_taps(const PassDesc& p, float** dg, float** dd) {
+  int n = p.radius + 1;
+  std::vector<float> hg(n), hd(n);
+  for (int k = 0; k < n; ++k) {
+    hg[k] = p.g ? (float)p.g[k] : 0.f;
+    hd[k] = p.d ? (float)p.d[k] : 0.f;
+  }
+  MFISH_CUDA(cudaMallocAsync((void**)dg, 2 * n * sizeof(float), p.st));
+  *dd = *dg + n;
+  MFISH_CUDA(cudaMemcpyAsync(*dg, hg.data(), n * sizeof(float), cudaMemcpyHostToDevice, p.st));
+  MFISH_CUDA(cudaMemcpyAsync(*dd, hd.data(), n * sizeof(float), cudaMemcpyHostToDevice, p.st));
+  // pageable-source async copies return after staging, so the vectors may go out of scope
+  return MFISH_OK;
+}
+
+template <int R>
+static int launch_y(const PassDesc& p) {
+  YArgs<R> a;
+  a.in = p.in0;
+  a.out0 = p.out0;
+  a.out1 = p.out1;
+  a.nrows = p.nz * p.nx;
+  a.ny = (int)p.ny;
+  a.nseg = (int)((p.ny + YSEG - 1) / YSEG);
+  a.bmode = p.boundary;
+  a.mm = p.mm;
+  fill_taps<R>(a.t, p.g, p.d, p.radius);
+  int64_t blocks = a.nrows * a.nseg;
+  MFISH_REQUIRE(blocks < (1ll << 31), "sepconv(y): too many row segments");
+  if (p.op == MFISH_CONV_G)
+    conv_y_kernel<R, MFISH_CONV_G><<<(unsigned)blocks, YTHREADS, 0, p.st>>>(a);
+  else
+    conv_y_kernel<R, MFISH_CONV_GD><<<(unsigned)blocks, YTHREADS, 0, p.st>>>(a);
+  count_launch(1);
+  return check_launch("conv_y");
+}
+
+template <int R>
+static int launch_strided(const PassDesc& p) {
+  SArgs<R> a;
+  a.in0 = p.in0;
+  a.in1 = p.in1;
+  a.out0 = p.out0;
+  a.out1 = p.out1;
+  int64_t nouter;
+  if (p.axis == MFISH_AXIS_Z) {
+    a.inner = p.nx * p.ny;
+    a.stride = (int)(p.nx * p.ny);
+    a.outer_stride = 0;
+    a.L = (int)p.nz;
+    nouter = 1;
+  } else {
+    a.inner = p.ny;
+    a.stride = (int)p.ny;
+    a.outer_stride = p.nx * p.ny;
+    a.L = (int)p.nx;
+    nouter = p.nz;
+  }
+  a.bmode = p.boundary;
+  a.scale = p.scale;
+  fill_taps<R>(a.t, p.g, p.d, p.radius);
+  // split long lines into chunks until the grid holds >= ~4 waves of threads
+  int64_t bx = (a.inner + STHREADS - 1) / STHREADS;
+  int64_t want = (int64_t)num_sms() * 16 * 2;  // blocks
+  int chunks = 1;
+  const int min_chunk = std::max(64, 8 * R);
+  while (bx * nouter * chunks < want && a.L / (chunks * 2) >= min_chunk) chunks *= 2;
+  a.chunk_len = (a.L + chunks - 1) / chunks;
+  MFISH_REQUIRE(bx < (1ll << 31) && nouter < 65536, "sepconv(strided): grid too large");
+  dim3 grid((unsigned)bx, (unsigned)nouter, (unsigned)chunks);
+  switch (p.op) {
+    case MFISH_CONV_G: conv_strided_kernel<R, MFISH_CONV_G><<<grid, STHREADS, 0, p.st>>>(a); break;
+    case MFISH_CONV_GD: conv_strided_kernel<R, MFISH_CONV_GD><<<grid, STHREADS, 0, p.st>>>(a); break;
+    case MFISH_CONV_MID: conv_strided_kernel<R, MFISH_CONV_MID><<<grid, STHREADS, 0, p.st>>>(a); break;
+    default: conv_strided_kernel<R, MFISH_CONV_LAST><<<grid, STHREADS, 0, p.st>>>(a); break;
+  }
+  count_launch(1);
+  return check_launch("conv_strided");
+}
+
+static int launch_generic(const PassDesc& p);
+
+template <int R>
+static int launch_R(const PassDesc& p);
+
+static int launch_generic(const PassDesc& p) {
+  float *dg = nullptr, *dd = nullptr;
+  int rc = upload_taps(p, &dg, &dd);
+  if (rc != MFISH_OK) return rc;
+  if (p.axis == MFISH_AXIS_Y) {
+    YGenArgs a;
+    a.in = p.in0;
+    a.out0 = p.out0;
+    a.out1 = p.out1;
+    a.nrows = p.nz * p.nx;
+    a.ny = (int)p.ny;
+    a.nseg = (int)((p.ny + YSEG - 1) / YSEG);
+    a.bmode = p.boundary;
+    a.radius = p.radius;
+    a.op = p.op;
+    a.mm = p.mm;
+    a.taps_g = dg;
+    a.taps_d = dd;
+    int64_t blocks = a.nrows * a.nseg;
+    size_t smem = (size_t)(2 * (p.radius + 1) + YSEG + 2 * p.radius) * sizeof(float);
+    conv_y_generic_kernel<<<(unsigned)blocks, YTHREADS, smem, p.st>>>(a);
+  } else {
+    SGenArgs a;
+    a.in0 = p.in0;
+    a.in1 = p.in1;
+    a.out0 = p.out0;
+    a.out1 = p.out1;
+    int64_t nouter;
+    if (p.axis == MFISH_AXIS_Z) {
+      a.inner = p.nx * p.ny;
+      a.stride = p.nx * p.ny;
+      a.outer_stride = 0;
+      a.L = (int)p.nz;
+      nouter = 1;
+    } else {
+      a.inner = p.ny;
+      a.stride = p.ny;
+      a.outer_stride = p.nx * p.ny;
+      a.L = (int)p.nx;
+      nouter = p.nz;
+    }
+    a.bmode = p.boundary;
+    a.radius = p.radius;
+    a.op = p.op;
+    a.scale = p.scale;
+    a.taps_g = dg;
+    a.taps_d = dd;
+    int64_t bx = (a.inner + STHREADS - 1) / STHREADS;
+    MFISH_REQUIRE(nouter < 65536 && a.L < 65536, "sepconv(generic): grid too large");
+    dim3 grid((unsigned)bx, (unsigned)nouter, (unsigned)a.L);
+    size_t smem = (size_t)2 * (p.radius + 1) * sizeof(float);
+    conv_strided_generic_kernel<<<grid, STHREADS, smem, p.st>>>(a);
+  }
+  count_launch(1);
+  rc = check_launch("conv_generic");
+  cudaFreeAsync(dg, p.st);
+  return rc;
+}
+
+template <int R>
+static int launch_R(const PassDesc& p) {
+  if (p.axis == MFISH_AXIS_Y) return launch_y<R>(p);
+  // the ring walker folds indices once, so the line must be at least R long and the plane
+  // stride must fit 32 bits; anything else goes through the gather fallback
+  const int64_t L = p.axis == MFISH_AXIS_Z ? p.nz : p.nx;
+  if (L < R || p.nz * p.nx * p.ny >= (1ll << 32)) return launch_generic(p);
+  return launch_strided<R>(p);
+}
+
+int run_pass(const PassDesc& p) {
+  MFISH_REQUIRE(p.in0 && p.out0, "sepconv: null in0/out0");
+  MFISH_REQUIRE(p.nz > 0 && p.nx > 0 && p.ny > 0, "sepconv: empty volume");
+  MFISH_REQUIRE(p.nz < (1 << 30) && p.nx < (1 << 30) && p.ny < (1 << 30), "sepconv: dimension too large");
+  MFISH_REQUIRE(p.radius >= 0 && p.radius <= MFISH_MAX_RADIUS, "sepconv: radius %d out of range", p.radius);
+  MFISH_REQUIRE(p.g != nullptr, "sepconv: taps_g required");
+  MFISH_REQUIRE(p.op >= MFISH_CONV_G && p.op <= MFISH_CONV_LAST, "sepconv: bad op");
+  MFISH_REQUIRE(p.op == MFISH_CONV_G || p.d != nullptr, "sepconv: taps_d required for this op");
+  const bool two_in = (p.op == MFISH_CONV_MID || p.op == MFISH_CONV_LAST);
+  const bool two_out = (p.op == MFISH_CONV_GD || p.op == MFISH_CONV_MID);
+  MFISH_REQUIRE(!two_in || p.in1, "sepconv: in1 required for this op");
+  MFISH_REQUIRE(!two_out || p.out1, "sepconv: out1 required for this op");
+  MFISH_REQUIRE(p.boundary == MFISH_BOUNDARY_REFLECT || p.boundary == MFISH_BOUNDARY_NEAREST,
+                "sepconv: bad boundary mode");
+  MFISH_REQUIRE(p.out0 != p.in0 && p.out0 != p.in1 && (!two_out || (p.out1 != p.in0 && p.out1 != p.in1)),
+                "sepconv: in-place operation is not supported");
+  if (p.axis == MFISH_AXIS_Y) {
+    if (two_in) {
+      set_error("sepconv: ops MID/LAST are implemented for the z and x axes only");
+      return MFISH_ERR_UNSUPPORTED;
+    }
+  } else {
+    MFISH_REQUIRE(p.axis == MFISH_AXIS_Z || p.axis == MFISH_AXIS_X, "sepconv: bad axis");
+    MFISH_REQUIRE(p.mm == nullptr, "sepconv: normalise-on-load is implemented for the y axis only");
+  }
+  const int r = p.radius;
+  if (r <= 1) return launch_R<1>(p);
+  if (r <= 2) return launch_R<2>(p);
+  if (r <= 3) return launch_R<3>(p);
+  if (r <= 4) return launch_R<4>(p);
+  if (r <= 6) return launch_R<6>(p);
+  if (r <= 8) return launch_R<8>(p);
+  if (r <= 10) return launch_R<10>(p);
+  if (r <= 12) return launch_R<12>(p);
+  if (r <= 16) return launch_R<16>(p);
+  return launch_generic(p);
+}
+
+// Host-side taps, identical formula to muscle-fish_b200/taps.py (scipy _gaussian_kernel1d).
+static void host_taps(double sigma, std::vector<double>& g, std::vector<double>& d, int& radius) {
+  radius = (int)(4.0 * sigma + 0.5);
+  g.assign(radius + 1, 0.0);
+  d.assign(radius + 1, 0.0);
+  if (sigma <= 0.0) {
+    radius = 0;
+    g.assign(1, 1.0);
+    d.assign(1, 0.0);
+    return;
+  }
+  double s2 = sigma * sigma, sum = 0.0;
+  std::vector<double> phi(2 * radius + 1);
+  for (int x = -radius; x <= radius; ++x) {
+    phi[x + radius] = exp(-0.5 / s2 * (double)(x * x));
+  }
+  for (double v : phi) sum += v;
+  for (int k = 0; k <= radius; ++k) {
+    double ph = phi[k + radius] / sum;
+    g[k] = ph;
+    d[k] = ((double)(k * k) / (s2 * s2) - 1.0 / s2) * ph;
+  }
+}
+
+}  // namespace mfish
+
+using namespace mfish;
+
+extern "C" int mfish_sepconv_f32(const float* in0_dev, const float* in1_dev, float* out0_dev,
+                                 float* out1_dev, int64_t nz, int64_t nx, int64_t ny, int axis,
+                                 const double* taps_g_host, const double* taps_d_host, int radius,
+                                 int boundary, int op, float out_scale, const float* norm_minmax_dev,
+                                 void* stream) {
+  PassDesc p{in0_dev, in1_dev, out0_dev, out1_dev, nz, nx, ny, axis, taps_g_host, taps_d_host,
+             radius, boundary, op, out_scale, norm_minmax_dev, as_stream(stream)};
+  return run_pass(p);
+}
+
+extern "C" int mfish_gaussian3d_f32(const float* in_dev, float* out_dev, float* tmp_dev, int64_t nz,
+                                    int64_t nx, int64_t ny, const double* sigma_zxy_host, int boundary,
+                                    const float* norm_minmax_dev, void* stream) {
+  MFISH_REQUIRE(in_dev && out_dev && tmp_dev && sigma_zxy_host, "gaussian3d: null pointer");
+  MFISH_REQUIRE(in_dev != out_dev && in_dev != tmp_dev && out_dev != tmp_dev, "gaussian3d: buffers must differ");
+  const double sz = sigma_zxy_host[0], sx = sigma_zxy_host[1], sy = sigma_zxy_host[2];
+  // pass order y, z, x; a zero sigma skips the pass (y is kept when normalising on load)
+  struct P { int axis; double s; };
+  P passes[3];
+  int np = 0;
+  if (sy > 0.0 || norm_minmax_dev) passes[np++] = {MFISH_AXIS_Y, sy};
+  if (sz > 0.0) passes[np++] = {MFISH_AXIS_Z, sz};
+  if (sx > 0.0) passes[np++] = {MFISH_AXIS_X, sx};
+  cudaStream_t st = as_stream(stream);
+  if (np == 0) {
+    MFISH_CUDA(cudaMemcpyAsync(out_dev, in_dev, sizeof(float) * nz * nx * ny, cudaMemcpyDeviceToDevice, st));
+    return MFISH_OK;
+  }
+  const float* src = in_dev;
+  float* dst = (np & 1) ? out_dev : tmp_dev;
+  for (int i = 0; i < np; ++i) {
+    std::vector<double> g, d;
+    int radius;
+    host_taps(passes[i].s, g, d, radius);
+    PassDesc p{src, nullptr, dst, nullptr, nz, nx, ny, passes[i].axis, g.data(), nullptr, radius,
+               boundary, MFISH_CONV_G, 1.0f, (passes[i].axis == MFISH_AXIS_Y) ? norm_minmax_dev : nullptr, st};
+    int rc = run_pass(p);
+    if (rc != MFISH_OK) return rc;
+    src = dst;
+    dst = (dst == out_dev) ? tmp_dev : out_dev;
+  }
+  return MFISH_OK;
+}
+
+extern "C" int mfish_log3d_f32(const float* in_dev, float* out_dev, float* tmp1_dev, float* tmp2_dev,
+                               float* tmp3_dev, int64_t nz, int64_t nx, int64_t ny, double sigma,
+                               const float* norm_minmax_dev, void* stream) {
+  MFISH_REQUIRE(in_dev && out_dev && tmp1_dev && tmp2_dev && tmp3_dev, "log3d: null pointer");
+  MFISH_REQUIRE(sigma > 0.0, "log3d: sigma must be positive");
+  std::vector<double> g, d;
+  int radius;
+  host_taps(sigma, g, d, radius);
+  cudaStream_t st = as_stream(stream);
+  // y: in -> (A = G in, B = D in)
+  PassDesc py{in_dev, nullptr, out_dev, tmp1_dev, nz, nx, ny, MFISH_AXIS_Y, g.data(), d.data(), radius,
+              MFISH_BOUNDARY_REFLECT, MFISH_CONV_GD, 1.0f, norm_minmax_dev, st};
+  int rc = run_pass(py);
+  if (rc != MFISH_OK) return rc;
+  // z: (A, B) -> (C = G A, F = D A + G B)
+  PassDesc pz{out_dev, tmp1_dev, tmp2_dev, tmp3_dev, nz, nx, ny, MFISH_AXIS_Z, g.data(), d.data(), radius,
+              MFISH_BOUNDARY_REFLECT, MFISH_CONV_MID, 1.0f, nullptr, st};
+  rc = run_pass(pz);
+  if (rc != MFISH_OK) return rc;
+  // x: (C, F) -> -sigma^2 (D C + G F)
+  PassDesc px{tmp2_dev, tmp3_dev, out_dev, nullptr, nz, nx, ny, MFISH_AXIS_X, g.data(), d.data(), radius,
+              MFISH_BOUNDARY_REFLECT, MFISH_CONV_LAST, (float)(-(sigma * sigma)), nullptr, st};
+  return run_pass(px);
+}

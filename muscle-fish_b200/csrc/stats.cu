@@ -1,0 +1,387 @@
+// Statistics kernels of find_spots_snrfilter / fix_bleaching (modules/muscle_fish.py:335-400,
+// 441-507) and the point look-ups (mask[spot], distance-map gather).
+//  * masked_quantile: exact order statistics of the masked voxels by a 3-pass (11/11/10 bit)
+//    radix select on the monotone float key: 3 x (R4 + R1) B/voxel, no sort, no host round trip.
+//  * blur_at_points : skimage.filters.gaussian(img, (3,3,0.3)) is only ever read at spot voxels
+//    (muscle_fish.py:362-365,385-388), so it is evaluated sparsely, one warp per spot, in float64.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace mfish {
+
+// ------------------------------------------------------------------------------------------
+// masked radix select
+// ------------------------------------------------------------------------------------------
+constexpr int QBINS = 2048;
+struct QState {
+  uint32_t prefix[2];
+  unsigned long long k[2];
+  unsigned long long n;
+  double gamma;
+  double q;
+};
+struct QWs {
+  uint32_t hist[2][QBINS];
+  QState st;
+};
+static_assert(sizeof(QWs) <= MFISH_QUANTILE_WS_BYTES, "quantile workspace too small");
+
+template <int PASS>
+__device__ __forceinline__ void qsel_digits(uint32_t key, const uint32_t pfx0, const uint32_t pfx1,
+                                            int& d0, int& d1) {
+  // PASS 0: bits 31..21, PASS 1: bits 20..10, PASS 2: bits 9..0
+  if (PASS == 0) {
+    d0 = d1 = (int)(key >> 21);
+  } else if (PASS == 1) {
+    int d = (int)((key >> 10) & 0x7ffu);
+    uint32_t hi = key >> 21;
+    d0 = hi == pfx0 ? d : -1;
+    d1 = hi == pfx1 ? d : -1;
+  } else {
+    int d = (int)(key & 0x3ffu);
+    uint32_t hi = key >> 10;
+    d0 = hi == pfx0 ? d : -1;
+    d1 = hi == pfx1 ? d : -1;
+  }
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(256) qsel_hist_kernel(const float* __restrict__ v,
+                                                        const uint8_t* __restrict__ m, int64_t n, QWs* ws) {
+  __shared__ uint32_t sh[2][QBINS];
+  for (int i = threadIdx.x; i < 2 * QBINS; i += blockDim.x) (&sh[0][0])[i] = 0;
+  __syncthreads();
+  const uint32_t pfx0 = PASS == 0 ? 0u : ws->st.prefix[0];
+  const uint32_t pfx1 = PASS == 0 ? 0u : ws->st.prefix[1];
+  const bool same = (PASS == 0) || (pfx0 == pfx1);
+  // run-length aggregation in registers: neighbouring voxels usually fall in the same bin
+  int run_d0 = -1, run_d1 = -1;
+  uint32_t run_c0 = 0, run_c1 = 0;
+  auto push = [&](float val) {
+    int d0, d1;
+    qsel_digits<PASS>(f32_to_key(val), pfx0, pfx1, d0, d1);
+    if (d0 >= 0) {
+      if (d0 == run_d0) {
+        ++run_c0;
+      } else {
+        if (run_c0) atomicAdd(&sh[0][run_d0], run_c0);
+        run_d0 = d0;
+        run_c0 = 1;
+      }
+    }
+    if (!same && d1 >= 0) {
+      if (d1 == run_d1) {
+        ++run_c1;
+      } else {
+        if (run_c1) atomicAdd(&sh[1][run_d1], run_c1);
+        run_d1 = d1;
+        run_c1 = 1;
+      }
+    }
+  };
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const bool vec = aligned16_dev(v) && ((reinterpret_cast<uintptr_t>(m) & 3u) == 0);
+  const int64_t n4 = vec ? n / 4 : 0;
+  for (int64_t i = tid; i < n4; i += stride) {
+    const uchar4 mk = __ldg(reinterpret_cast<const uchar4*>(m) + i);
+    if (mk.x | mk.y | mk.z | mk.w) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(v) + i);
+      if (mk.x) push(a.x);
+      if (mk.y) push(a.y);
+      if (mk.z) push(a.z);
+      if (mk.w) push(a.w);
+    }
+  }
+  for (int64_t i = n4 * 4 + tid; i < n; i += stride) {
+    if (m[i]) push(v[i]);
+  }
+  if (run_c0) atomicAdd(&sh[0][run_d0], run_c0);
+  if (run_c1) atomicAdd(&sh[1][run_d1], run_c1);
+  __syncthreads();
+  for (int i = threadIdx.x; i < QBINS; i += blockDim.x) {
+    uint32_t c0 = sh[0][i];
+    if (c0) atomicAdd(&ws->hist[0][i], c0);
+    if (!same) {
+      uint32_t c1 = sh[1][i];
+      if (c1) atomicAdd(&ws->hist[1][i], c1);
+    }
+  }
+}
+
+__global__ void qsel_init_kernel(QWs* ws, double q) {
+  for (int i = threadIdx.x; i < 2 * QBINS; i += blockDim.x) (&ws->hist[0][0])[i] = 0;
+  if (threadIdx.x == 0) {
+    ws->st.prefix[0] = ws->st.prefix[1] = 0;
+    ws->st.k[0] = ws->st.k[1] = 0;
+    ws->st.n = 0;
+    ws->st.gamma = 0.0;
+    ws->st.q = q;
+  }
+}
+
+// single thread: locate the bins holding ranks k[0], k[1]; narrow the prefixes; clear hist
+template <int PASS>
+__global__ void qsel_scan_kernel(QWs* ws, float* out, double* info) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  QState& s = ws->st;
+  const int nb = PASS == 2 ? 1024 : QBINS;
+  const bool same = (PASS == 0) || (s.prefix[0] == s.prefix[1]);
+  if (PASS == 0) {
+    unsigned long long n = 0;
+    for (int i = 0; i < nb; ++i) n += ws->hist[0][i];
+    s.n = n;
+    if (n == 0) {
+      out[0] = out[1] = nanf("");
+      info[0] = 0.0;
+      info[1] = 0.0;
+    } else {
+      // numpy 'linear': virtual index = n*q + (alpha + q*(1 - alpha - beta)) - 1, alpha = beta = 1
+      double vi = (double)n * s.q + (1.0 + s.q * (1.0 - 1.0 - 1.0)) - 1.0;
+      double fl = floor(vi);
+      s.gamma = vi - fl;
+      long long k0 = (long long)fl;
+      k0 = k0 < 0 ? 0 : (k0 > (long long)n - 1 ? (long long)n - 1 : k0);
+      long long k1 = k0 + 1 > (long long)n - 1 ? (long long)n - 1 : k0 + 1;
+      s.k[0] = (unsigned long long)k0;
+      s.k[1] = (unsigned long long)k1;
+    }
+  }
+  if (s.n != 0) {
+    for (int j = 0; j < 2; ++j) {
+      const uint32_t* h = ws->hist[(same ? 0 : j)];
+      unsigned long long cum = 0;
+      int b = 0;
+      for (; b < nb; ++b) {
+        unsigned long long c = h[b];
+        if (s.k[j] < cum + c) break;
+        cum += c;
+      }
+      if (b >= nb) b = nb - 1;  // unreachable when counts are consistent
+      s.k[j] -= cum;
+      s.prefix[j] = PASS == 0 ? (uint32_t)b : ((s.prefix[j] << (PASS == 2 ? 10 : 11)) | (uint32_t)b);
+    }
+    if (PASS == 2) {
+      out[0] = key_to_f32(s.prefix[0]);
+      out[1] = key_to_f32(s.prefix[1]);
+      info[0] = s.gamma;
+      info[1] = (double)s.n;
+    }
+  }
+  for (int i = 0; i < 2 * QBINS; ++i) (&ws->hist[0][0])[i] = 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// sparse Gaussian blur at points, float64
+// ------------------------------------------------------------------------------------------
+struct BlurArgs {
+  const float* vol;
+  int nz, nx, ny;
+  const int32_t* pts;  // n x 3 (z, x, y)
+  int64_t npts;
+  const double* tz;
+  const double* tx;
+  const double* ty;
+  int rz, rx, ry;
+  int bmode;
+  const float* mm;
+  double* out;
+};
+
+__global__ void __launch_bounds__(128) blur_points_kernel(const BlurArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t p = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (p >= a.npts) return;
+  const int z = a.pts[3 * p], x = a.pts[3 * p + 1], y = a.pts[3 * p + 2];
+  double mn = 0.0, slope = 1.0;
+  bool degen = false;
+  if (a.mm) {
+    double lo = (double)a.mm[0], hi = (double)a.mm[1];
+    mn = lo;
+    if (hi > lo) slope = 1.0 / (hi - lo); else degen = true;
+  }
+  const int wz = 2 * a.rz + 1, wx = 2 * a.rx + 1, wy = 2 * a.ry + 1;
+  const int total = wz * wx * wy;
+  double acc = 0.0;
+  for (int t = lane; t < total; t += 32) {
+    int dy = t % wy - a.ry;
+    int r = t / wy;
+    int dx = r % wx - a.rx;
+    int dz = r / wx - a.rz;
+    int zz, xx, yy;
+    if (a.bmode == MFISH_BOUNDARY_NEAREST) {
+      zz = bmap<MFISH_BOUNDARY_NEAREST>(z + dz, a.nz);
+      xx = bmap<MFISH_BOUNDARY_NEAREST>(x + dx, a.nx);
+      yy = bmap<MFISH_BOUNDARY_NEAREST>(y + dy, a.ny);
+    } else {
+      zz = bmap<MFISH_BOUNDARY_REFLECT>(z + dz, a.nz);
+      xx = bmap<MFISH_BOUNDARY_REFLECT>(x + dx, a.nx);
+      yy = bmap<MFISH_BOUNDARY_REFLECT>(y + dy, a.ny);
+    }
+    double w = a.tz[abs(dz)] * a.tx[abs(dx)] * a.ty[abs(dy)];
+    double v = (double)__ldg(&a.vol[((int64_t)zz * a.nx + xx) * a.ny + yy]);
+    v = degen ? 1.0 : (v - mn) * slope;
+    acc = fma(w, v, acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) a.out[p] = acc;
+}
+
+// ------------------------------------------------------------------------------------------
+// gathers, plane sums, plane scaling
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void gather_kernel(const T* __restrict__ vol, int nz, int nx, int ny, const int32_t* pts,
+                              int64_t n, T* out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int z = pts[3 * i], x = pts[3 * i + 1], y = pts[3 * i + 2];
+  bool ok = z >= 0 && z < nz && x >= 0 && x < nx && y >= 0 && y < ny;
+  out[i] = ok ? vol[((int64_t)z * nx + x) * ny + y] : T(0);
+}
+
+__global__ void __launch_bounds__(256) plane_sums_kernel(const float* __restrict__ v,
+                                                         const uint8_t* __restrict__ m, int64_t plane,
+                                                         double* sums, double* counts) {
+  const int z = blockIdx.y;
+  const float* pv = v + (int64_t)z * plane;
+  const uint8_t* pm = m ? m + (int64_t)z * plane : nullptr;
+  double s = 0.0;
+  unsigned long long c = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    if (!pm || pm[i]) {
+      s += (double)pv[i];
+      ++c;
+    }
+  }
+  double cd = (double)c;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    cd += __shfl_xor_sync(0xffffffffu, cd, o);
+  }
+  __shared__ double ss[8], sc[8];
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) {
+    ss[w] = s;
+    sc[w] = cd;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ts = 0.0, tc = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) {
+      ts += ss[i];
+      tc += sc[i];
+    }
+    atomicAdd(&sums[z], ts);
+    atomicAdd(&counts[z], tc);
+  }
+}
+
+__global__ void __launch_bounds__(256) scale_planes_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                           int64_t plane, const float* __restrict__ f) {
+  const int z = blockIdx.y;
+  const float fz = f[z];
+  const float* pi = in + (int64_t)z * plane;
+  float* po = out + (int64_t)z * plane;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane;
+       i += (int64_t)gridDim.x * blockDim.x)
+    po[i] = pi[i] * fz;
+}
+
+}  // namespace mfish
+
+using namespace mfish;
+
+extern "C" int mfish_masked_quantile_f32(const float* vol_dev, const uint8_t* mask_dev, int64_t n, double q,
+                                         void* ws_dev, float* out_dev, double* info_dev, void* stream) {
+  MFISH_REQUIRE(vol_dev && mask_dev && ws_dev && out_dev && info_dev, "masked_quantile: null pointer");
+  MFISH_REQUIRE(n > 0 && q >= 0.0 && q <= 1.0, "masked_quantile: bad arguments");
+  cudaStream_t st = as_stream(stream);
+  QWs* ws = reinterpret_cast<QWs*>(ws_dev);
+  int blocks = (int)std::min<int64_t>((n / 4 + 255) / 256 + 1, (int64_t)num_sms() * 8);
+  qsel_init_kernel<<<1, 256, 0, st>>>(ws, q);
+  qsel_hist_kernel<0><<<blocks, 256, 0, st>>>(vol_dev, mask_dev, n, ws);
+  qsel_scan_kernel<0><<<1, 32, 0, st>>>(ws, out_dev, info_dev);
+  qsel_hist_kernel<1><<<blocks, 256, 0, st>>>(vol_dev, mask_dev, n, ws);
+  qsel_scan_kernel<1><<<1, 32, 0, st>>>(ws, out_dev, info_dev);
+  qsel_hist_kernel<2><<<blocks, 256, 0, st>>>(vol_dev, mask_dev, n, ws);
+  qsel_scan_kernel<2><<<1, 32, 0, st>>>(ws, out_dev, info_dev);
+  count_launch(7);
+  return check_launch("masked_quantile");
+}
+
+extern "C" int mfish_blur_at_points(const float* vol_dev, int64_t nz, int64_t nx, int64_t ny,
+                                    const int32_t* pts_dev, int64_t npts, const double* taps_z_host, int rz,
+                                    const double* taps_x_host, int rx, const double* taps_y_host, int ry,
+                                    int boundary, const float* norm_minmax_dev, double* out_dev, void* stream) {
+  MFISH_REQUIRE(npts >= 0, "blur_at_points: negative npts");
+  if (npts == 0) return MFISH_OK;
+  MFISH_REQUIRE(vol_dev && pts_dev && out_dev && taps_z_host && taps_x_host && taps_y_host,
+                "blur_at_points: null pointer");
+  MFISH_REQUIRE(rz >= 0 && rx >= 0 && ry >= 0 && rz <= 4096 && rx <= 4096 && ry <= 4096, "blur_at_points: bad radius");
+  cudaStream_t st = as_stream(stream);
+  int nt = (rz + 1) + (rx + 1) + (ry + 1);
+  std::vector<double> h(nt);
+  std::copy(taps_z_host, taps_z_host + rz + 1, h.begin());
+  std::copy(taps_x_host, taps_x_host + rx + 1, h.begin() + rz + 1);
+  std::copy(taps_y_host, taps_y_host + ry + 1, h.begin() + rz + 1 + rx + 1);
+  double* d = nullptr;
+  MFISH_CUDA(cudaMallocAsync((void**)&d, nt * sizeof(double), st));
+  MFISH_CUDA(cudaMemcpyAsync(d, h.data(), nt * sizeof(double), cudaMemcpyHostToDevice, st));
+  BlurArgs a{vol_dev, (int)nz, (int)nx, (int)ny, pts_dev, npts, d, d + rz + 1, d + rz + 1 + rx + 1,
+             rz, rx, ry, boundary, norm_minmax_dev, out_dev};
+  blur_points_kernel<<<(unsigned)((npts + 3) / 4), 128, 0, st>>>(a);
+  count_launch(1);
+  int rc = check_launch("blur_at_points");
+  cudaFreeAsync(d, st);
+  return rc;
+}
+
+extern "C" int mfish_gather_f32(const float* vol_dev, int64_t nz, int64_t nx, int64_t ny, const int32_t* pts_dev,
+                                int64_t npts, float* out_dev, void* stream) {
+  if (npts == 0) return MFISH_OK;
+  MFISH_REQUIRE(vol_dev && pts_dev && out_dev && npts > 0, "gather: bad arguments");
+  gather_kernel<float><<<(unsigned)((npts + 255) / 256), 256, 0, as_stream(stream)>>>(
+      vol_dev, (int)nz, (int)nx, (int)ny, pts_dev, npts, out_dev);
+  count_launch(1);
+  return check_launch("gather_f32");
+}
+
+extern "C" int mfish_gather_u8(const uint8_t* vol_dev, int64_t nz, int64_t nx, int64_t ny, const int32_t* pts_dev,
+                               int64_t npts, uint8_t* out_dev, void* stream) {
+  if (npts == 0) return MFISH_OK;
+  MFISH_REQUIRE(vol_dev && pts_dev && out_dev && npts > 0, "gather: bad arguments");
+  gather_kernel<uint8_t><<<(unsigned)((npts + 255) / 256), 256, 0, as_stream(stream)>>>(
+      vol_dev, (int)nz, (int)nx, (int)ny, pts_dev, npts, out_dev);
+  count_launch(1);
+  return check_launch("gather_u8");
+}
+
+extern "C" int mfish_plane_sums_f32(const float* vol_dev, const uint8_t* mask_dev, int64_t nz, int64_t nx,
+                                    int64_t ny, double* sums_dev, double* counts_dev, void* stream) {
+  MFISH_REQUIRE(vol_dev && sums_dev && counts_dev && nz > 0 && nx > 0 && ny > 0, "plane_sums: bad arguments");
+  MFISH_REQUIRE(nz < 65536, "plane_sums: too many planes");
+  cudaStream_t st = as_stream(stream);
+  MFISH_CUDA(cudaMemsetAsync(sums_dev, 0, nz * sizeof(double), st));
+  MFISH_CUDA(cudaMemsetAsync(counts_dev, 0, nz * sizeof(double), st));
+  int64_t plane = nx * ny;
+  int bx = (int)std::min<int64_t>((plane + 255) / 256, 64);
+  plane_sums_kernel<<<dim3(bx, (unsigned)nz), 256, 0, st>>>(vol_dev, mask_dev, plane, sums_dev, counts_dev);
+  count_launch(1);
+  return check_launch("plane_sums");
+}
+
+extern "C" int mfish_scale_planes_f32(const float* in_dev, float* out_dev, int64_t nz, int64_t nx, int64_t ny,
+                                      const float* factor_dev, void* stream) {
+  MFISH_REQUIRE(in_dev && out_dev && factor_dev && nz > 0 && nx > 0 && ny > 0, "scale_planes: bad arguments");
+  MFISH_REQUIRE(nz < 65536, "scale_planes: too many planes");
+  int64_t plane = nx * ny;
+  int bx = (int)std::min<int64_t>((plane + 255) / 256, 256);
+  scale_planes_kernel<<<dim3(bx, (unsigned)nz), 256, 0, as_stream(stream)>>>(in_dev, out_dev, plane, factor_dev);
+  count_launch(1);
+  return check_launch("scale_planes");
+}

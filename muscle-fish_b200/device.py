@@ -1,0 +1,426 @@
+"""Device-side pipeline: torch CUDA tensors as buffer carriers, every voxel
+operation a call into ``libmfish_sm100.so`` on torch's current stream.
+
+Device volumes are ``[nz, nx, ny]`` (y contiguous); the reference's logical
+order is ``(x, y, z)`` (``modules/muscle_fish.py:60-71``).  ``Volume`` keeps the
+raw float32 voxels plus the global (min, max) pair; ``su.normalize_image`` is
+never materialised -- the filters map ``(v - min) / (max - min)`` on load.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import taps as T
+
+_DTYPES = {
+    np.dtype(np.uint8): L.U8, np.dtype(np.bool_): L.U8, np.dtype(np.uint16): L.U16,
+    np.dtype(np.int16): L.I16, np.dtype(np.int32): L.I32, np.dtype(np.int64): L.I64,
+    np.dtype(np.float32): L.F32, np.dtype(np.float64): L.F64,
+}
+_TORCH_DTYPES = {
+    torch.uint8: L.U8, torch.bool: L.U8, torch.uint16: L.U16, torch.int16: L.I16, torch.int32: L.I32,
+    torch.int64: L.I64, torch.float32: L.F32, torch.float64: L.F64,
+}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("muscle-fish_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+def host_to_device(arr) -> torch.Tensor:
+    """Copy a host array to the device in its own dtype (pinned sources go async)."""
+    _require_cuda()
+    if isinstance(arr, torch.Tensor):
+        if arr.is_cuda:
+            return arr.contiguous()
+        t = arr.contiguous()
+        if t.dtype == torch.bool:
+            t = t.view(torch.uint8)
+        return t.to("cuda", non_blocking=t.is_pinned())
+    a = np.asarray(arr)
+    if a.dtype == np.bool_:
+        a = a.view(np.uint8)
+    if a.dtype not in _DTYPES:
+        a = a.astype(np.float64)
+    if not a.flags.c_contiguous:
+        a = np.ascontiguousarray(a)
+    if not a.flags.writeable:  # torch.from_numpy warns on read-only arrays
+        a = a.copy()
+    t = torch.from_numpy(a)
+    return t.to("cuda", non_blocking=t.is_pinned())
+
+
+@dataclass
+class Volume:
+    """One channel on the device: raw float32 voxels [nz, nx, ny] + {min, max}."""
+    data: torch.Tensor
+    minmax: torch.Tensor | None  # float32[2] on device, or None (use voxels as they are)
+
+    @property
+    def shape_zxy(self):
+        return tuple(self.data.shape)
+
+    @property
+    def shape_xyz(self):
+        nz, nx, ny = self.data.shape
+        return (nx, ny, nz)
+
+    @property
+    def nvox(self):
+        return self.data.numel()
+
+    def minmax_host(self):
+        lo, hi = self.minmax.tolist()
+        return float(lo), float(hi)
+
+
+def ingest(src, z_first=False, as_mask=False, want_minmax=True, negate=False):
+    """Host/device array in reference order (x,y,z) [or (z,x,y) when ``z_first``]
+    -> device layout.  Returns ``Volume`` (float32 + minmax) or a uint8 mask tensor."""
+    t = host_to_device(src)
+    if t.dim() != 3:
+        raise ValueError("expected a 3-D volume, got shape %r" % (tuple(t.shape),))
+    if t.dtype == torch.bool:
+        t = t.view(torch.uint8)
+    if t.dtype not in _TORCH_DTYPES:
+        raise TypeError(f"unsupported dtype {t.dtype}")
+    if z_first:
+        nz, nx, ny = t.shape
+        layout = L.LAYOUT_ZXY
+    else:
+        nx, ny, nz = t.shape
+        layout = L.LAYOUT_XYZ
+    if as_mask:
+        out = torch.empty((nz, nx, ny), dtype=torch.uint8, device=t.device)
+        L.check(L.lib().mfish_ingest(t.data_ptr(), _TORCH_DTYPES[t.dtype], layout, nx, ny, nz, out.data_ptr(),
+                                     L.DST_ISZERO if negate else L.DST_NONZERO, None, _stream()))
+        return out
+    out = torch.empty((nz, nx, ny), dtype=torch.float32, device=t.device)
+    mm = torch.empty(2, dtype=torch.float32, device=t.device) if want_minmax else None
+    L.check(L.lib().mfish_ingest(t.data_ptr(), _TORCH_DTYPES[t.dtype], layout, nx, ny, nz, out.data_ptr(),
+                                 L.DST_F32, mm.data_ptr() if mm is not None else None, _stream()))
+    return Volume(out, mm)
+
+
+def minmax(vol: torch.Tensor) -> torch.Tensor:
+    mm = torch.empty(2, dtype=torch.float32, device=vol.device)
+    L.check(L.lib().mfish_minmax_f32(vol.data_ptr(), vol.numel(), mm.data_ptr(), _stream()))
+    return mm
+
+
+def normalize_f64(src: torch.Tensor, vmin=0.0, vmax=1.0) -> torch.Tensor:
+    """np.interp(src, (min, max), (vmin, vmax)) as float64, same element order."""
+    src = src.contiguous()
+    if src.dtype == torch.bool:
+        src = src.view(torch.uint8)
+    out = torch.empty(src.shape, dtype=torch.float64, device=src.device)
+    ws = torch.empty(2, dtype=torch.int64, device=src.device)
+    L.check(L.lib().mfish_normalize_f64(src.data_ptr(), _TORCH_DTYPES[src.dtype], src.numel(), float(vmin),
+                                        float(vmax), out.data_ptr(), ws.data_ptr(), _stream()))
+    return out
+
+
+def export_f64(vol_zxy: torch.Tensor, z_first=False, out: torch.Tensor | None = None) -> torch.Tensor:
+    """device [nz,nx,ny] float32 -> float64 in the reference's (x,y,z) order (or (z,x,y))."""
+    nz, nx, ny = vol_zxy.shape
+    shp = (nz, nx, ny) if z_first else (nx, ny, nz)
+    if out is None:
+        out = torch.empty(shp, dtype=torch.float64, device=vol_zxy.device)
+    L.check(L.lib().mfish_export_f64(vol_zxy.data_ptr(), nx, ny, nz,
+                                     L.LAYOUT_ZXY if z_first else L.LAYOUT_XYZ, out.data_ptr(), _stream()))
+    return out
+
+
+# ------------------------------------------------------------------ filters
+class Workspace:
+    """Scratch volumes reused across calls (keyed by shape) so steady-state steps do not allocate."""
+
+    def __init__(self):
+        self._bufs = {}
+
+    def get(self, key, shape, dtype, device):
+        k = (key, tuple(shape), dtype, str(device))
+        b = self._bufs.get(k)
+        if b is None:
+            b = torch.empty(shape, dtype=dtype, device=device)
+            self._bufs[k] = b
+        return b
+
+    def clear(self):
+        self._bufs.clear()
+
+
+WS = Workspace()
+
+
+def log_volume(vol: Volume, sigma: float, out: torch.Tensor | None = None) -> torch.Tensor:
+    """-sigma^2 * gaussian_laplace(normalize(img), sigma): one scale of blob_log's cube."""
+    d = vol.data
+    shp, dev = d.shape, d.device
+    if out is None:
+        out = torch.empty(shp, dtype=torch.float32, device=dev)
+    t1 = WS.get("log1", shp, torch.float32, dev)
+    t2 = WS.get("log2", shp, torch.float32, dev)
+    t3 = WS.get("log3", shp, torch.float32, dev)
+    nz, nx, ny = shp
+    L.check(L.lib().mfish_log3d_f32(d.data_ptr(), out.data_ptr(), t1.data_ptr(), t2.data_ptr(), t3.data_ptr(),
+                                    nz, nx, ny, float(sigma),
+                                    vol.minmax.data_ptr() if vol.minmax is not None else None, _stream()))
+    return out
+
+
+def log_cube(vol: Volume, sigmas) -> torch.Tensor:
+    """[ns, nz, nx, ny] scale-normalised negative LoG cube."""
+    sigmas = [float(s) for s in sigmas]
+    cube = torch.empty((len(sigmas),) + tuple(vol.data.shape), dtype=torch.float32, device=vol.data.device)
+    for k, s in enumerate(sigmas):
+        log_volume(vol, s, out=cube[k])
+    return cube
+
+
+def gaussian(vol: Volume, sigma_xyz, mode="nearest") -> torch.Tensor:
+    """skimage.filters.gaussian(normalize(img), sigma) on the device, [nz,nx,ny] float32."""
+    d = vol.data
+    if np.isscalar(sigma_xyz):
+        sigma_xyz = (sigma_xyz,) * 3
+    sx, sy, sz = [float(s) for s in sigma_xyz]
+    out = torch.empty_like(d)
+    tmp = WS.get("gtmp", d.shape, torch.float32, d.device)
+    nz, nx, ny = d.shape
+    b = {"nearest": L.BOUNDARY_NEAREST, "reflect": L.BOUNDARY_REFLECT}[mode]
+    sig = L.darray([sz, sx, sy])
+    L.check(L.lib().mfish_gaussian3d_f32(d.data_ptr(), out.data_ptr(), tmp.data_ptr(), nz, nx, ny, sig, b,
+                                         vol.minmax.data_ptr() if vol.minmax is not None else None, _stream()))
+    return out
+
+
+# ------------------------------------------------------------ spot detection
+_DEFAULT_CAPACITY = 1 << 20
+
+
+def detect_peaks(cube: torch.Tensor, threshold: float, capacity: int | None = None):
+    """peak_local_max on the cube: returns (raster_idx int64[n], value float32[n]) on the device,
+    unordered.  Raster index is over the reference's (x, y, z, s) cube."""
+    if cube.dim() == 3:
+        cube = cube.unsqueeze(0)
+    ns, nz, nx, ny = cube.shape
+    dev = cube.device
+    thr = max(float(threshold), 0.0)  # threshold_rel = 0.0  =>  max(t, 0 * cube.max()), cube.max() >= 0
+    if float(threshold) < 0:
+        raise ValueError("negative thresholds are not supported (reference zero-pads the scale axis)")
+    cap = int(capacity or max(_DEFAULT_CAPACITY, cube.numel() // 512))
+    count = torch.zeros(1, dtype=torch.int32, device=dev)
+    while True:
+        idx = WS.get("pk_idx", (cap,), torch.int64, dev)
+        val = WS.get("pk_val", (cap,), torch.float32, dev)
+        L.check(L.lib().mfish_nms_compact_f32(cube.data_ptr(), ns, nz, nx, ny, thr, idx.data_ptr(), val.data_ptr(),
+                                              count.data_ptr(), cap, _stream()))
+        n = int(count.item()) & 0xFFFFFFFF
+        if n <= cap:
+            return idx[:n], val[:n]
+        cap = int(n * 1.25) + 1024
+
+
+def rank_prune_equal(idx, val, dims_sxyz, cutoff_sq: int):
+    """Order peaks (descending value, ties by raster index) and apply the equal-sigma prune.
+    Returns (idx_ranked, val_ranked, alive uint8), all on the device."""
+    ns, nx, ny, nz = dims_sxyz
+    n = idx.numel()
+    dev = idx.device
+    idx_o = torch.empty(n, dtype=torch.int64, device=dev)
+    val_o = torch.empty(n, dtype=torch.float32, device=dev)
+    alive = torch.ones(n, dtype=torch.uint8, device=dev)
+    if n:
+        L.check(L.lib().mfish_rank_prune(idx.data_ptr(), val.data_ptr(), n, ns, nz, nx, ny, int(cutoff_sq),
+                                         idx_o.data_ptr(), val_o.data_ptr(), alive.data_ptr(), _stream()))
+    return idx_o, val_o, alive
+
+
+def overlap_pairs(idx_ranked, dims_sxyz, cutoff_sq_matrix):
+    """Candidate (i<j) rank pairs for the unequal-sigma prune.  Returns int32 [npairs, 2] on the host."""
+    ns, nx, ny, nz = dims_sxyz
+    n = idx_ranked.numel()
+    dev = idx_ranked.device
+    cut = L.i64array(np.asarray(cutoff_sq_matrix, dtype=np.int64).reshape(-1).tolist())
+    cap = max(1 << 16, 4 * n)
+    count = torch.zeros(1, dtype=torch.int32, device=dev)
+    while True:
+        pairs = torch.empty((cap, 2), dtype=torch.int32, device=dev)
+        L.check(L.lib().mfish_overlap_pairs(idx_ranked.data_ptr(), n, ns, nz, nx, ny, cut, pairs.data_ptr(),
+                                            count.data_ptr(), cap, _stream()))
+        m = int(count.item()) & 0xFFFFFFFF
+        if m <= cap:
+            return pairs[:m].cpu().numpy()
+        cap = int(m * 1.25) + 1024
+
+
+def decode_raster(idx: np.ndarray, dims_sxyz):
+    """raster index over (x, y, z, s) -> integer arrays x, y, z, s."""
+    ns, nx, ny, nz = dims_sxyz
+    idx = np.asarray(idx, dtype=np.int64)
+    s = idx % ns
+    t = idx // ns
+    z = t % nz
+    t = t // nz
+    y = t % ny
+    x = t // ny
+    return x, y, z, s
+
+
+def prune_unequal_host(n, s_idx, sigmas, pairs):
+    """skimage _prune_blobs over candidate pairs in sorted (i, j) order; every candidate pair
+    already overlaps by more than 0.5 (cut-off table), so only the sigma comparison remains."""
+    sig = np.asarray(sigmas, dtype=np.float64)[s_idx].copy()
+    if len(pairs):
+        order = np.lexsort((pairs[:, 1], pairs[:, 0]))
+        for i, j in pairs[order]:
+            si, sj = sig[i], sig[j]
+            if si == 0.0 and sj == 0.0:
+                continue  # overlap of two dead blobs is 0
+            # a dead blob (sigma 0) still "overlaps" a live one only if it lies inside it; the
+            # reference then zeroes the smaller sigma, i.e. the dead one again: no effect
+            if si == 0.0 or sj == 0.0:
+                continue
+            if si > sj:
+                sig[j] = 0.0
+            else:
+                sig[i] = 0.0
+    return sig
+
+
+def blob_log(vol: Volume, min_sigma, max_sigma, num_sigma, threshold, overlap=0.5, cube=None):
+    """skimage.feature.blob_log on the device.  Returns host float64 array (N, 4) rows
+    [x, y, z, sigma] in peak_local_max order (descending response)."""
+    sigmas = T.sigma_list(min_sigma, max_sigma, num_sigma)
+    if cube is None:
+        cube = log_cube(vol, sigmas)
+    ns = len(sigmas)
+    nz, nx, ny = vol.data.shape
+    dims = (ns, nx, ny, nz)
+    idx, val = detect_peaks(cube, threshold)
+    if idx.numel() == 0:
+        return np.empty((0, 3))
+    if ns == 1:
+        cutoff = T.prune_cutoff_sq(float(sigmas[0]), None, overlap)
+        idx_r, _, alive = rank_prune_equal(idx, val, dims, max(cutoff, 0))
+        keep = alive.bool()
+        idx_h = idx_r[keep].cpu().numpy()
+        x, y, z, s = decode_raster(idx_h, dims)
+        return np.stack([x, y, z, sigmas[s]], axis=1).astype(np.float64)
+    # multi-scale: rank, candidate pairs on the device, sequential sigma rule on the host
+    idx_r, _, _ = rank_prune_equal(idx, val, dims, 0)
+    cut = np.array([[T.prune_cutoff_sq(float(a), float(b), overlap) for b in sigmas] for a in sigmas], dtype=np.int64)
+    pairs = overlap_pairs(idx_r, dims, cut)
+    idx_h = idx_r.cpu().numpy()
+    x, y, z, s = decode_raster(idx_h, dims)
+    sig = prune_unequal_host(len(idx_h), s, sigmas, pairs)
+    keep = sig > 0
+    return np.stack([x[keep], y[keep], z[keep], sig[keep]], axis=1).astype(np.float64)
+
+
+# ------------------------------------------------------------------ lookups
+def _points_zxy(spots_xyz, device):
+    p = np.asarray(spots_xyz)[:, :3].astype(np.int64)
+    zxy = np.ascontiguousarray(np.stack([p[:, 2], p[:, 0], p[:, 1]], axis=1).astype(np.int32))
+    return torch.from_numpy(zxy).to(device)
+
+
+def gather(vol: torch.Tensor, spots_xyz) -> np.ndarray:
+    """vol[x, y, z] at integer spot positions (rows [x, y, z, ...]); float32 or uint8 volume."""
+    n = len(spots_xyz)
+    if n == 0:
+        return np.empty((0,), dtype=np.float32 if vol.dtype == torch.float32 else np.uint8)
+    nz, nx, ny = vol.shape
+    pts = _points_zxy(spots_xyz, vol.device)
+    out = torch.empty(n, dtype=vol.dtype, device=vol.device)
+    fn = L.lib().mfish_gather_f32 if vol.dtype == torch.float32 else L.lib().mfish_gather_u8
+    L.check(fn(vol.data_ptr(), nz, nx, ny, pts.data_ptr(), n, out.data_ptr(), _stream()))
+    return out.cpu().numpy()
+
+
+def blur_at_points(vol: Volume, spots_xyz, sigma_xyz=(3, 3, 0.3), mode="nearest") -> np.ndarray:
+    """skimage.filters.gaussian(normalize(img), sigma)[spot] in float64 at the given spots only."""
+    n = len(spots_xyz)
+    if n == 0:
+        return np.empty((0,), dtype=np.float64)
+    nz, nx, ny = vol.data.shape
+    sx, sy, sz = [float(s) for s in sigma_xyz]
+    tz, rz = T.gaussian_taps(sz)
+    tx, rx = T.gaussian_taps(sx)
+    ty, ry = T.gaussian_taps(sy)
+    pts = _points_zxy(spots_xyz, vol.data.device)
+    out = torch.empty(n, dtype=torch.float64, device=vol.data.device)
+    b = {"nearest": L.BOUNDARY_NEAREST, "reflect": L.BOUNDARY_REFLECT}[mode]
+    L.check(L.lib().mfish_blur_at_points(vol.data.data_ptr(), nz, nx, ny, pts.data_ptr(), n, L.darray(tz), rz,
+                                         L.darray(tx), rx, L.darray(ty), ry, b,
+                                         vol.minmax.data_ptr() if vol.minmax is not None else None,
+                                         out.data_ptr(), _stream()))
+    return out.cpu().numpy()
+
+
+def masked_percentile(vol: Volume, mask: torch.Tensor, q_percent: float) -> float:
+    """np.percentile(normalize(img)[mask], q) finished in float64 on the host from the two
+    order statistics the device selects."""
+    dev = vol.data.device
+    ws = WS.get("qws", (L.QUANTILE_WS_BYTES,), torch.uint8, dev)
+    out = torch.empty(2, dtype=torch.float32, device=dev)
+    info = torch.empty(2, dtype=torch.float64, device=dev)
+    L.check(L.lib().mfish_masked_quantile_f32(vol.data.data_ptr(), mask.data_ptr(), vol.data.numel(),
+                                              float(q_percent) / 100.0, ws.data_ptr(), out.data_ptr(),
+                                              info.data_ptr(), _stream()))
+    v0, v1 = out.tolist()
+    gamma, n = info.tolist()
+    if n == 0:
+        raise IndexError("percentile of an empty selection (mask selects no voxel)")
+    if vol.minmax is not None:
+        lo, hi = vol.minmax_host()
+        a, b = T.interp01(np.array([v0, v1], dtype=np.float64), lo, hi)
+    else:
+        a, b = float(v0), float(v1)
+    return T.lerp(float(a), float(b), float(gamma))
+
+
+def plane_means(vol: torch.Tensor, mask: torch.Tensor | None):
+    """Per-z-plane (masked) sum and count, float64 on the host."""
+    nz, nx, ny = vol.shape
+    sums = torch.empty(nz, dtype=torch.float64, device=vol.device)
+    cnts = torch.empty(nz, dtype=torch.float64, device=vol.device)
+    L.check(L.lib().mfish_plane_sums_f32(vol.data_ptr(), mask.data_ptr() if mask is not None else None, nz, nx, ny,
+                                         sums.data_ptr(), cnts.data_ptr(), _stream()))
+    return sums.cpu().numpy(), cnts.cpu().numpy()
+
+
+def scale_planes(vol: torch.Tensor, factors) -> torch.Tensor:
+    nz, nx, ny = vol.shape
+    f = torch.as_tensor(np.asarray(factors, dtype=np.float32), device=vol.device)
+    out = torch.empty_like(vol)
+    L.check(L.lib().mfish_scale_planes_f32(vol.data_ptr(), out.data_ptr(), nz, nx, ny, f.data_ptr(), _stream()))
+    return out
+
+
+# ---------------------------------------------------------------------- EDT
+def edt(mask_zxy: torch.Tensor, sampling_xyz=None, want_sq=False):
+    """Exact distance to the nearest ZERO voxel of ``mask_zxy`` (uint8 [nz,nx,ny]).
+    Returns float32 distances [nz,nx,ny] (and int32 squared voxel distances when ``want_sq``)."""
+    nz, nx, ny = mask_zxy.shape
+    dev = mask_zxy.device
+    if sampling_xyz is None:
+        sampling_xyz = (1.0, 1.0, 1.0)
+    sx, sy, sz = [float(s) for s in sampling_xyz]
+    ws_bytes = int(L.lib().mfish_edt_workspace_bytes(nz, nx, ny))
+    ws = WS.get("edt_ws", (ws_bytes,), torch.uint8, dev)
+    dist = torch.empty((nz, nx, ny), dtype=torch.float32, device=dev)
+    sq = torch.empty((nz, nx, ny), dtype=torch.int32, device=dev) if want_sq else None
+    L.check(L.lib().mfish_edt3d_u8(mask_zxy.data_ptr(), nz, nx, ny, L.darray([sz, sx, sy]), dist.data_ptr(),
+                                   sq.data_ptr() if sq is not None else None, ws.data_ptr(), _stream()))
+    return (dist, sq) if want_sq else dist

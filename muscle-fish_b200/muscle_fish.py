@@ -1,0 +1,125 @@
+"""Drop-in host API for the spot path of ``modules/muscle_fish.py`` (reference paths are
+relative to the upstream repository root).
+
+Same names, argument meaning, return types and error behaviour as the reference:
+
+* ``find_spots``            modules/muscle_fish.py:631-672
+* ``find_spots_snrfilter``  modules/muscle_fish.py:281-402
+* ``fix_bleaching``         modules/muscle_fish.py:405-512
+
+Inputs are host numpy arrays in the reference's (x, y, z) order; results are host float64
+arrays.  All voxel work runs on the GPU through ``device`` (no CPU fallback).  ``draw=True``
+is accepted for signature compatibility and ignored (plotting is outside the hot path).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import device as D
+from . import scope_utils3 as su  # noqa: F401  (reference modules import it the same way)
+
+
+def _prep(img_fish, mask, z_first):
+    vol = D.ingest(img_fish, z_first=z_first)
+    m = None
+    if mask is not None:
+        m = D.ingest(mask, z_first=z_first, as_mask=True)
+        if tuple(m.shape) != tuple(vol.data.shape):
+            raise IndexError("mask and image shapes differ: %r vs %r" % (tuple(m.shape), tuple(vol.data.shape)))
+    return vol, m
+
+
+def _row_stack(rows):
+    # np.row_stack([]) raises "need at least one array to concatenate" (ValueError), which is what
+    # callers of the reference see when no spot survives (modules/muscle_fish.py:341, 402)
+    if len(rows) == 0:
+        raise ValueError("need at least one array to concatenate")
+    return np.vstack(rows)
+
+
+def find_spots(img_fish, sigma=1., t_spot=0.025, mask=None):
+    """Find FISH spots with blob_log; optionally keep only spots inside ``mask``.
+    Returns an (N, 4) float64 array of rows [x, y, z, sigma]."""
+    vol, m = _prep(img_fish, mask, False)
+    spots = D.blob_log(vol, sigma, sigma, 1, t_spot)
+    if mask is not None:
+        if len(spots) == 0:
+            return _row_stack([])
+        keep = D.gather(m, spots) != 0
+        return _row_stack(list(spots[keep]))
+    return spots
+
+
+def find_spots_snrfilter(img_fish, snr=None, sigma=1., t_spot=0.025, mask=None, z_first=False, draw=False,
+                         imgprefix='fiber'):
+    """blob_log spots, kept when inside ``mask`` and when their blurred intensity over the
+    fibre baseline exceeds an (automatic) signal-to-noise threshold.
+
+    Returns ``(spots, spot_data)``: (N, 4) float64 rows [x, y, z, sigma] ([z, x, y, sigma] when
+    ``z_first``) and the per-spot table ``[['spot_id','x','y','z','intensity','SNR'], ...]``.
+    """
+    vol, m = _prep(img_fish, mask, z_first)
+    spots = D.blob_log(vol, sigma, sigma, 1, t_spot)
+
+    if mask is not None:
+        if len(spots) == 0:
+            return _row_stack([]), None
+        spots_masked = _row_stack(list(spots[D.gather(m, spots) != 0]))
+    else:
+        spots_masked = spots
+
+    if m is None:
+        # np.logical_not(None) masks every voxel in the reference, so the percentile below is
+        # taken over an empty selection and fails (modules/muscle_fish.py:355-356)
+        raise IndexError("find_spots_snrfilter needs a mask: percentile of an empty selection")
+    baseline = D.masked_percentile(vol, m, 25)
+    spot_int = D.blur_at_points(vol, spots_masked, (3, 3, 0.3), mode="nearest")
+
+    if snr is None:
+        thresh = np.percentile(spot_int, 90) / (baseline * np.sqrt(10))
+        snr_min = np.sqrt(10)
+        snr = thresh if thresh > snr_min else snr_min
+
+    print('SNR threshold = ' + str(snr))
+
+    spots_filtered = []
+    spot_data = [['spot_id', 'x', 'y', 'z', 'intensity', 'SNR']]
+    for c, spot in enumerate(spots_masked):
+        intensity = spot_int[c]
+        if intensity / baseline > snr:
+            spots_filtered.append(spot[[2, 0, 1, 3]] if z_first else spot)
+        spot_data.append([c] + list(spot[0:3]) + [intensity, intensity / baseline])
+    return _row_stack(spots_filtered), spot_data
+
+
+def fix_bleaching(img, second_half=True, mask=None, z_first=False, draw=False, imgprefix='fiber'):
+    """Exponential photobleaching correction along z (per-plane masked means on the GPU,
+    the two-parameter fit on the host, the per-plane rescale on the GPU)."""
+    from scipy import optimize
+
+    def expo_fit(x, A, k):
+        return A * np.exp(k * x)
+
+    img = np.asarray(img)
+    vol = D.ingest(img, z_first=z_first, want_minmax=False)
+    m = D.ingest(mask, z_first=z_first, as_mask=True) if mask is not None else None
+    nz = vol.data.shape[0]
+    start_frame = nz // 2 if second_half else 0
+    sums, cnts = D.plane_means(vol.data, m)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        means = sums / cnts
+    intensities = list(means[start_frame:])
+    total_mean = float(np.sum(D.plane_means(vol.data, None)[0]) / vol.data.numel()) if m is not None \
+        else float(np.sum(sums) / vol.data.numel())
+    try:
+        e_params, _ = optimize.curve_fit(expo_fit, list(range(start_frame, nz)), intensities,
+                                         p0=[total_mean, -0.1])
+    except RuntimeError:
+        print('WARNING: Bleaching correction optimization failed. Continuing without correction...')
+        return img
+    if e_params[1] > 0:
+        print('WARNING: Bleaching correction optimization failed. Continuing without correction...')
+        return img
+    correction = np.array([expo_fit(z, 1, -1. * e_params[1]) for z in range(nz)])
+    out = D.scale_planes(vol.data, correction)
+    return D.export_f64(out, z_first=z_first).cpu().numpy()

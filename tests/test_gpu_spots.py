@@ -1,0 +1,299 @@
+"""GPU parity: peak detection, prune, SNR filter and the drop-in spot API against the oracle.
+
+Bar (BASELINE.json north_star): spot coordinate sets identical except for documented ties at
+the threshold (>= 99.9 % exact match).  Index work (NMS on a given cube, ranking, prune,
+percentile order statistics) is bit exact.
+"""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import match_fraction, spot_set
+
+pytestmark = pytest.mark.gpu
+
+MIN_MATCH = 0.999
+
+
+def _cube_xyzs(cube_t):
+    # device [ns, nz, nx, ny] -> reference (x, y, z, s)
+    return cube_t.permute(2, 3, 1, 0).contiguous().cpu().numpy()
+
+
+def _peaks_gpu(cube_t, thr):
+    from muscle_fish_b200 import device as D
+    ns, nz, nx, ny = cube_t.shape
+    idx, val = D.detect_peaks(cube_t, thr)
+    idx_r, val_r, alive = D.rank_prune_equal(idx, val, (ns, nx, ny, nz), 0)
+    assert bool(alive.all())
+    x, y, z, s = D.decode_raster(idx_r.cpu().numpy(), (ns, nx, ny, nz))
+    return np.stack([x, y, z, s], axis=1), val_r.cpu().numpy()
+
+
+@pytest.mark.parametrize("ns", [1, 3])
+@pytest.mark.parametrize("shape", [(24, 31, 9), (64, 64, 12), (7, 132, 5)])
+def test_nms_exact_on_random_cube(ns, shape):
+    """exact peak set AND order on the same float32 cube, incl. borders (zero padding)"""
+    import torch
+    rng = np.random.default_rng(11 + ns)
+    cube = rng.random(shape + (ns,)).astype(np.float32)
+    ref = oracle.peak_local_max(cube, threshold_abs=0.5)
+    cube_t = torch.from_numpy(np.ascontiguousarray(cube.transpose(3, 2, 0, 1))).cuda()
+    got, vals = _peaks_gpu(cube_t, 0.5)
+    np.testing.assert_array_equal(got, ref)
+    np.testing.assert_array_equal(vals, cube[tuple(ref.T)])
+
+
+def test_nms_plateau_ties_are_all_kept():
+    """quantised cube: plateaus produce ties; every tied voxel is a peak (documented ties)"""
+    import torch
+    rng = np.random.default_rng(12)
+    cube = (rng.integers(0, 6, size=(40, 40, 10, 1)) / 5.0).astype(np.float32)
+    ref = oracle.peak_local_max(cube, threshold_abs=0.1)
+    cube_t = torch.from_numpy(np.ascontiguousarray(cube.transpose(3, 2, 0, 1))).cuda()
+    got, _ = _peaks_gpu(cube_t, 0.1)
+    assert len(ref) > 100
+    np.testing.assert_array_equal(got, ref)
+
+
+def test_nms_threshold_is_strict_and_capacity_grows():
+    import torch
+    from muscle_fish_b200 import device as D
+    cube = np.zeros((16, 16, 4, 1), dtype=np.float32)
+    cube[3, 3, 1, 0] = 0.25
+    cube[9, 9, 2, 0] = 0.5
+    cube_t = torch.from_numpy(np.ascontiguousarray(cube.transpose(3, 2, 0, 1))).cuda()
+    got, _ = _peaks_gpu(cube_t, 0.25)  # strict '>': the 0.25 voxel is not a peak
+    np.testing.assert_array_equal(got, [[9, 9, 2, 0]])
+    # capacity smaller than the number of peaks: the wrapper re-runs with a larger buffer
+    rng = np.random.default_rng(13)
+    big = rng.random((1, 8, 64, 64)).astype(np.float32)
+    idx, val = D.detect_peaks(torch.from_numpy(big).cuda(), 0.0, capacity=16)
+    ref = oracle.peak_local_max(big.transpose(2, 3, 1, 0), threshold_abs=0.0)
+    assert idx.numel() == len(ref) > 16
+    with pytest.raises(ValueError):
+        D.detect_peaks(torch.from_numpy(big).cuda(), -0.1)
+
+
+@pytest.mark.parametrize("sigma,cutoff", [(1.0, 1), (2.0, 5), (3.0, 12)])
+def test_prune_cutoff_known_answers(sigma, cutoff):
+    from muscle_fish_b200 import taps as T
+    assert T.prune_cutoff_sq(sigma) == oracle.prune_cutoff_sq(sigma)
+    if sigma in (1.0, 2.0):
+        assert T.prune_cutoff_sq(sigma) == cutoff
+
+
+@pytest.mark.parametrize("sigma", [1.0, 2.0])
+def test_equal_sigma_prune_matches_oracle(sigma):
+    """dense random peaks so that many pairs (and chains) overlap"""
+    import torch
+    from muscle_fish_b200 import device as D, taps as T
+    rng = np.random.default_rng(14)
+    shape = (48, 40, 12)
+    n = 2500
+    flat = rng.choice(np.prod(shape), size=n, replace=False)
+    vals = rng.random(n).astype(np.float32)
+    vals[: n // 10] = vals[0]  # value ties -> order decided by raster index
+    idx = torch.from_numpy(flat.astype(np.int64)).cuda()
+    val = torch.from_numpy(vals).cuda()
+    dims = (1,) + shape
+    idx_r, val_r, alive = D.rank_prune_equal(idx, val, dims, T.prune_cutoff_sq(sigma))
+    x, y, z, _ = D.decode_raster(idx_r.cpu().numpy(), dims)
+    # oracle: same peaks in peak_local_max order
+    order = np.lexsort((flat, -vals.astype(np.float64)))
+    xr, yr, zr = np.unravel_index(flat[order], shape)
+    np.testing.assert_array_equal(np.stack([x, y, z], 1), np.stack([xr, yr, zr], 1))
+    blobs = np.stack([xr, yr, zr, np.full(n, sigma)], axis=1).astype(np.float64)
+    ref_sorted = oracle.prune_blobs(blobs, 0.5, pair_order="sorted")
+    keep = alive.cpu().numpy().astype(bool)
+    got = np.stack([x[keep], y[keep], z[keep], np.full(keep.sum(), sigma)], axis=1)
+    assert len(ref_sorted) < n  # something was pruned
+    np.testing.assert_array_equal(got, ref_sorted)
+
+
+@pytest.mark.parametrize("sigma", [1.0, 2.0])
+def test_equal_sigma_prune_vs_reference_set_order(sigma):
+    """The reference iterates the KD-tree pairs in Python-set order, which makes chains A-B-C
+    order dependent; the device prune uses sorted-pair order.  At the dense-stress density of
+    BASELINE config 5 (1 peak / 839 voxels) both give the same survivors."""
+    import torch
+    from muscle_fish_b200 import device as D, taps as T
+    rng = np.random.default_rng(17)
+    shape = (256, 256, 32)
+    n = 2500
+    flat = rng.choice(np.prod(shape), size=n, replace=False)
+    vals = rng.random(n).astype(np.float32)
+    dims = (1,) + shape
+    idx_r, _, alive = D.rank_prune_equal(torch.from_numpy(flat.astype(np.int64)).cuda(),
+                                         torch.from_numpy(vals).cuda(), dims, T.prune_cutoff_sq(sigma))
+    x, y, z, _ = D.decode_raster(idx_r.cpu().numpy(), dims)
+    keep = alive.cpu().numpy().astype(bool)
+    got = np.stack([x[keep], y[keep], z[keep], np.full(keep.sum(), sigma)], axis=1)
+    blobs = np.stack([x, y, z, np.full(n, sigma)], axis=1).astype(np.float64)
+    ref_set = oracle.prune_blobs(blobs, 0.5, pair_order="set")
+    assert len(ref_set) < n
+    assert match_fraction(got, ref_set) >= MIN_MATCH
+
+
+def test_blob_log_single_scale_vs_oracle():
+    from muscle_fish_b200 import device as D, synth
+    st = synth.make_config("small")
+    img = oracle.normalize_image(st["img"])
+    ref = oracle.blob_log(img, 2.0, 2.0, 1, 0.025, pair_order="sorted")
+    got = D.blob_log(D.ingest(st["img"]), 2.0, 2.0, 1, 0.025)
+    assert len(ref) > 100
+    assert match_fraction(got, ref) >= MIN_MATCH
+    # rows come in descending-response order; float32 vs float64 responses may swap near-equal
+    # neighbours, so the order is compared through the oracle's own (float64) responses
+    cube = oracle.log_cube(img, [2.0])
+    resp = cube[tuple(got[:, :3].astype(int).T) + (0,)]
+    assert np.all(np.diff(resp) <= 1e-5 * resp.max())
+
+
+def test_blob_log_multi_scale_vs_oracle():
+    """config-5 style sigma sweep (modules/scope_utils3.py:403): 80-neighbour NMS + unequal-sigma prune"""
+    from muscle_fish_b200 import ndimage as nd, synth
+    st = synth.make_stack(shape=(128, 96, 24), n_spots=1500, n_nuclei=2, seed=5)
+    img = oracle.normalize_image(st["img"])
+    ref = oracle.blob_log(img, 1.0, 3.0, 5, 0.02, pair_order="sorted")
+    got = nd.blob_log(img, 1.0, 3.0, 5, 0.02)
+    assert len(ref) > 300
+    assert match_fraction(got, ref) >= MIN_MATCH
+    ref_set = oracle.blob_log(img, 1.0, 3.0, 5, 0.02, pair_order="set")
+    assert match_fraction(got, ref_set) >= 0.995
+
+
+def test_blob_log_no_peaks_returns_empty_0x3():
+    from muscle_fish_b200 import ndimage as nd
+    got = nd.blob_log(np.zeros((20, 20, 8)), 1, 1, 1, 0.1)
+    assert got.shape == (0, 3)
+
+
+def test_find_spots_vs_oracle():
+    """modules/muscle_fish.py:631-672 incl. the mask filter"""
+    from muscle_fish_b200 import muscle_fish as mf, synth
+    st = synth.make_config("small")
+    ref = oracle.find_spots(st["img"], sigma=1.0, t_spot=0.02, mask=st["fiber_mask"], pair_order="sorted")
+    got = mf.find_spots(st["img"], sigma=1.0, t_spot=0.02, mask=st["fiber_mask"])
+    assert got.dtype == np.float64 and got.shape[1] == 4
+    assert match_fraction(got, ref) >= MIN_MATCH
+    ref2 = oracle.find_spots(st["img"], sigma=1.0, t_spot=0.02, pair_order="sorted")
+    got2 = mf.find_spots(st["img"], sigma=1.0, t_spot=0.02)
+    assert match_fraction(got2, ref2) >= MIN_MATCH
+    assert len(got2) >= len(got)
+    # int64 0/1 masks, as the scripts build them with np.where(..., 1, 0)
+    got3 = mf.find_spots(st["img"], sigma=1.0, t_spot=0.02, mask=st["fiber_mask"].astype(np.int64))
+    np.testing.assert_array_equal(got3, got)
+
+
+def test_find_spots_raises_valueerror_when_nothing_survives():
+    from muscle_fish_b200 import muscle_fish as mf, synth
+    st = synth.make_config("tiny")
+    empty = np.zeros(st["img"].shape, dtype=np.uint8)
+    with pytest.raises(ValueError):
+        mf.find_spots(st["img"], sigma=1.0, t_spot=0.02, mask=empty)
+    with pytest.raises(ValueError):
+        mf.find_spots_snrfilter(st["img"], sigma=2.0, t_spot=0.025, mask=empty)
+
+
+@pytest.mark.parametrize("cfg", ["tiny", "small"])
+def test_find_spots_snrfilter_vs_oracle(cfg, capsys):
+    """modules/muscle_fish.py:281-402: spots, spot_data table, SNR print"""
+    from muscle_fish_b200 import muscle_fish as mf, synth
+    st = synth.make_config(cfg)
+    ref_spots, ref_data = oracle.find_spots_snrfilter(st["img"], sigma=2.0, t_spot=0.025, mask=st["fiber_mask"],
+                                                      pair_order="sorted")
+    got_spots, got_data = mf.find_spots_snrfilter(st["img"], sigma=2.0, t_spot=0.025, mask=st["fiber_mask"])
+    assert "SNR threshold = " in capsys.readouterr().out
+    assert got_spots.dtype == np.float64
+    assert match_fraction(got_spots, ref_spots) >= MIN_MATCH
+    assert got_data[0] == ref_data[0] == ['spot_id', 'x', 'y', 'z', 'intensity', 'SNR']
+    if len(got_data) == len(ref_data):
+        g = np.array([r[1:] for r in got_data[1:]], dtype=np.float64)
+        r = np.array([r[1:] for r in ref_data[1:]], dtype=np.float64)
+        np.testing.assert_array_equal(g[:, :3], r[:, :3])
+        np.testing.assert_allclose(g[:, 3:], r[:, 3:], rtol=1e-6)  # float32 voxels vs float64
+    # explicit snr and z_first
+    zimg = np.ascontiguousarray(st["img"].transpose(2, 0, 1))
+    zmask = np.ascontiguousarray(st["fiber_mask"].transpose(2, 0, 1))
+    got_z, _ = mf.find_spots_snrfilter(zimg, snr=4.0, sigma=2.0, t_spot=0.025, mask=zmask, z_first=True)
+    ref_z, _ = oracle.find_spots_snrfilter(zimg, snr=4.0, sigma=2.0, t_spot=0.025, mask=zmask, z_first=True,
+                                           pair_order="sorted")
+    assert match_fraction(got_z, ref_z) >= MIN_MATCH
+
+
+def test_find_spots_snrfilter_mask_none_fails_like_reference():
+    from muscle_fish_b200 import muscle_fish as mf, synth
+    st = synth.make_config("tiny")
+    with pytest.raises((IndexError, ValueError)):
+        mf.find_spots_snrfilter(st["img"], sigma=2.0, t_spot=0.025, mask=None)
+
+
+@pytest.mark.parametrize("q", [0, 25, 50, 90, 99.9, 100])
+def test_masked_percentile_exact(q):
+    from muscle_fish_b200 import device as D
+    rng = np.random.default_rng(15)
+    a = (rng.standard_normal((61, 47, 13)) * 50 + 10).astype(np.float32)
+    a[::7] = a[0, 0, 0]  # many duplicates
+    mask = rng.random(a.shape) < 0.4
+    vol = D.ingest(a)
+    m = D.ingest(mask, as_mask=True)
+    got = D.masked_percentile(vol, m, q)
+    ref = np.percentile(oracle.normalize_image(a)[mask], q)
+    assert got == ref
+    with pytest.raises(IndexError):
+        D.masked_percentile(vol, D.ingest(np.zeros(a.shape, np.uint8), as_mask=True), q)
+
+
+def test_blur_at_points_matches_dense_blur():
+    from muscle_fish_b200 import device as D
+    rng = np.random.default_rng(16)
+    a = (rng.random((70, 66, 15)) * 1000).astype(np.float32)
+    pts = np.stack([rng.integers(0, 70, 200), rng.integers(0, 66, 200), rng.integers(0, 15, 200)], 1)
+    pts[:8] = [[0, 0, 0], [69, 65, 14], [0, 65, 0], [69, 0, 14], [1, 1, 1], [68, 64, 13], [0, 30, 7], [35, 0, 0]]
+    ref = oracle.gaussian(oracle.normalize_image(a), (3, 3, 0.3))[tuple(pts.T)]
+    got = D.blur_at_points(D.ingest(a), pts.astype(np.float64), (3, 3, 0.3))
+    np.testing.assert_allclose(got, ref, rtol=1e-12, atol=1e-15)
+
+
+def test_fix_bleaching_vs_oracle():
+    """modules/muscle_fish.py:405-512"""
+    from muscle_fish_b200 import muscle_fish as mf, synth
+    st = synth.make_config("small")
+    img = st["img"].astype(np.float64)
+    decay = np.exp(-0.03 * np.arange(img.shape[2]))
+    img = img * decay
+    for mask in (None, st["fiber_mask"]):
+        ref = oracle.fix_bleaching(img, mask=mask)
+        got = mf.fix_bleaching(img, mask=mask)
+        assert got.dtype == np.float64 and got.shape == img.shape
+        np.testing.assert_allclose(got, ref, rtol=2e-6)
+    zimg = np.ascontiguousarray(img.transpose(2, 0, 1))
+    ref = oracle.fix_bleaching(zimg, second_half=False, z_first=True)
+    got = mf.fix_bleaching(zimg, second_half=False, z_first=True)
+    np.testing.assert_allclose(got, ref, rtol=2e-6)
+    # brightening stack: k > 0 -> returned unchanged
+    up = st["img"].astype(np.float64) * np.exp(0.02 * np.arange(img.shape[2]))
+    np.testing.assert_array_equal(mf.fix_bleaching(up), up)
+
+
+def test_optimize_threshold_blob_log_counts():
+    """modules/scope_utils3.py:388-422: same spot count per threshold as the oracle"""
+    from muscle_fish_b200 import device as D, synth, taps as T
+    st = synth.make_stack(shape=(96, 80, 20), n_spots=300, n_nuclei=1, seed=21)
+    img = oracle.normalize_image(st["img"])
+    _, ref_counts = None, []
+    vol = D.ingest(img, want_minmax=False)
+    cube = D.log_cube(vol, T.sigma_list(1.0, 2.0, 2))
+    for t in np.linspace(0.01, 0.08, 5):
+        ref_counts.append(len(oracle.blob_log(img, 1.0, 2.0, 2, threshold=t, pair_order="sorted")))
+        got = len(D.blob_log(vol, 1.0, 2.0, 2, t, cube=cube))
+        assert abs(got - ref_counts[-1]) <= max(1, round(0.001 * ref_counts[-1]))
+
+
+def test_golden_spots(golden):
+    from muscle_fish_b200 import muscle_fish as mf
+    got = mf.find_spots(golden["img"], sigma=2.0, t_spot=0.025)
+    assert match_fraction(got, golden["spots_s2"]) >= MIN_MATCH
+    got_f, _ = mf.find_spots_snrfilter(golden["img"], sigma=2.0, t_spot=0.025, mask=golden["fiber_mask"])
+    assert match_fraction(got_f, golden["spots_snr_s2"]) >= MIN_MATCH
