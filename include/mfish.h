@@ -73,6 +73,10 @@ int mfish_abi_version(void);
 const char* mfish_last_error(void);
 /* number of kernels this library has launched in the calling process */
 int64_t mfish_launch_count(void);
+/* per-kernel CUDA-event timing on the launching stream (bench / roofline reporting):
+ * enable, run, then collect "name calls total_ms" lines (returns bytes needed). */
+void mfish_profile_enable(int on);
+int64_t mfish_profile_collect(char* buf, int64_t cap);
 
 /* ---- ingest / normalisation ------------------------------------------- *
  * replaces the float64 copies made by su.normalize_image

@@ -37,6 +37,8 @@ SIGNATURES = {
     "mfish_abi_version": (_i, []),
     "mfish_last_error": (C.c_char_p, []),
     "mfish_launch_count": (_i64, []),
+    "mfish_profile_enable": (None, [_i]),
+    "mfish_profile_collect": (_i64, [C.c_char_p, _i64]),
     "mfish_ingest": (_i, [_p, _i, _i, _i64, _i64, _i64, _p, _i, _p, _p]),
     "mfish_minmax_f32": (_i, [_p, _i64, _p, _p]),
     "mfish_normalize_f64": (_i, [_p, _i, _i64, _d, _d, _p, _p, _p]),
@@ -91,6 +93,21 @@ def check(code):
 
 def launch_count() -> int:
     return int(lib().mfish_launch_count())
+
+
+def profile_enable(on: bool):
+    lib().mfish_profile_enable(1 if on else 0)
+
+
+def profile_collect():
+    """{kernel name: (calls, total_ms)} for the launches recorded since the last collect."""
+    buf = C.create_string_buffer(1 << 16)
+    lib().mfish_profile_collect(buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, calls, ms = line.split()
+        out[name] = (int(calls), float(ms))
+    return out
 
 
 def darray(values):

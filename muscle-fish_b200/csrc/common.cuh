@@ -49,6 +49,16 @@ int num_sms();
 // launch accounting (mfish_launch_count)
 void count_launch(int k);
 
+// Optional per-kernel timing (mfish_profile_enable / mfish_profile_collect): a scope records a
+// CUDA event pair on the launching stream around the launches made inside it.
+struct ProfScope {
+  const char* name;
+  cudaStream_t st;
+  void* rec;
+  ProfScope(const char* n, cudaStream_t s);
+  ~ProfScope();
+};
+
 // ---- device helpers -------------------------------------------------------
 
 // Monotone float <-> uint32 key (total order, -0 < +0, NaNs at the ends).

@@ -312,6 +312,7 @@ static int launch_env(const TIn* in, void* link, void* out, int32_t* out_sq, int
   int64_t bx = (a.inner + ENV_THREADS - 1) / ENV_THREADS;
   MFISH_REQUIRE(bx < (1ll << 31) && nouter < 65536, "edt: grid too large");
   dim3 grid((unsigned)bx, (unsigned)nouter);
+  ProfScope prof(axis == MFISH_AXIS_Z ? "edt_envelope_z" : "edt_envelope_x", st);
   edt_envelope_kernel<TIn, LinkT, OUT><<<grid, ENV_THREADS, 0, st>>>(a);
   count_launch(1);
   return check_launch("edt_envelope");
@@ -376,6 +377,7 @@ extern "C" int mfish_edt_inplane_u8(const uint8_t* mask_dev, int64_t nz, int64_t
     if (smem > 48 * 1024)
       MFISH_CUDA(cudaFuncSetAttribute(edt_scan_y_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t blocks = std::min<int64_t>((a.nrows + SCAN_WARPS - 1) / SCAN_WARPS, (int64_t)num_sms() * 32);
+    ProfScope prof("edt_scan_y", st);
     edt_scan_y_kernel<<<(unsigned)blocks, SCAN_WARPS * 32, smem, st>>>(a);
     count_launch(1);
     rc = check_launch("edt_scan_y");

@@ -145,6 +145,7 @@ template <typename S>
 static int launch_ingest(const void* src, int layout, int64_t nx, int64_t ny, int64_t nz, void* dst,
                          int dst_kind, uint32_t* mm, cudaStream_t st) {
   const S* s = reinterpret_cast<const S*>(src);
+  ProfScope prof(layout == MFISH_LAYOUT_XYZ ? "ingest_xyz" : "ingest_flat", st);
   if (layout == MFISH_LAYOUT_XYZ) {
     int nyt = (int)((ny + TY - 1) / TY);
     int64_t gx = (int64_t)nyt * nx;
@@ -212,6 +213,7 @@ extern "C" int mfish_minmax_f32(const float* vol_dev, int64_t n, float* minmax_d
   MFISH_REQUIRE(vol_dev && minmax_dev && n > 0, "minmax: bad arguments");
   cudaStream_t st = as_stream(stream);
   uint32_t* mm = reinterpret_cast<uint32_t*>(minmax_dev);
+  ProfScope prof("minmax", st);
   minmax_init_kernel<<<1, 1, 0, st>>>(mm);
   int blocks = (int)std::min<int64_t>((n / 4 + 255) / 256 + 1, (int64_t)num_sms() * 8);
   minmax_kernel<<<blocks, 256, 0, st>>>(vol_dev, n, mm);

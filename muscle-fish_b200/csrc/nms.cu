@@ -298,6 +298,7 @@ extern "C" int mfish_nms_compact_f32(const float* cube_dev, int64_t ns, int64_t 
   NmsArgs a{cube_dev, (int)ns, (int)nz, (int)nx, (int)ny, threshold, out_idx_dev, out_val_dev, count_dev, capacity};
   int64_t total = ns * nz * nx * ((ny + 3) / 4);
   int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 16);
+  ProfScope prof("nms_compact", st);
   nms_compact_kernel<<<blocks, 256, 0, st>>>(a);
   count_launch(1);
   return check_launch("nms_compact");
@@ -311,6 +312,7 @@ extern "C" int mfish_rank_prune(const int64_t* idx_dev, const float* val_dev, in
   MFISH_REQUIRE(idx_dev && val_dev && idx_out_dev && val_out_dev && alive_out_dev, "rank_prune: null pointer");
   MFISH_REQUIRE(cutoff_sq < (1 << 20), "rank_prune: cutoff too large");
   cudaStream_t st = as_stream(stream);
+  ProfScope prof("rank_prune", st);
   RankBuffers b;
   int rc = rank_spots(idx_dev, val_dev, n, idx_out_dev, val_out_dev, b, st);
   if (rc == MFISH_OK) {

@@ -445,6 +445,7 @@ static int launch_y(const PassDesc& p) {
   fill_taps<R>(a.t, p.g, p.d, p.radius);
   int64_t blocks = a.nrows * a.nseg;
   MFISH_REQUIRE(blocks < (1ll << 31), "sepconv(y): too many row segments");
+  ProfScope prof(p.op == MFISH_CONV_G ? "conv_y_g" : "conv_y_gd", p.st);
   if (p.op == MFISH_CONV_G)
     conv_y_kernel<R, MFISH_CONV_G><<<(unsigned)blocks, YTHREADS, 0, p.st>>>(a);
   else
@@ -486,6 +487,9 @@ static int launch_strided(const PassDesc& p) {
   a.chunk_len = (a.L + chunks - 1) / chunks;
   MFISH_REQUIRE(bx < (1ll << 31) && nouter < 65536, "sepconv(strided): grid too large");
   dim3 grid((unsigned)bx, (unsigned)nouter, (unsigned)chunks);
+  static const char* const names[2][4] = {{"conv_z_g", "conv_z_gd", "conv_z_mid", "conv_z_last"},
+                                          {"conv_x_g", "conv_x_gd", "conv_x_mid", "conv_x_last"}};
+  ProfScope prof(names[p.axis == MFISH_AXIS_Z ? 0 : 1][p.op], p.st);
   switch (p.op) {
     case MFISH_CONV_G: conv_strided_kernel<R, MFISH_CONV_G><<<grid, STHREADS, 0, p.st>>>(a); break;
     case MFISH_CONV_GD: conv_strided_kernel<R, MFISH_CONV_GD><<<grid, STHREADS, 0, p.st>>>(a); break;
@@ -505,6 +509,7 @@ static int launch_generic(const PassDesc& p) {
   float *dg = nullptr, *dd = nullptr;
   int rc = upload_taps(p, &dg, &dd);
   if (rc != MFISH_OK) return rc;
+  ProfScope prof(p.axis == MFISH_AXIS_Y ? "conv_y_generic" : "conv_strided_generic", p.st);
   if (p.axis == MFISH_AXIS_Y) {
     YGenArgs a;
     a.in = p.in0;

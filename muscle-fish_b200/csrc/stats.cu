@@ -137,8 +137,8 @@ __global__ void qsel_scan_kernel(QWs* ws, float* out, double* info) {
       info[0] = 0.0;
       info[1] = 0.0;
     } else {
-      // numpy 'linear': virtual index = n*q + (alpha + q*(1 - alpha - beta)) - 1, alpha = beta = 1
-      double vi = (double)n * s.q + (1.0 + s.q * (1.0 - 1.0 - 1.0)) - 1.0;
+      // numpy method 'linear': virtual index = (n - 1) * q
+      double vi = (double)(n - 1) * s.q;
       double fl = floor(vi);
       s.gamma = vi - fl;
       long long k0 = (long long)fl;
@@ -303,6 +303,7 @@ extern "C" int mfish_masked_quantile_f32(const float* vol_dev, const uint8_t* ma
   cudaStream_t st = as_stream(stream);
   QWs* ws = reinterpret_cast<QWs*>(ws_dev);
   int blocks = (int)std::min<int64_t>((n / 4 + 255) / 256 + 1, (int64_t)num_sms() * 8);
+  ProfScope prof("masked_quantile_3pass", st);
   qsel_init_kernel<<<1, 256, 0, st>>>(ws, q);
   qsel_hist_kernel<0><<<blocks, 256, 0, st>>>(vol_dev, mask_dev, n, ws);
   qsel_scan_kernel<0><<<1, 32, 0, st>>>(ws, out_dev, info_dev);
@@ -334,6 +335,7 @@ extern "C" int mfish_blur_at_points(const float* vol_dev, int64_t nz, int64_t nx
   MFISH_CUDA(cudaMemcpyAsync(d, h.data(), nt * sizeof(double), cudaMemcpyHostToDevice, st));
   BlurArgs a{vol_dev, (int)nz, (int)nx, (int)ny, pts_dev, npts, d, d + rz + 1, d + rz + 1 + rx + 1,
              rz, rx, ry, boundary, norm_minmax_dev, out_dev};
+  ProfScope prof("blur_at_points", st);
   blur_points_kernel<<<(unsigned)((npts + 3) / 4), 128, 0, st>>>(a);
   count_launch(1);
   int rc = check_launch("blur_at_points");

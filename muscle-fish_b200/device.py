@@ -424,3 +424,67 @@ def edt(mask_zxy: torch.Tensor, sampling_xyz=None, want_sq=False):
     L.check(L.lib().mfish_edt3d_u8(mask_zxy.data_ptr(), nz, nx, ny, L.darray([sz, sx, sy]), dist.data_ptr(),
                                    sq.data_ptr() if sq is not None else None, ws.data_ptr(), _stream()))
     return (dist, sq) if want_sq else dist
+
+
+# ----------------------------------------------------- device-resident pipeline
+class StageTimer:
+    """CUDA-event timing of the individual C-ABI calls of a step, on the launching stream."""
+
+    def __init__(self):
+        self.events = []  # (name, start, end)
+
+    def run(self, name, fn, *a, **k):
+        s = torch.cuda.Event(enable_timing=True)
+        e = torch.cuda.Event(enable_timing=True)
+        s.record()
+        out = fn(*a, **k)
+        e.record()
+        self.events.append((name, s, e))
+        return out
+
+    def totals_ms(self):
+        """{stage: [ms per recorded call]} -- call after a synchronize."""
+        out = {}
+        for name, s, e in self.events:
+            out.setdefault(name, []).append(s.elapsed_time(e))
+        return out
+
+
+class _NoTimer:
+    def run(self, name, fn, *a, **k):
+        return fn(*a, **k)
+
+
+def analyze_stack(img_zxy: torch.Tensor, fiber_zxy: torch.Tensor, notnuc_zxy: torch.Tensor, sigma=2.0,
+                  t_spot=0.025, sampling_xyz=(1.0, 1.0, 1.0), snr=None, timer=None):
+    """The whole hot path on device-resident inputs (general_pipeline/fish_analysis.py:199 +
+    nocodazole/fish_analysis_noco.py:218-221,297-298): normalise -> LoG -> NMS -> prune -> mask ->
+    P25 baseline -> blur at spots -> SNR filter, then EDT of the NOT-nucleus mask and the per-spot
+    distance gather.  ``img_zxy`` float32 [nz,nx,ny]; masks uint8.  Returns a dict of host arrays."""
+    t = timer or _NoTimer()
+    nz, nx, ny = img_zxy.shape
+    dims = (1, nx, ny, nz)
+    mm = t.run("minmax", minmax, img_zxy)
+    vol = Volume(img_zxy, mm)
+    log = WS.get("log_out", img_zxy.shape, torch.float32, img_zxy.device)
+    t.run("log3d", log_volume, vol, sigma, log)
+    idx, val = t.run("nms", detect_peaks, log, t_spot)
+    spots = np.empty((0, 4))
+    if idx.numel():
+        cutoff = max(T.prune_cutoff_sq(float(sigma), None, 0.5), 0)
+        idx_r, _, alive = t.run("rank_prune", rank_prune_equal, idx, val, dims, cutoff)
+        idx_h = idx_r[alive.bool()].cpu().numpy()
+        x, y, z, _ = decode_raster(idx_h, dims)
+        spots = np.stack([x, y, z, np.full(len(x), float(sigma))], axis=1).astype(np.float64)
+    if len(spots):
+        spots = spots[gather(fiber_zxy, spots) != 0]
+    baseline = t.run("quantile", masked_percentile, vol, fiber_zxy, 25)
+    inten = t.run("blur_pts", blur_at_points, vol, spots, (3, 3, 0.3), "nearest")
+    if snr is None and len(spots):
+        thresh = np.percentile(inten, 90) / (baseline * np.sqrt(10))
+        snr = max(thresh, np.sqrt(10))
+    keep = (inten / baseline > snr) if len(spots) else np.zeros(0, bool)
+    dist = t.run("edt", edt, notnuc_zxy, sampling_xyz)
+    spot_dist = gather(dist, spots[keep]).astype(np.float64) if keep.any() else np.empty(0)
+    return {"spots": spots[keep], "spots_masked": spots, "intensity": inten, "baseline": baseline, "snr": snr,
+            "spot_dist": spot_dist, "dist": dist}

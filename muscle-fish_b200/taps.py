@@ -108,9 +108,9 @@ def interp01(x, lo: float, hi: float):
 
 
 def percentile_virtual_index(n: int, q_percent: float):
-    """numpy 'linear' method: virtual index, floor index, gamma."""
+    """numpy 'linear' method (virtual index (n - 1) * q): virtual index, floor index, gamma."""
     q = np.true_divide(q_percent, 100.0)
-    vi = n * q + (1.0 + q * (1.0 - 1.0 - 1.0)) - 1.0
+    vi = (n - 1) * q
     k = math.floor(vi)
     k = min(max(k, 0), n - 1)
     gamma = vi - math.floor(vi)
