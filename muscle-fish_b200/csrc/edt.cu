@@ -18,6 +18,7 @@
 //                           integer < 2^53.  A backward sweep walks the hull and evaluates.
 // Algorithmic bytes per voxel: pass 1 R1+W2, pass 2 R2+W2(link)+W4, pass 3 R4+W2(link)+W4.
 #include <algorithm>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -153,25 +154,40 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) edt_scan_y_kernel(const ScanA
 // ------------------------------------------------------------------------------------------
 enum { EDT_OUT_I32 = 0, EDT_OUT_F32 = 1, EDT_OUT_DIST = 2 };
 
+// uint32 -> double without the (slow) I2F pipe: 2^52 + v is exactly representable
+__device__ __forceinline__ double u2d(uint32_t v) {
+  return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0;
+}
+// non-negative double < 2^31 holding an integer -> int32, without F2I
+__device__ __forceinline__ int32_t d2i_exact(double v) { return __double2loint(v + 4503599627370496.0); }
+
+// raw input value -> (valid, integer payload).  u16 rows hold |dy| (squared here).
 template <typename TIn>
-__device__ __forceinline__ bool edt_load(const TIn* p, double sin, double& F);
+__device__ __forceinline__ bool edt_raw(const TIn* p, uint32_t& v);
 template <>
-__device__ __forceinline__ bool edt_load<uint16_t>(const uint16_t* p, double sin, double& F) {
-  const unsigned v = __ldg(p);
-  F = sin * (double)(v * v);
-  return v != EDT_INF_U16;
+__device__ __forceinline__ bool edt_raw<uint16_t>(const uint16_t* p, uint32_t& v) {
+  const uint32_t d = __ldg(p);
+  v = d * d;
+  return d != EDT_INF_U16;
 }
 template <>
-__device__ __forceinline__ bool edt_load<int32_t>(const int32_t* p, double sin, double& F) {
-  const int32_t v = __ldg(p);
-  F = sin * (double)v;
-  return v != EDT_INF_I32;
+__device__ __forceinline__ bool edt_raw<int32_t>(const int32_t* p, uint32_t& v) {
+  v = (uint32_t)__ldg(p);
+  return v != (uint32_t)EDT_INF_I32;
 }
 template <>
-__device__ __forceinline__ bool edt_load<float>(const float* p, double sin, double& F) {
-  const float v = __ldg(p);
-  F = sin * (double)v;
-  return v < INFINITY;
+__device__ __forceinline__ bool edt_raw<float>(const float* p, uint32_t& v) {
+  const float f = __ldg(p);
+  v = __float_as_uint(f);
+  return f < INFINITY;
+}
+template <typename TIn>
+__device__ __forceinline__ double edt_value(uint32_t v) {
+  return u2d(v);
+}
+template <>
+__device__ __forceinline__ double edt_value<float>(uint32_t v) {
+  return (double)__uint_as_float(v);
 }
 
 template <typename TIn, typename LinkT>
@@ -184,16 +200,19 @@ struct EnvArgs {
   int64_t outer_stride;
   int64_t stride;
   int L;
-  double sin;     // F = sin * input value
-  double w2;      // squared spacing of this axis
-  double inv_w2;  // 1 / w2
+  double sin;        // F = sin * input value            (float64 arithmetic only)
+  double w2;         // squared spacing of this axis     (float64 arithmetic only)
+  double inv_w2;     // 1 / w2
   double out_scale;  // EDT_OUT_DIST: dist = sqrt(val * out_scale)
 };
 
 constexpr int ENV_THREADS = 128;
 constexpr int ENV_BATCH = 8;
 
-template <typename TIn, typename LinkT, int OUT>
+// INT = true : unit weights, every quantity an integer < 2^31 -> hull tests are int32 x int32 ->
+//              int64 products (one IMAD.WIDE each), no floating point at all.
+// INT = false: float64 hull tests (exact whenever the operands are integers < 2^53).
+template <typename TIn, typename LinkT, int OUT, bool INT>
 __global__ void __launch_bounds__(ENV_THREADS) edt_envelope_kernel(const EnvArgs<TIn, LinkT> a) {
   const int64_t i = (int64_t)blockIdx.x * ENV_THREADS + threadIdx.x;
   if (i >= a.inner) return;
@@ -202,88 +221,130 @@ __global__ void __launch_bounds__(ENV_THREADS) edt_envelope_kernel(const EnvArgs
   LinkT* __restrict__ link = a.link + base;
   const int64_t st = a.stride;
   const int L = a.L;
+  using GT = typename std::conditional<INT, int32_t, double>::type;
   const double sin = a.sin, inv_w2 = a.inv_w2, w2 = a.w2;
+  const double sG = sin * inv_w2;  // G(u) = F(u)/w2 + u^2 = sG * raw + u^2
 
-  // G(u) = F(u)/w2 + u^2 ; parabola u at p, divided by w2:  G(u) - 2 p u + p^2
+  auto makeG = [&](uint32_t raw, int u) -> GT {
+    if (INT) return (GT)(int32_t)(raw + (uint32_t)(u * u));
+    return (GT)fma(sG, edt_value<TIn>(raw), u2d((uint32_t)(u * u)));
+  };
+  // site `top` is hidden by (sec, q)  <=>  (Gtop - Gsec)(q - top) >= (Gq - Gtop)(top - sec)
+  auto hidden = [&](GT Gsec, GT Gtop, GT Gq, int sec, int top, int q) -> bool {
+    if (INT) {
+      const long long lhs = (long long)((int32_t)Gtop - (int32_t)Gsec) * (long long)(q - top);
+      const long long rhs = (long long)((int32_t)Gq - (int32_t)Gtop) * (long long)(top - sec);
+      return lhs >= rhs;
+    }
+    const double lhs = ((double)Gtop - (double)Gsec) * u2d((uint32_t)(q - top));
+    const double rhs = ((double)Gq - (double)Gtop) * u2d((uint32_t)(top - sec));
+    return lhs >= rhs;
+  };
+
   int top = EDT_NO_SITE, sec = EDT_NO_SITE;
-  double Gtop = 0.0, Gsec = 0.0;
+  GT Gtop = 0, Gsec = 0;
 
+  const TIn* __restrict__ pin = in;
+  LinkT* __restrict__ plink = link;
   for (int q0 = 0; q0 < L; q0 += ENV_BATCH) {
-    double Fq[ENV_BATCH];
+    uint32_t raw[ENV_BATCH];
     bool ok[ENV_BATCH];
 #pragma unroll
     for (int u = 0; u < ENV_BATCH; ++u) {
       ok[u] = false;
-      Fq[u] = 0.0;
-      if (q0 + u < L) ok[u] = edt_load<TIn>(in + (int64_t)(q0 + u) * st, sin, Fq[u]);
+      raw[u] = 0;
+      if (q0 + u < L) ok[u] = edt_raw<TIn>(pin + u * st, raw[u]);
     }
 #pragma unroll
     for (int u = 0; u < ENV_BATCH; ++u) {
-      if (!ok[u]) continue;
-      const int q = q0 + u;
-      const double Gq = Fq[u] * inv_w2 + (double)q * (double)q;
-      while (sec != EDT_NO_SITE) {
-        // top is hidden by (sec, q)  <=>  s(sec, top) >= s(top, q)
-        const double lhs = (Gtop - Gsec) * (double)(q - top);
-        const double rhs = (Gq - Gtop) * (double)(top - sec);
-        if (lhs < rhs) break;
-        top = sec;
-        Gtop = Gsec;
-        sec = (int)link[(int64_t)top * st];
-        if (sec != EDT_NO_SITE) {
-          double Fs;
-          edt_load<TIn>(in + (int64_t)sec * st, sin, Fs);
-          Gsec = Fs * inv_w2 + (double)sec * (double)sec;
+      if (ok[u]) {
+        const int q = q0 + u;
+        const GT Gq = makeG(raw[u], q);
+        while (sec != EDT_NO_SITE && hidden(Gsec, Gtop, Gq, sec, top, q)) {
+          top = sec;
+          Gtop = Gsec;
+          sec = (int)link[(int64_t)top * st];
+          if (sec != EDT_NO_SITE) {
+            uint32_t r;
+            edt_raw<TIn>(in + (int64_t)sec * st, r);
+            Gsec = makeG(r, sec);
+          }
         }
+        plink[u * st] = (LinkT)top;
+        sec = top;
+        Gsec = Gtop;
+        top = q;
+        Gtop = Gq;
       }
-      link[(int64_t)q * st] = (LinkT)top;
-      sec = top;
-      Gsec = Gtop;
-      top = q;
-      Gtop = Gq;
     }
+    pin += ENV_BATCH * st;
+    plink += ENV_BATCH * st;
   }
 
-  // backward sweep over the hull
+  // backward sweep over the hull: parabola u at p (divided by w2) = G(u) - 2 p u + p^2
   int cur = top, prev = sec;
-  double Gcur = Gtop, Gprev = Gsec;
-  for (int p = L - 1; p >= 0; --p) {
-    const int64_t o = base + (int64_t)p * st;
-    if (cur == EDT_NO_SITE) {
+  GT Gcur = Gtop, Gprev = Gsec;
+  int64_t o = base + (int64_t)(L - 1) * st;
+  if (cur == EDT_NO_SITE) {  // no site on this line
+    for (int p = L - 1; p >= 0; --p, o -= st) {
       if (OUT == EDT_OUT_I32) {
         reinterpret_cast<int32_t*>(a.out)[o] = EDT_INF_I32;
       } else {
         if (a.out) reinterpret_cast<float*>(a.out)[o] = INFINITY;
         if (OUT == EDT_OUT_DIST && a.out_sq) a.out_sq[o] = EDT_INF_I32;
       }
-      continue;
     }
-    const double tp = 2.0 * (double)p;
-    while (prev != EDT_NO_SITE && (Gprev - tp * (double)prev) <= (Gcur - tp * (double)cur)) {
+    return;
+  }
+  for (int p = L - 1; p >= 0; --p, o -= st) {
+    // move down the hull while the site below is at least as good at p
+    while (prev != EDT_NO_SITE) {
+      bool better;
+      if (INT) {
+        // Gprev - 2 p prev <= Gcur - 2 p cur   <=>   Gprev - Gcur <= 2 p (prev - cur)
+        better = (long long)((int32_t)Gprev - (int32_t)Gcur) <= (long long)(2 * p) * (long long)(prev - cur);
+      } else {
+        const double tp = u2d((uint32_t)(2 * p));
+        better = ((double)Gprev - (double)Gcur) <= -tp * u2d((uint32_t)(cur - prev));
+      }
+      if (!better) break;
       cur = prev;
       Gcur = Gprev;
       prev = (int)link[(int64_t)cur * st];
       if (prev != EDT_NO_SITE) {
-        double Fs;
-        edt_load<TIn>(in + (int64_t)prev * st, sin, Fs);
-        Gprev = Fs * inv_w2 + (double)prev * (double)prev;
+        uint32_t r;
+        edt_raw<TIn>(in + (int64_t)prev * st, r);
+        Gprev = makeG(r, prev);
       }
     }
-    const double dp = (double)(p - cur);
-    const double Fcur = (Gcur - (double)cur * (double)cur) * w2;
-    const double val = Fcur + w2 * dp * dp;
-    if (OUT == EDT_OUT_I32) {
-      reinterpret_cast<int32_t*>(a.out)[o] = (int32_t)__double2ll_rn(val);
-    } else if (OUT == EDT_OUT_F32) {
-      reinterpret_cast<float*>(a.out)[o] = (float)val;
+    const int dp = p - cur;
+    if (INT) {
+      // F(cur) + (p - cur)^2 with F(cur) = G(cur) - cur^2
+      const int32_t val = (int32_t)Gcur - cur * cur + dp * dp;
+      if (OUT == EDT_OUT_I32) {
+        reinterpret_cast<int32_t*>(a.out)[o] = val;
+      } else if (OUT == EDT_OUT_F32) {
+        reinterpret_cast<float*>(a.out)[o] = (float)val;
+      } else {
+        if (a.out) reinterpret_cast<float*>(a.out)[o] = (float)sqrt(u2d((uint32_t)val) * a.out_scale);
+        if (a.out_sq) a.out_sq[o] = val;
+      }
     } else {
-      if (a.out) reinterpret_cast<float*>(a.out)[o] = (float)sqrt(val * a.out_scale);
-      if (a.out_sq) a.out_sq[o] = (int32_t)__double2ll_rn(val);
+      const double Fcur = ((double)Gcur - u2d((uint32_t)(cur * cur))) * w2;
+      const double val = fma(w2, u2d((uint32_t)(dp * dp)), Fcur);
+      if (OUT == EDT_OUT_I32) {
+        reinterpret_cast<int32_t*>(a.out)[o] = d2i_exact(val);
+      } else if (OUT == EDT_OUT_F32) {
+        reinterpret_cast<float*>(a.out)[o] = (float)val;
+      } else {
+        if (a.out) reinterpret_cast<float*>(a.out)[o] = (float)sqrt(val * a.out_scale);
+        if (a.out_sq) a.out_sq[o] = d2i_exact(val);
+      }
     }
   }
 }
 
-template <typename TIn, typename LinkT, int OUT>
+template <typename TIn, typename LinkT, int OUT, bool INT>
 static int launch_env(const TIn* in, void* link, void* out, int32_t* out_sq, int axis, int64_t nz, int64_t nx,
                       int64_t ny, double sin, double w2, double out_scale, cudaStream_t st) {
   EnvArgs<TIn, LinkT> a;
@@ -313,18 +374,24 @@ static int launch_env(const TIn* in, void* link, void* out, int32_t* out_sq, int
   MFISH_REQUIRE(bx < (1ll << 31) && nouter < 65536, "edt: grid too large");
   dim3 grid((unsigned)bx, (unsigned)nouter);
   ProfScope prof(axis == MFISH_AXIS_Z ? "edt_envelope_z" : "edt_envelope_x", st);
-  edt_envelope_kernel<TIn, LinkT, OUT><<<grid, ENV_THREADS, 0, st>>>(a);
+  edt_envelope_kernel<TIn, LinkT, OUT, INT><<<grid, ENV_THREADS, 0, st>>>(a);
   count_launch(1);
   return check_launch("edt_envelope");
 }
 
+// int_arith: unit weights and max(F) + L^2 < 2^31 (checked by the caller)
 template <typename TIn, int OUT>
-static int launch_env_link(const TIn* in, void* link, bool link16, void* out, int32_t* out_sq, int axis,
-                           int64_t nz, int64_t nx, int64_t ny, double sin, double w2, double out_scale,
+static int launch_env_link(const TIn* in, void* link, bool link16, bool int_arith, void* out, int32_t* out_sq,
+                           int axis, int64_t nz, int64_t nx, int64_t ny, double sin, double w2, double out_scale,
                            cudaStream_t st) {
+  if (int_arith) {
+    if (link16)
+      return launch_env<TIn, int16_t, OUT, true>(in, link, out, out_sq, axis, nz, nx, ny, sin, w2, out_scale, st);
+    return launch_env<TIn, int32_t, OUT, true>(in, link, out, out_sq, axis, nz, nx, ny, sin, w2, out_scale, st);
+  }
   if (link16)
-    return launch_env<TIn, int16_t, OUT>(in, link, out, out_sq, axis, nz, nx, ny, sin, w2, out_scale, st);
-  return launch_env<TIn, int32_t, OUT>(in, link, out, out_sq, axis, nz, nx, ny, sin, w2, out_scale, st);
+    return launch_env<TIn, int16_t, OUT, false>(in, link, out, out_sq, axis, nz, nx, ny, sin, w2, out_scale, st);
+  return launch_env<TIn, int32_t, OUT, false>(in, link, out, out_sq, axis, nz, nx, ny, sin, w2, out_scale, st);
 }
 
 static inline int64_t align256(int64_t v) { return (v + 255) & ~int64_t(255); }
@@ -386,12 +453,14 @@ extern "C" int mfish_edt_inplane_u8(const uint8_t* mask_dev, int64_t nz, int64_t
   const bool link16 = nx <= 32767;
   if (plane_int) {
     *f2_kind_host = MFISH_EDT_F2_I32;
-    return launch_env_link<uint16_t, EDT_OUT_I32>(dy, link, link16, f2_out_dev, nullptr, MFISH_AXIS_X, nz, nx, ny,
-                                                  1.0, 1.0, 1.0, st);
+    // all-integer hull tests need max(F) + L^2 = (ny-1)^2 + nx^2 below 2^31
+    const bool int_arith = (double)(ny - 1) * (ny - 1) + (double)nx * nx < 2147483000.0;
+    return launch_env_link<uint16_t, EDT_OUT_I32>(dy, link, link16, int_arith, f2_out_dev, nullptr, MFISH_AXIS_X, nz,
+                                                  nx, ny, 1.0, 1.0, 1.0, st);
   }
   *f2_kind_host = MFISH_EDT_F2_F32;
-  return launch_env_link<uint16_t, EDT_OUT_F32>(dy, link, link16, f2_out_dev, nullptr, MFISH_AXIS_X, nz, nx, ny,
-                                                wy * wy, wx * wx, 1.0, st);
+  return launch_env_link<uint16_t, EDT_OUT_F32>(dy, link, link16, false, f2_out_dev, nullptr, MFISH_AXIS_X, nz, nx,
+                                                ny, wy * wy, wx * wx, 1.0, st);
 }
 
 // pass 3 along z.  link_ws_dev: nz*nx*ny*4 bytes of scratch.
@@ -419,14 +488,17 @@ extern "C" int mfish_edt_zpass(const void* f2_dev, int f2_kind, int64_t nz, int6
   const bool link16 = nz <= 32767;
   if (f2_kind == MFISH_EDT_F2_I32) {
     const int32_t* f2 = reinterpret_cast<const int32_t*>(f2_dev);
-    if (iso)  // keep integers, scale once at the end: dist = sqrt(sq * w^2)
-      return launch_env_link<int32_t, EDT_OUT_DIST>(f2, link_ws_dev, link16, out_dist_dev, out_sq_dev, MFISH_AXIS_Z,
-                                                    nz, nx, ny, 1.0, 1.0, wz * wz, st);
-    return launch_env_link<int32_t, EDT_OUT_DIST>(f2, link_ws_dev, link16, out_dist_dev, nullptr, MFISH_AXIS_Z, nz,
-                                                  nx, ny, wx * wx, wz * wz, 1.0, st);
+    if (iso) {  // keep integers, scale once at the end: dist = sqrt(sq * w^2)
+      const double gmax = (double)(nx - 1) * (nx - 1) + (double)(ny - 1) * (ny - 1) + (double)nz * nz;
+      return launch_env_link<int32_t, EDT_OUT_DIST>(f2, link_ws_dev, link16, gmax < 2147483000.0, out_dist_dev,
+                                                    out_sq_dev, MFISH_AXIS_Z, nz, nx, ny, 1.0, 1.0, wz * wz, st);
+    }
+    return launch_env_link<int32_t, EDT_OUT_DIST>(f2, link_ws_dev, link16, false, out_dist_dev, nullptr,
+                                                  MFISH_AXIS_Z, nz, nx, ny, wx * wx, wz * wz, 1.0, st);
   }
-  return launch_env_link<float, EDT_OUT_DIST>(reinterpret_cast<const float*>(f2_dev), link_ws_dev, link16,
-                                              out_dist_dev, nullptr, MFISH_AXIS_Z, nz, nx, ny, 1.0, wz * wz, 1.0, st);
+  return launch_env_link<float, EDT_OUT_DIST>(reinterpret_cast<const float*>(f2_dev), link_ws_dev, link16, false,
+                                              out_dist_dev, nullptr, MFISH_AXIS_Z, nz, nx, ny, 1.0, wz * wz, 1.0,
+                                              st);
 }
 
 extern "C" int mfish_edt3d_u8(const uint8_t* mask_dev, int64_t nz, int64_t nx, int64_t ny,

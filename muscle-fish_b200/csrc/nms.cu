@@ -22,25 +22,43 @@ struct NmsArgs {
   int64_t capacity;
 };
 
+// Neighbour test for one super-threshold voxel.  Out-of-volume neighbours do not exist (the
+// reference pads with 0, which can never exceed v > t >= 0).  Loads are issued in independent
+// batches so that a test costs a few L2 round trips instead of 26 dependent ones:
+//   1. the 4 in-plane / cross-plane face neighbours (x+-1, z+-1)   -> rejects most non-peaks
+//   2. the remaining rows, 3 values per row, 9 rows in flight
 __device__ __forceinline__ bool is_peak(const NmsArgs& a, int s, int z, int x, int y, float v) {
   const int64_t plane = (int64_t)a.nx * a.ny;
   const int64_t vol = plane * a.nz;
+  const float* c = a.cube + s * vol + z * plane + (int64_t)x * a.ny + y;
+  {
+    const float xm = x > 0 ? __ldg(c - a.ny) : 0.f;
+    const float xp = x + 1 < a.nx ? __ldg(c + a.ny) : 0.f;
+    const float zm = z > 0 ? __ldg(c - plane) : 0.f;
+    const float zp = z + 1 < a.nz ? __ldg(c + plane) : 0.f;
+    if (fmaxf(fmaxf(xm, xp), fmaxf(zm, zp)) > v) return false;
+  }
+  const bool ym = y > 0, yp = y + 1 < a.ny;
   for (int ds = -1; ds <= 1; ++ds) {
-    int ss = s + ds;
+    const int ss = s + ds;
     if (ss < 0 || ss >= a.ns) continue;
+    float m = 0.f;
+#pragma unroll
     for (int dz = -1; dz <= 1; ++dz) {
-      int zz = z + dz;
-      if (zz < 0 || zz >= a.nz) continue;
+#pragma unroll
       for (int dx = -1; dx <= 1; ++dx) {
-        int xx = x + dx;
-        if (xx < 0 || xx >= a.nx) continue;
-        const float* row = a.cube + ss * vol + zz * plane + (int64_t)xx * a.ny;
-        int ylo = max(y - 1, 0), yhi = min(y + 1, a.ny - 1);
-        for (int yy = ylo; yy <= yhi; ++yy) {
-          if (__ldg(&row[yy]) > v) return false;
+        const int zz = z + dz, xx = x + dx;
+        if (zz >= 0 && zz < a.nz && xx >= 0 && xx < a.nx) {
+          const float* row = c + ds * vol + dz * plane + dx * (int64_t)a.ny;
+          const float r0 = ym ? __ldg(row - 1) : 0.f;
+          const float r1 = __ldg(row);
+          const float r2 = yp ? __ldg(row + 1) : 0.f;
+          // the centre voxel itself takes part with its own value: harmless (v > v is false)
+          m = fmaxf(m, fmaxf(r0, fmaxf(r1, r2)));
         }
       }
     }
+    if (m > v) return false;
   }
   return true;
 }
@@ -61,37 +79,64 @@ __device__ __forceinline__ void emit_peak(const NmsArgs& a, int s, int z, int x,
   }
 }
 
-// One thread per 4 consecutive y (128-bit load when the row allows it).
+constexpr int NMS_UNROLL = 4;
+
+__device__ __forceinline__ void nms_test4(const NmsArgs& a, int64_t row, int y0, const float v[4]) {
+  const float m = fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3]));
+  if (!(m > a.thr)) return;
+  const int x = (int)(row % a.nx);
+  const int64_t sz = row / a.nx;
+  const int z = (int)(sz % a.nz);
+  const int s = (int)(sz / a.nz);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (v[i] > a.thr && y0 + i < a.ny) {
+      // y neighbours inside the register quad reject most candidates without a load
+      const float l = i > 0 ? v[i - 1] : -INFINITY;
+      const float r = i < 3 ? v[i + 1] : -INFINITY;
+      if (fmaxf(l, r) > v[i]) continue;
+      if (is_peak(a, s, z, x, y0 + i, v[i])) emit_peak(a, s, z, x, y0 + i, v[i]);
+    }
+  }
+}
+
+// One thread per 4 consecutive y (128-bit load when the row allows it), NMS_UNROLL quads in flight.
 __global__ void __launch_bounds__(256) nms_compact_kernel(const NmsArgs a) {
   const int ny4 = (a.ny + 3) >> 2;
   const int64_t nrows = (int64_t)a.ns * a.nz * a.nx;
   const int64_t total = nrows * ny4;
   const bool vec = ((a.ny & 3) == 0) && aligned16_dev(a.cube);
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-       t += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = t / ny4;
-    const int y0 = (int)(t - row * ny4) * 4;
-    const float* p = a.cube + row * a.ny + y0;
-    float v[4];
-    if (vec) {
-      float4 q = __ldg(reinterpret_cast<const float4*>(p));
-      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-    } else {
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (vec) {
+    // ny % 4 == 0: quad t sits at float offset 4 t
+    const float4* __restrict__ c4 = reinterpret_cast<const float4*>(a.cube);
+    for (int64_t t0 = tid; t0 < total; t0 += nthreads * NMS_UNROLL) {
+      float4 q[NMS_UNROLL];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) v[i] = (y0 + i < a.ny) ? __ldg(p + i) : -INFINITY;
-    }
-    const float m = fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3]));
-    if (m > a.thr) {
-      const int x = (int)(row % a.nx);
-      const int64_t sz = row / a.nx;
-      const int z = (int)(sz % a.nz);
-      const int s = (int)(sz / a.nz);
+      for (int u = 0; u < NMS_UNROLL; ++u) {
+        const int64_t t = t0 + u * nthreads;
+        q[u] = t < total ? __ldg(c4 + t) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (v[i] > a.thr && y0 + i < a.ny) {
-          if (is_peak(a, s, z, x, y0 + i, v[i])) emit_peak(a, s, z, x, y0 + i, v[i]);
+      for (int u = 0; u < NMS_UNROLL; ++u) {
+        const int64_t t = t0 + u * nthreads;
+        const float v[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+        if (fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])) > a.thr) {
+          const int64_t row = t / ny4;
+          nms_test4(a, row, (int)(t - row * ny4) * 4, v);
         }
       }
+    }
+  } else {
+    for (int64_t t = tid; t < total; t += nthreads) {
+      const int64_t row = t / ny4;
+      const int y0 = (int)(t - row * ny4) * 4;
+      const float* p = a.cube + row * a.ny + y0;
+      float v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = (y0 + i < a.ny) ? __ldg(p + i) : -INFINITY;
+      nms_test4(a, row, y0, v);
     }
   }
 }
@@ -297,7 +342,7 @@ extern "C" int mfish_nms_compact_f32(const float* cube_dev, int64_t ns, int64_t 
   MFISH_CUDA(cudaMemsetAsync(count_dev, 0, sizeof(uint32_t), st));
   NmsArgs a{cube_dev, (int)ns, (int)nz, (int)nx, (int)ny, threshold, out_idx_dev, out_val_dev, count_dev, capacity};
   int64_t total = ns * nz * nx * ((ny + 3) / 4);
-  int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 16);
+  int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 32);
   ProfScope prof("nms_compact", st);
   nms_compact_kernel<<<blocks, 256, 0, st>>>(a);
   count_launch(1);
