@@ -165,6 +165,14 @@ int mfish_overlap_pairs(const int64_t* idx_ranked_dev, int64_t n, int64_t ns, in
 int mfish_masked_quantile_f32(const float* vol_dev, const uint8_t* mask_dev, int64_t n, double q,
                               void* ws_dev, float* out_dev, double* info_dev, void* stream);
 
+/* the same select in its three steps, for a z-slab decomposed volume: after every
+ * mfish_qsel_hist the caller all-reduces (sum) the first 2*2048 uint32 of ws_dev
+ * across the slabs, then calls mfish_qsel_scan; passes 0, 1, 2 in order.      */
+int mfish_qsel_begin(void* ws_dev, double q, void* stream);
+int mfish_qsel_hist(const float* vol_dev, const uint8_t* mask_dev, int64_t n, int pass, void* ws_dev,
+                    void* stream);
+int mfish_qsel_scan(int pass, void* ws_dev, float* out_dev, double* info_dev, void* stream);
+
 /* img_blur[pos] of skimage.filters.gaussian(normalize(img), sigma)
  * (modules/muscle_fish.py:357-365,385-388), evaluated only at the given
  * points in float64.  pts_dev is npts x 3 int32 (z, x, y).                 */

@@ -204,6 +204,7 @@ struct EnvArgs {
   double w2;         // squared spacing of this axis     (float64 arithmetic only)
   double inv_w2;     // 1 / w2
   double out_scale;  // EDT_OUT_DIST: dist = sqrt(val * out_scale)
+  float out_mul;     // (float)sqrt(out_scale)
 };
 
 constexpr int ENV_THREADS = 128;
@@ -212,14 +213,20 @@ constexpr int ENV_BATCH = 8;
 // INT = true : unit weights, every quantity an integer < 2^31 -> hull tests are int32 x int32 ->
 //              int64 products (one IMAD.WIDE each), no floating point at all.
 // INT = false: float64 hull tests (exact whenever the operands are integers < 2^53).
-template <typename TIn, typename LinkT, int OUT, bool INT>
+// IdxT: element offsets inside a line bundle (uint32 when the volume has < 2^32 elements, so an
+//       address is one IMAD.WIDE.U32 on top of the base pointer).
+template <typename TIn, typename LinkT, int OUT, bool INT, typename IdxT>
 __global__ void __launch_bounds__(ENV_THREADS) edt_envelope_kernel(const EnvArgs<TIn, LinkT> a) {
   const int64_t i = (int64_t)blockIdx.x * ENV_THREADS + threadIdx.x;
   if (i >= a.inner) return;
   const int64_t base = (int64_t)blockIdx.y * a.outer_stride + i;
   const TIn* __restrict__ in = a.in + base;
   LinkT* __restrict__ link = a.link + base;
-  const int64_t st = a.stride;
+  int32_t* __restrict__ out_i = reinterpret_cast<int32_t*>(a.out) + base;
+  float* __restrict__ out_f = reinterpret_cast<float*>(a.out) + base;
+  int32_t* __restrict__ out_sq = a.out_sq ? a.out_sq + base : nullptr;
+  const bool has_out = a.out != nullptr;
+  const IdxT st = (IdxT)a.stride;
   const int L = a.L;
   using GT = typename std::conditional<INT, int32_t, double>::type;
   const double sin = a.sin, inv_w2 = a.inv_w2, w2 = a.w2;
@@ -241,8 +248,11 @@ __global__ void __launch_bounds__(ENV_THREADS) edt_envelope_kernel(const EnvArgs
     return lhs >= rhs;
   };
 
-  int top = EDT_NO_SITE, sec = EDT_NO_SITE;
-  GT Gtop = 0, Gsec = 0;
+  // The top three hull entries live in registers (t0 = top); deeper ones are re-read through the
+  // link chain only when a burst of pops runs the cache dry.  EDT_UNKNOWN = "not cached".
+  constexpr int EDT_UNKNOWN = -2;
+  int t0 = EDT_NO_SITE, t1 = EDT_NO_SITE, t2 = EDT_NO_SITE;
+  GT G0 = 0, G1 = 0, G2 = 0;
 
   const TIn* __restrict__ pin = in;
   LinkT* __restrict__ plink = link;
@@ -253,93 +263,152 @@ __global__ void __launch_bounds__(ENV_THREADS) edt_envelope_kernel(const EnvArgs
     for (int u = 0; u < ENV_BATCH; ++u) {
       ok[u] = false;
       raw[u] = 0;
-      if (q0 + u < L) ok[u] = edt_raw<TIn>(pin + u * st, raw[u]);
+      if (q0 + u < L) ok[u] = edt_raw<TIn>(pin + (IdxT)u * st, raw[u]);
     }
 #pragma unroll
     for (int u = 0; u < ENV_BATCH; ++u) {
       if (ok[u]) {
         const int q = q0 + u;
         const GT Gq = makeG(raw[u], q);
-        while (sec != EDT_NO_SITE && hidden(Gsec, Gtop, Gq, sec, top, q)) {
-          top = sec;
-          Gtop = Gsec;
-          sec = (int)link[(int64_t)top * st];
-          if (sec != EDT_NO_SITE) {
-            uint32_t r;
-            edt_raw<TIn>(in + (int64_t)sec * st, r);
-            Gsec = makeG(r, sec);
+        while (t0 != EDT_NO_SITE) {
+          if (t1 == EDT_UNKNOWN) {
+            t1 = (int)link[(IdxT)t0 * st];
+            if (t1 != EDT_NO_SITE) {
+              uint32_t r;
+              edt_raw<TIn>(in + (IdxT)t1 * st, r);
+              G1 = makeG(r, t1);
+            }
           }
+          if (t1 == EDT_NO_SITE || !hidden(G1, G0, Gq, t1, t0, q)) break;
+          t0 = t1;
+          G0 = G1;
+          t1 = t2;
+          G1 = G2;
+          t2 = EDT_UNKNOWN;
         }
-        plink[u * st] = (LinkT)top;
-        sec = top;
-        Gsec = Gtop;
-        top = q;
-        Gtop = Gq;
+        plink[(IdxT)u * st] = (LinkT)t0;
+        t2 = t1;
+        G2 = G1;
+        t1 = t0;
+        G1 = G0;
+        t0 = q;
+        G0 = Gq;
       }
     }
-    pin += ENV_BATCH * st;
-    plink += ENV_BATCH * st;
+    pin += (IdxT)ENV_BATCH * st;
+    plink += (IdxT)ENV_BATCH * st;
   }
 
-  // backward sweep over the hull: parabola u at p (divided by w2) = G(u) - 2 p u + p^2
-  int cur = top, prev = sec;
-  GT Gcur = Gtop, Gprev = Gsec;
-  int64_t o = base + (int64_t)(L - 1) * st;
+  // backward sweep over the hull.  Parabola u at p (divided by w2) is G(u) - 2 p u + p^2, so with
+  //   D(p) = (Gprev - Gcur) + 2 p (cur - prev)     prev is at least as good as cur  <=>  D(p) <= 0
+  //   val(p) = F(cur) + w2 (p - cur)^2
+  // both are advanced incrementally as p steps down (exact for integer-valued operands):
+  //   D(p-1) = D(p) - 2 (cur - prev),   val(p-1) = val(p) - e(p),  e(p) = w2 (2 (p-cur) - 1),  e(p-1) = e(p) - 2 w2
+  int cur = t0, prev = t1;
+  GT Gcur = G0, Gprev = G1;
+  if (cur != EDT_NO_SITE && prev == EDT_UNKNOWN) {
+    prev = (int)link[(IdxT)cur * st];
+    if (prev != EDT_NO_SITE) {
+      uint32_t r;
+      edt_raw<TIn>(in + (IdxT)prev * st, r);
+      Gprev = makeG(r, prev);
+    }
+  }
+  // one entry ahead: index of the entry below prev, plus its payload and its own link, are
+  // requested when prev is entered and consumed only at the next hull move
+  int nxt = EDT_NO_SITE;
+  uint32_t nxt_raw = 0;
+  int nxt_link = EDT_NO_SITE;
+  auto prefetch_below = [&](int idx) {  // idx = entry whose link names the new nxt
+    nxt = EDT_NO_SITE;
+    if (idx != EDT_NO_SITE) nxt = (int)link[(IdxT)idx * st];
+  };
+  auto request_nxt = [&]() {
+    if (nxt != EDT_NO_SITE) {
+      edt_raw<TIn>(in + (IdxT)nxt * st, nxt_raw);
+      nxt_link = (int)link[(IdxT)nxt * st];
+    }
+  };
+  prefetch_below(prev);
+  request_nxt();
+  IdxT o = (IdxT)(L - 1) * st;
   if (cur == EDT_NO_SITE) {  // no site on this line
     for (int p = L - 1; p >= 0; --p, o -= st) {
       if (OUT == EDT_OUT_I32) {
-        reinterpret_cast<int32_t*>(a.out)[o] = EDT_INF_I32;
+        out_i[o] = EDT_INF_I32;
       } else {
-        if (a.out) reinterpret_cast<float*>(a.out)[o] = INFINITY;
-        if (OUT == EDT_OUT_DIST && a.out_sq) a.out_sq[o] = EDT_INF_I32;
+        if (has_out) out_f[o] = INFINITY;
+        if (OUT == EDT_OUT_DIST && out_sq) out_sq[o] = EDT_INF_I32;
       }
     }
     return;
   }
-  for (int p = L - 1; p >= 0; --p, o -= st) {
-    // move down the hull while the site below is at least as good at p
-    while (prev != EDT_NO_SITE) {
-      bool better;
-      if (INT) {
-        // Gprev - 2 p prev <= Gcur - 2 p cur   <=>   Gprev - Gcur <= 2 p (prev - cur)
-        better = (long long)((int32_t)Gprev - (int32_t)Gcur) <= (long long)(2 * p) * (long long)(prev - cur);
-      } else {
-        const double tp = u2d((uint32_t)(2 * p));
-        better = ((double)Gprev - (double)Gcur) <= -tp * u2d((uint32_t)(cur - prev));
-      }
-      if (!better) break;
-      cur = prev;
-      Gcur = Gprev;
-      prev = (int)link[(int64_t)cur * st];
-      if (prev != EDT_NO_SITE) {
-        uint32_t r;
-        edt_raw<TIn>(in + (int64_t)prev * st, r);
-        Gprev = makeG(r, prev);
-      }
-    }
+  using WT = typename std::conditional<INT, long long, double>::type;
+  const float out_mul = a.out_mul;
+  // INT: D and val advance incrementally (exact integers).  float64: both are re-evaluated from
+  // cached per-pair constants with one fma each (an incremental sum would cancel catastrophically
+  // when val falls from far-field magnitudes to ~0 along a run).
+  WT D = 0, Dstep = 0, Gdiff = 0;  // valid while prev != EDT_NO_SITE
+  WT val = 0, e = 0;
+  double Fcur = 0.0, curd = 0.0;
+  auto enter = [&](int p) {  // (re)initialise the running quantities for the pair (prev, cur) at p
     const int dp = p - cur;
     if (INT) {
-      // F(cur) + (p - cur)^2 with F(cur) = G(cur) - cur^2
-      const int32_t val = (int32_t)Gcur - cur * cur + dp * dp;
-      if (OUT == EDT_OUT_I32) {
-        reinterpret_cast<int32_t*>(a.out)[o] = val;
-      } else if (OUT == EDT_OUT_F32) {
-        reinterpret_cast<float*>(a.out)[o] = (float)val;
-      } else {
-        if (a.out) reinterpret_cast<float*>(a.out)[o] = (float)sqrt(u2d((uint32_t)val) * a.out_scale);
-        if (a.out_sq) a.out_sq[o] = val;
+      val = (WT)((int32_t)Gcur - cur * cur + dp * dp);
+      e = (WT)(2 * dp - 1);
+      if (prev != EDT_NO_SITE) {
+        Dstep = (WT)(2 * (cur - prev));
+        D = (WT)((int32_t)Gprev - (int32_t)Gcur) + (long long)p * (long long)Dstep;
       }
     } else {
-      const double Fcur = ((double)Gcur - u2d((uint32_t)(cur * cur))) * w2;
-      const double val = fma(w2, u2d((uint32_t)(dp * dp)), Fcur);
-      if (OUT == EDT_OUT_I32) {
-        reinterpret_cast<int32_t*>(a.out)[o] = d2i_exact(val);
-      } else if (OUT == EDT_OUT_F32) {
-        reinterpret_cast<float*>(a.out)[o] = (float)val;
-      } else {
-        if (a.out) reinterpret_cast<float*>(a.out)[o] = (float)sqrt(val * a.out_scale);
-        if (a.out_sq) a.out_sq[o] = d2i_exact(val);
+      curd = u2d((uint32_t)cur);
+      Fcur = ((double)Gcur - curd * curd) * w2;
+      if (prev != EDT_NO_SITE) {
+        Dstep = (WT)u2d((uint32_t)(2 * (cur - prev)));
+        Gdiff = (WT)((double)Gprev - (double)Gcur);
       }
+    }
+  };
+  enter(L - 1);
+  double pd = u2d((uint32_t)(L - 1));
+  for (int p = L - 1; p >= 0; --p, o -= st) {
+    if (!INT) D = (WT)fma(pd, (double)Dstep, (double)Gdiff);
+    while (prev != EDT_NO_SITE && D <= (WT)0) {  // move down the hull
+      cur = prev;
+      Gcur = Gprev;
+      prev = nxt;
+      if (prev != EDT_NO_SITE) Gprev = makeG(nxt_raw, prev);
+      nxt = (prev != EDT_NO_SITE) ? nxt_link : EDT_NO_SITE;
+      request_nxt();
+      enter(p);
+      if (!INT) D = (WT)fma(pd, (double)Dstep, (double)Gdiff);
+    }
+    if (INT) {
+      const int32_t v32 = (int32_t)val;
+      if (OUT == EDT_OUT_I32) {
+        out_i[o] = v32;
+      } else if (OUT == EDT_OUT_F32) {
+        out_f[o] = (float)v32;
+      } else {
+        // float32 sqrt of the (exact) integer: |rel err| < 1e-7 after the two roundings
+        if (has_out) out_f[o] = sqrtf((float)v32) * out_mul;
+        if (out_sq) out_sq[o] = v32;
+      }
+      val -= e;
+      e -= (WT)2;
+      D -= Dstep;
+    } else {
+      const double dpd = pd - curd;
+      const double v = fma(w2, dpd * dpd, Fcur);
+      if (OUT == EDT_OUT_I32) {
+        out_i[o] = d2i_exact(v);
+      } else if (OUT == EDT_OUT_F32) {
+        out_f[o] = (float)v;
+      } else {
+        if (has_out) out_f[o] = sqrtf((float)(v * a.out_scale));
+        if (out_sq) out_sq[o] = d2i_exact(v);
+      }
+      pd -= 1.0;
     }
   }
 }
@@ -370,11 +439,15 @@ static int launch_env(const TIn* in, void* link, void* out, int32_t* out_sq, int
   a.w2 = w2;
   a.inv_w2 = 1.0 / w2;
   a.out_scale = out_scale;
+  a.out_mul = (float)sqrt(out_scale);
   int64_t bx = (a.inner + ENV_THREADS - 1) / ENV_THREADS;
   MFISH_REQUIRE(bx < (1ll << 31) && nouter < 65536, "edt: grid too large");
   dim3 grid((unsigned)bx, (unsigned)nouter);
   ProfScope prof(axis == MFISH_AXIS_Z ? "edt_envelope_z" : "edt_envelope_x", st);
-  edt_envelope_kernel<TIn, LinkT, OUT, INT><<<grid, ENV_THREADS, 0, st>>>(a);
+  if (nz * nx * ny < (1ll << 32))
+    edt_envelope_kernel<TIn, LinkT, OUT, INT, uint32_t><<<grid, ENV_THREADS, 0, st>>>(a);
+  else
+    edt_envelope_kernel<TIn, LinkT, OUT, INT, int64_t><<<grid, ENV_THREADS, 0, st>>>(a);
   count_launch(1);
   return check_launch("edt_envelope");
 }

@@ -296,23 +296,58 @@ __global__ void __launch_bounds__(256) scale_planes_kernel(const float* __restri
 
 using namespace mfish;
 
+// The select in its three steps, so that a z-slab decomposed volume can all-reduce the histogram
+// (first 2*2048 uint32 of the workspace) between `hist` and `scan` of every pass.
+extern "C" int mfish_qsel_begin(void* ws_dev, double q, void* stream) {
+  MFISH_REQUIRE(ws_dev && q >= 0.0 && q <= 1.0, "qsel_begin: bad arguments");
+  qsel_init_kernel<<<1, 256, 0, as_stream(stream)>>>(reinterpret_cast<QWs*>(ws_dev), q);
+  count_launch(1);
+  return check_launch("qsel_begin");
+}
+
+extern "C" int mfish_qsel_hist(const float* vol_dev, const uint8_t* mask_dev, int64_t n, int pass, void* ws_dev,
+                               void* stream) {
+  MFISH_REQUIRE(vol_dev && mask_dev && ws_dev && n > 0, "qsel_hist: bad arguments");
+  MFISH_REQUIRE(pass >= 0 && pass <= 2, "qsel_hist: pass must be 0, 1 or 2");
+  cudaStream_t st = as_stream(stream);
+  QWs* ws = reinterpret_cast<QWs*>(ws_dev);
+  int blocks = (int)std::min<int64_t>((n / 4 + 255) / 256 + 1, (int64_t)num_sms() * 8);
+  if (pass == 0)
+    qsel_hist_kernel<0><<<blocks, 256, 0, st>>>(vol_dev, mask_dev, n, ws);
+  else if (pass == 1)
+    qsel_hist_kernel<1><<<blocks, 256, 0, st>>>(vol_dev, mask_dev, n, ws);
+  else
+    qsel_hist_kernel<2><<<blocks, 256, 0, st>>>(vol_dev, mask_dev, n, ws);
+  count_launch(1);
+  return check_launch("qsel_hist");
+}
+
+extern "C" int mfish_qsel_scan(int pass, void* ws_dev, float* out_dev, double* info_dev, void* stream) {
+  MFISH_REQUIRE(ws_dev && out_dev && info_dev, "qsel_scan: null pointer");
+  MFISH_REQUIRE(pass >= 0 && pass <= 2, "qsel_scan: pass must be 0, 1 or 2");
+  cudaStream_t st = as_stream(stream);
+  QWs* ws = reinterpret_cast<QWs*>(ws_dev);
+  if (pass == 0)
+    qsel_scan_kernel<0><<<1, 32, 0, st>>>(ws, out_dev, info_dev);
+  else if (pass == 1)
+    qsel_scan_kernel<1><<<1, 32, 0, st>>>(ws, out_dev, info_dev);
+  else
+    qsel_scan_kernel<2><<<1, 32, 0, st>>>(ws, out_dev, info_dev);
+  count_launch(1);
+  return check_launch("qsel_scan");
+}
+
 extern "C" int mfish_masked_quantile_f32(const float* vol_dev, const uint8_t* mask_dev, int64_t n, double q,
                                          void* ws_dev, float* out_dev, double* info_dev, void* stream) {
   MFISH_REQUIRE(vol_dev && mask_dev && ws_dev && out_dev && info_dev, "masked_quantile: null pointer");
   MFISH_REQUIRE(n > 0 && q >= 0.0 && q <= 1.0, "masked_quantile: bad arguments");
-  cudaStream_t st = as_stream(stream);
-  QWs* ws = reinterpret_cast<QWs*>(ws_dev);
-  int blocks = (int)std::min<int64_t>((n / 4 + 255) / 256 + 1, (int64_t)num_sms() * 8);
-  ProfScope prof("masked_quantile_3pass", st);
-  qsel_init_kernel<<<1, 256, 0, st>>>(ws, q);
-  qsel_hist_kernel<0><<<blocks, 256, 0, st>>>(vol_dev, mask_dev, n, ws);
-  qsel_scan_kernel<0><<<1, 32, 0, st>>>(ws, out_dev, info_dev);
-  qsel_hist_kernel<1><<<blocks, 256, 0, st>>>(vol_dev, mask_dev, n, ws);
-  qsel_scan_kernel<1><<<1, 32, 0, st>>>(ws, out_dev, info_dev);
-  qsel_hist_kernel<2><<<blocks, 256, 0, st>>>(vol_dev, mask_dev, n, ws);
-  qsel_scan_kernel<2><<<1, 32, 0, st>>>(ws, out_dev, info_dev);
-  count_launch(7);
-  return check_launch("masked_quantile");
+  ProfScope prof("masked_quantile_3pass", as_stream(stream));
+  int rc = mfish_qsel_begin(ws_dev, q, stream);
+  for (int pass = 0; pass < 3 && rc == MFISH_OK; ++pass) {
+    rc = mfish_qsel_hist(vol_dev, mask_dev, n, pass, ws_dev, stream);
+    if (rc == MFISH_OK) rc = mfish_qsel_scan(pass, ws_dev, out_dev, info_dev, stream);
+  }
+  return rc;
 }
 
 extern "C" int mfish_blur_at_points(const float* vol_dev, int64_t nz, int64_t nx, int64_t ny,

@@ -390,6 +390,25 @@ def masked_percentile(vol: Volume, mask: torch.Tensor, q_percent: float) -> floa
     return T.lerp(float(a), float(b), float(gamma))
 
 
+def masked_quantile_distributed(vol: torch.Tensor, mask: torch.Tensor, q: float, reduce_hist):
+    """Masked radix select over a volume that is split across ranks: ``reduce_hist(int32 tensor)``
+    sums the 2x2048-bin histogram over the ranks between the hist and scan step of each pass.
+    Returns (value[k], value[k+1], gamma, n_masked) of the RAW values."""
+    dev = vol.device
+    ws = WS.get("qws", (L.QUANTILE_WS_BYTES,), torch.uint8, dev)
+    out = torch.empty(2, dtype=torch.float32, device=dev)
+    info = torch.empty(2, dtype=torch.float64, device=dev)
+    hist = ws[:2 * 2048 * 4].view(torch.int32)
+    L.check(L.lib().mfish_qsel_begin(ws.data_ptr(), float(q), _stream()))
+    for p in range(3):
+        L.check(L.lib().mfish_qsel_hist(vol.data_ptr(), mask.data_ptr(), vol.numel(), p, ws.data_ptr(), _stream()))
+        reduce_hist(hist)
+        L.check(L.lib().mfish_qsel_scan(p, ws.data_ptr(), out.data_ptr(), info.data_ptr(), _stream()))
+    v0, v1 = out.tolist()
+    gamma, n = info.tolist()
+    return v0, v1, gamma, n
+
+
 def plane_means(vol: torch.Tensor, mask: torch.Tensor | None):
     """Per-z-plane (masked) sum and count, float64 on the host."""
     nz, nx, ny = vol.shape
@@ -424,6 +443,35 @@ def edt(mask_zxy: torch.Tensor, sampling_xyz=None, want_sq=False):
     L.check(L.lib().mfish_edt3d_u8(mask_zxy.data_ptr(), nz, nx, ny, L.darray([sz, sx, sy]), dist.data_ptr(),
                                    sq.data_ptr() if sq is not None else None, ws.data_ptr(), _stream()))
     return (dist, sq) if want_sq else dist
+
+
+def edt_inplane(mask_zxy: torch.Tensor, sampling_xyz=None):
+    """y and x passes only: squared in-plane distance [nz,nx,ny] (int32 or float32) + its kind."""
+    import ctypes
+    nz, nx, ny = mask_zxy.shape
+    dev = mask_zxy.device
+    sx, sy, sz = [float(s) for s in (sampling_xyz or (1.0, 1.0, 1.0))]
+    ws = WS.get("edt_ws", (int(L.lib().mfish_edt_workspace_bytes(nz, nx, ny)),), torch.uint8, dev)
+    f2 = torch.empty((nz, nx, ny), dtype=torch.int32, device=dev)
+    kind = ctypes.c_int(-1)
+    L.check(L.lib().mfish_edt_inplane_u8(mask_zxy.data_ptr(), nz, nx, ny, L.darray([sz, sx, sy]), f2.data_ptr(),
+                                         ctypes.byref(kind), ws.data_ptr(), _stream()))
+    if kind.value == L.EDT_F2_F32:
+        f2 = f2.view(torch.float32)
+    return f2, kind.value
+
+
+def edt_zpass(f2: torch.Tensor, kind: int, sampling_xyz=None):
+    """z pass on (possibly re-partitioned) in-plane squared distances -> float32 distances."""
+    nz, nx, ny = f2.shape
+    dev = f2.device
+    sx, sy, sz = [float(s) for s in (sampling_xyz or (1.0, 1.0, 1.0))]
+    link = WS.get("edt_link", (nz * nx * ny,), torch.int32, dev)
+    out = torch.empty((nz, nx, ny), dtype=torch.float32, device=dev)
+    f2 = f2.contiguous()
+    L.check(L.lib().mfish_edt_zpass(f2.data_ptr(), int(kind), nz, nx, ny, L.darray([sz, sx, sy]), out.data_ptr(), None,
+                                    link.data_ptr(), _stream()))
+    return out
 
 
 # ----------------------------------------------------- device-resident pipeline

@@ -1,0 +1,79 @@
+"""GPU: the slab-decomposed drivers with the CUDA ``DeviceOps`` (nccl).  World size 1 runs on any
+box; world size 2 needs two GPUs (one process per GPU) and is skipped otherwise."""
+import os
+import socket
+import tempfile
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import match_fraction
+
+pytestmark = pytest.mark.gpu
+ANISO = (0.0577, 0.0577, 0.5)
+SHAPE = (160, 128, 40)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _job(rank, world, port, outdir):
+    import torch
+    import torch.distributed as dist
+    import muscle_fish_b200  # noqa: F401
+    from muscle_fish_b200 import parallel as P, synth
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    try:
+        st = synth.make_stack(shape=SHAPE, n_spots=250, n_nuclei=4, seed=77, nuc_semi=(14.0, 9.0, 5.0))
+        lay = P.SlabLayout(SHAPE[2], SHAPE[0], SHAPE[1])
+        z = slice(lay.z0, lay.z1)
+        img = torch.from_numpy(np.ascontiguousarray(st["img"].transpose(2, 0, 1)[z])).cuda()
+        fib = torch.from_numpy(np.ascontiguousarray(st["fiber_mask"].transpose(2, 0, 1)[z])).cuda()
+        notnuc = torch.from_numpy(np.ascontiguousarray((st["nuc_mask"] == 0).astype(np.uint8).transpose(2, 0, 1)[z])).cuda()
+        res = P.slab_find_spots_snrfilter(img, fib, lay, sigma=2.0, t_spot=0.025)
+        dmap = P.slab_edt(notnuc, lay, ANISO)
+        sd = P.slab_spot_distances(dmap, res["spots"], lay)
+        dz = P.slab_edt(notnuc, lay, ANISO, back_to_z=True).cpu().numpy()
+        np.save(os.path.join(outdir, f"r{rank}.npy"),
+                np.array([res["spots"], res["intensity"], res["baseline"], sd, dz, (lay.z0, lay.z1)], dtype=object),
+                allow_pickle=True)
+    finally:
+        dist.destroy_process_group()
+
+
+def _check(world):
+    import torch.multiprocessing as mp
+    import muscle_fish_b200  # noqa: F401
+    from muscle_fish_b200 import synth
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_job, args=(world, _free_port(), d), nprocs=world, join=True)
+        res = [np.load(os.path.join(d, f"r{r}.npy"), allow_pickle=True) for r in range(world)]
+    st = synth.make_stack(shape=SHAPE, n_spots=250, n_nuclei=4, seed=77, nuc_semi=(14.0, 9.0, 5.0))
+    ref_spots, ref_data = oracle.find_spots_snrfilter(st["img"], sigma=2.0, t_spot=0.025, mask=st["fiber_mask"],
+                                                      pair_order="sorted")
+    grass = oracle.distance_transform_edt(np.logical_not(st["nuc_mask"]), sampling=ANISO)
+    assert len(ref_spots) > 50
+    for spots, inten, baseline, sd, dz, (z0, z1) in res:
+        assert match_fraction(spots, ref_spots) >= 0.999
+        np.testing.assert_allclose(np.sort(inten), np.sort([r[4] for r in ref_data[1:]]), rtol=1e-6)
+        np.testing.assert_allclose(sd, oracle.edt_gather(grass, spots, ANISO), rtol=1e-6)
+        np.testing.assert_allclose(dz, grass.transpose(2, 0, 1)[z0:z1], rtol=1e-6)
+
+
+def test_slab_drivers_world1():
+    _check(1)
+
+
+def test_slab_drivers_world2_nccl():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (one process per GPU)")
+    _check(2)
