@@ -53,6 +53,27 @@ ALGO_BYTES = {
 }
 
 
+_JSON_FD = None
+
+
+def _capture_stdout():
+    """Everything libraries print to stdout (NCCL banners, ...) goes to stderr; the one JSON line is
+    written to the real stdout by _emit()."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def _emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _JSON_FD is None:
+        os.write(1, data)
+    else:
+        os.write(_JSON_FD, data)
+
+
 def _peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -193,7 +214,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ----------------------------------------------------------------------------------- GPU side
@@ -334,7 +355,7 @@ def run_ours(args):
         "kernels": kernels,
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -351,6 +372,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=320, help="x/y edge of the per-worker CPU sample stack")
     ap.add_argument("--ref-workers", type=int, default=0)
     args = ap.parse_args()
+    _capture_stdout()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = max(args.warmup, 1)
     if args.impl == "reference":

@@ -60,6 +60,59 @@ def host_to_device(arr) -> torch.Tensor:
     return t.to("cuda", non_blocking=t.is_pinned())
 
 
+_COPY_STREAMS = {}
+
+
+def host_to_device_many(arrs):
+    """Queue the H2D copies of several host arrays back to back on a side stream and return
+    [(device tensor, ready event)], so that work on the first array overlaps the later copies
+    (PCIe is the slow link of the host-buffer path).  Device / non-array inputs pass through."""
+    _require_cuda()
+    dev = torch.cuda.current_device()
+    cur = torch.cuda.current_stream()
+    cs = _COPY_STREAMS.get(dev)
+    if cs is None:
+        cs = _COPY_STREAMS[dev] = torch.cuda.Stream()
+    out = []
+    started = False
+    for arr in arrs:
+        if arr is None:
+            out.append((None, None))
+            continue
+        if isinstance(arr, torch.Tensor):
+            src = arr if arr.is_cuda else arr.contiguous()
+        else:
+            a = np.asarray(arr)
+            if a.dtype == np.bool_:
+                a = a.view(np.uint8)
+            if a.dtype not in _DTYPES:
+                a = a.astype(np.float64)
+            if not a.flags.c_contiguous:
+                a = np.ascontiguousarray(a)
+            if not a.flags.writeable:
+                a = a.copy()
+            src = torch.from_numpy(a)
+        if src.dtype == torch.bool:
+            src = src.view(torch.uint8)
+        if src.is_cuda:
+            out.append((src.contiguous(), None))
+            continue
+        if not src.is_pinned():
+            # pageable memory: the driver stages the copy synchronously anyway
+            out.append((src.to("cuda"), None))
+            continue
+        dst = torch.empty(src.shape, dtype=src.dtype, device="cuda")  # owned by the compute stream
+        if not started:
+            cs.wait_stream(cur)  # the block may have been in use by earlier compute work
+            started = True
+        with torch.cuda.stream(cs):
+            dst.copy_(src, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(cs)
+        out.append((dst, ev))
+    return out
+
+
 @dataclass
 class Volume:
     """One channel on the device: raw float32 voxels [nz, nx, ny] + {min, max}."""
@@ -84,10 +137,13 @@ class Volume:
         return float(lo), float(hi)
 
 
-def ingest(src, z_first=False, as_mask=False, want_minmax=True, negate=False):
+def ingest(src, z_first=False, as_mask=False, want_minmax=True, negate=False, ready=None):
     """Host/device array in reference order (x,y,z) [or (z,x,y) when ``z_first``]
-    -> device layout.  Returns ``Volume`` (float32 + minmax) or a uint8 mask tensor."""
+    -> device layout.  Returns ``Volume`` (float32 + minmax) or a uint8 mask tensor.
+    ``ready``: event of an asynchronous copy of ``src`` (see ``host_to_device_many``)."""
     t = host_to_device(src)
+    if ready is not None:
+        torch.cuda.current_stream().wait_event(ready)
     if t.dim() != 3:
         raise ValueError("expected a 3-D volume, got shape %r" % (tuple(t.shape),))
     if t.dtype == torch.bool:

@@ -19,13 +19,26 @@ from . import device as D
 from . import scope_utils3 as su  # noqa: F401  (reference modules import it the same way)
 
 
+class _Lazy:
+    """A mask whose host->device copy is already queued; converted on first use, so that the
+    filters on the image overlap the mask's trip over PCIe."""
+
+    def __init__(self, tensor, event, z_first, shape):
+        self.tensor, self.event, self.z_first, self.shape, self._m = tensor, event, z_first, shape, None
+
+    def get(self):
+        if self._m is None:
+            self._m = D.ingest(self.tensor, z_first=self.z_first, as_mask=True, ready=self.event)
+            if tuple(self._m.shape) != tuple(self.shape):
+                raise IndexError("mask and image shapes differ: %r vs %r" % (tuple(self._m.shape), tuple(self.shape)))
+            self.tensor = None
+        return self._m
+
+
 def _prep(img_fish, mask, z_first):
-    vol = D.ingest(img_fish, z_first=z_first)
-    m = None
-    if mask is not None:
-        m = D.ingest(mask, z_first=z_first, as_mask=True)
-        if tuple(m.shape) != tuple(vol.data.shape):
-            raise IndexError("mask and image shapes differ: %r vs %r" % (tuple(m.shape), tuple(vol.data.shape)))
+    (ti, ei), (tm, em) = D.host_to_device_many([img_fish, mask])
+    vol = D.ingest(ti, z_first=z_first, ready=ei)
+    m = _Lazy(tm, em, z_first, vol.data.shape) if mask is not None else None
     return vol, m
 
 
@@ -37,6 +50,12 @@ def _row_stack(rows):
     return np.vstack(rows)
 
 
+def _nonempty(rows):
+    if len(rows) == 0:
+        return _row_stack([])
+    return rows
+
+
 def find_spots(img_fish, sigma=1., t_spot=0.025, mask=None):
     """Find FISH spots with blob_log; optionally keep only spots inside ``mask``.
     Returns an (N, 4) float64 array of rows [x, y, z, sigma]."""
@@ -45,8 +64,7 @@ def find_spots(img_fish, sigma=1., t_spot=0.025, mask=None):
     if mask is not None:
         if len(spots) == 0:
             return _row_stack([])
-        keep = D.gather(m, spots) != 0
-        return _row_stack(list(spots[keep]))
+        return _nonempty(spots[D.gather(m.get(), spots) != 0])
     return spots
 
 
@@ -64,7 +82,7 @@ def find_spots_snrfilter(img_fish, snr=None, sigma=1., t_spot=0.025, mask=None, 
     if mask is not None:
         if len(spots) == 0:
             return _row_stack([]), None
-        spots_masked = _row_stack(list(spots[D.gather(m, spots) != 0]))
+        spots_masked = _nonempty(spots[D.gather(m.get(), spots) != 0])
     else:
         spots_masked = spots
 
@@ -72,7 +90,7 @@ def find_spots_snrfilter(img_fish, snr=None, sigma=1., t_spot=0.025, mask=None, 
         # np.logical_not(None) masks every voxel in the reference, so the percentile below is
         # taken over an empty selection and fails (modules/muscle_fish.py:355-356)
         raise IndexError("find_spots_snrfilter needs a mask: percentile of an empty selection")
-    baseline = D.masked_percentile(vol, m, 25)
+    baseline = D.masked_percentile(vol, m.get(), 25)
     spot_int = D.blur_at_points(vol, spots_masked, (3, 3, 0.3), mode="nearest")
 
     if snr is None:
@@ -82,14 +100,15 @@ def find_spots_snrfilter(img_fish, snr=None, sigma=1., t_spot=0.025, mask=None, 
 
     print('SNR threshold = ' + str(snr))
 
-    spots_filtered = []
+    # the reference's per-spot loop (modules/muscle_fish.py:382-400), vectorised
+    ratio = spot_int / baseline
+    spots_filtered = spots_masked[ratio > snr]
+    if z_first:
+        spots_filtered = spots_filtered[:, [2, 0, 1, 3]]
+    rows = np.column_stack([spots_masked[:, 0:3], spot_int, ratio]).tolist()
     spot_data = [['spot_id', 'x', 'y', 'z', 'intensity', 'SNR']]
-    for c, spot in enumerate(spots_masked):
-        intensity = spot_int[c]
-        if intensity / baseline > snr:
-            spots_filtered.append(spot[[2, 0, 1, 3]] if z_first else spot)
-        spot_data.append([c] + list(spot[0:3]) + [intensity, intensity / baseline])
-    return _row_stack(spots_filtered), spot_data
+    spot_data.extend([c] + r for c, r in enumerate(rows))
+    return _nonempty(spots_filtered), spot_data
 
 
 def fix_bleaching(img, second_half=True, mask=None, z_first=False, draw=False, imgprefix='fiber'):

@@ -1,0 +1,7 @@
+python -m pytest tests -m gpu -x -q 2>&1 | tail -12 > gpurun_out/pytest_gpu.log; tail -8 gpurun_out/pytest_gpu.log
+python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c2_b.json 2> gpurun_out/bench_c2_b.err; echo bench=$?; python - <<'PY'
+import json
+d=json.load(open('gpurun_out/bench_c2_b.json'))
+print('value',d['value'],'ms',d['ms_per_step'],'e2e',d['e2e']['value'])
+PY
+tail -3 gpurun_out/bench_c2_b.err
