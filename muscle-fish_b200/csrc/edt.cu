@@ -119,29 +119,32 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) edt_scan_y_kernel(const ScanA
       const uint32_t b = bits[w];
       const int y0 = w * 32;
       const int cl = carryL[w], cr = carryR[w];
-      uint32_t packed[16];
+      const bool full = vout && y0 + 32 <= ny;
+#pragma unroll 1
+      for (int k = 0; k < 4; ++k) {  // 8 voxels -> one 128-bit store (keeps the register count low)
+        uint32_t packed[4];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const uint32_t upto = b & (0xFFFFFFFFu >> (31 - j));
-        const uint32_t from = b >> j;
-        const int y = y0 + j;
-        const int l = upto ? (y0 + 31 - __clz(upto)) : cl;
-        const int r = from ? (y + __ffs(from) - 1) : cr;
-        const int d = min(min(y - l, r - y), (int)EDT_INF_U16);
-        if (j & 1)
-          packed[j >> 1] |= (uint32_t)d << 16;
-        else
-          packed[j >> 1] = (uint32_t)d;
-      }
-      if (vout && y0 + 32 <= ny) {
-        uint4* o4 = reinterpret_cast<uint4*>(dst + y0);
+        for (int jj = 0; jj < 8; ++jj) {
+          const int j = 8 * k + jj;
+          const uint32_t upto = b & (0xFFFFFFFFu >> (31 - j));
+          const uint32_t from = b >> j;
+          const int y = y0 + j;
+          const int l = upto ? (y0 + 31 - __clz(upto)) : cl;
+          const int r = from ? (y + __ffs(from) - 1) : cr;
+          const int d = min(min(y - l, r - y), (int)EDT_INF_U16);
+          if (jj & 1)
+            packed[jj >> 1] |= (uint32_t)d << 16;
+          else
+            packed[jj >> 1] = (uint32_t)d;
+        }
+        if (full) {
+          reinterpret_cast<uint4*>(dst + y0)[k] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        } else {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          o4[k] = make_uint4(packed[4 * k], packed[4 * k + 1], packed[4 * k + 2], packed[4 * k + 3]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (y0 + j < ny) dst[y0 + j] = (uint16_t)((packed[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu);
+          for (int jj = 0; jj < 8; ++jj) {
+            const int y = y0 + 8 * k + jj;
+            if (y < ny) dst[y] = (uint16_t)((packed[jj >> 1] >> ((jj & 1) * 16)) & 0xFFFFu);
+          }
         }
       }
     }

@@ -80,64 +80,81 @@ __device__ __forceinline__ void emit_peak(const NmsArgs& a, int s, int z, int x,
 }
 
 constexpr int NMS_UNROLL = 4;
+constexpr int NMS_THREADS = 256;
+constexpr int NMS_CHUNK = NMS_THREADS * NMS_UNROLL * 4;  // voxels scanned per block iteration
 
-__device__ __forceinline__ void nms_test4(const NmsArgs& a, int64_t row, int y0, const float v[4]) {
-  const float m = fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3]));
-  if (!(m > a.thr)) return;
-  const int x = (int)(row % a.nx);
-  const int64_t sz = row / a.nx;
-  const int z = (int)(sz % a.nz);
-  const int s = (int)(sz / a.nz);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    if (v[i] > a.thr && y0 + i < a.ny) {
-      // y neighbours inside the register quad reject most candidates without a load
-      const float l = i > 0 ? v[i - 1] : -INFINITY;
-      const float r = i < 3 ? v[i + 1] : -INFINITY;
-      if (fmaxf(l, r) > v[i]) continue;
-      if (is_peak(a, s, z, x, y0 + i, v[i])) emit_peak(a, s, z, x, y0 + i, v[i]);
-    }
-  }
+__device__ __forceinline__ void nms_decode(const NmsArgs& a, int64_t vox, int& s, int& z, int& x, int& y) {
+  y = (int)(vox % a.ny);
+  int64_t r = vox / a.ny;
+  x = (int)(r % a.nx);
+  r /= a.nx;
+  z = (int)(r % a.nz);
+  s = (int)(r / a.nz);
 }
 
-// One thread per 4 consecutive y (128-bit load when the row allows it), NMS_UNROLL quads in flight.
-__global__ void __launch_bounds__(256) nms_compact_kernel(const NmsArgs a) {
-  const int ny4 = (a.ny + 3) >> 2;
-  const int64_t nrows = (int64_t)a.ns * a.nz * a.nx;
-  const int64_t total = nrows * ny4;
+// Two phases per chunk so that no warp diverges on the (rare, expensive) neighbour test:
+//   1. stream NMS_UNROLL x 128-bit loads per thread; a voxel that is above the threshold and not
+//      beaten by its y neighbours inside the quad becomes a candidate (offset pushed to smem);
+//   2. the block walks the candidate list with all lanes busy: 26/80-neighbour test, append.
+__global__ void __launch_bounds__(NMS_THREADS) nms_compact_kernel(const NmsArgs a) {
+  __shared__ uint16_t s_cand[NMS_CHUNK];
+  __shared__ float s_val[NMS_CHUNK];
+  __shared__ int s_n;
+  const int64_t total_vox = (int64_t)a.ns * a.nz * a.nx * a.ny;
   const bool vec = ((a.ny & 3) == 0) && aligned16_dev(a.cube);
-  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (vec) {
-    // ny % 4 == 0: quad t sits at float offset 4 t
-    const float4* __restrict__ c4 = reinterpret_cast<const float4*>(a.cube);
-    for (int64_t t0 = tid; t0 < total; t0 += nthreads * NMS_UNROLL) {
+  const int64_t nchunks = (total_vox + NMS_CHUNK - 1) / NMS_CHUNK;
+  const float thr = a.thr;
+  for (int64_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    const int64_t v0 = ch * NMS_CHUNK;
+    if (vec) {
+      // ny % 4 == 0: every quad lies inside one row
       float4 q[NMS_UNROLL];
 #pragma unroll
       for (int u = 0; u < NMS_UNROLL; ++u) {
-        const int64_t t = t0 + u * nthreads;
-        q[u] = t < total ? __ldg(c4 + t) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        const int64_t off = v0 + (int64_t)(u * NMS_THREADS + threadIdx.x) * 4;
+        q[u] = off < total_vox ? __ldg(reinterpret_cast<const float4*>(a.cube + off))
+                               : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
       }
 #pragma unroll
       for (int u = 0; u < NMS_UNROLL; ++u) {
-        const int64_t t = t0 + u * nthreads;
         const float v[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
-        if (fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])) > a.thr) {
-          const int64_t row = t / ny4;
-          nms_test4(a, row, (int)(t - row * ny4) * 4, v);
+        if (fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])) > thr) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float l = i > 0 ? v[i - 1] : -INFINITY;
+            const float r = i < 3 ? v[i + 1] : -INFINITY;
+            if (v[i] > thr && !(fmaxf(l, r) > v[i])) {
+              const int pos = atomicAdd(&s_n, 1);
+              s_cand[pos] = (uint16_t)((u * NMS_THREADS + threadIdx.x) * 4 + i);
+              s_val[pos] = v[i];
+            }
+          }
+        }
+      }
+    } else {
+      for (int k = threadIdx.x; k < NMS_CHUNK; k += NMS_THREADS) {
+        const int64_t off = v0 + k;
+        if (off < total_vox) {
+          const float v = __ldg(a.cube + off);
+          if (v > thr) {
+            const int pos = atomicAdd(&s_n, 1);
+            s_cand[pos] = (uint16_t)k;
+            s_val[pos] = v;
+          }
         }
       }
     }
-  } else {
-    for (int64_t t = tid; t < total; t += nthreads) {
-      const int64_t row = t / ny4;
-      const int y0 = (int)(t - row * ny4) * 4;
-      const float* p = a.cube + row * a.ny + y0;
-      float v[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) v[i] = (y0 + i < a.ny) ? __ldg(p + i) : -INFINITY;
-      nms_test4(a, row, y0, v);
+    __syncthreads();
+    const int n = s_n;
+    for (int k = threadIdx.x; k < n; k += NMS_THREADS) {
+      int s, z, x, y;
+      nms_decode(a, v0 + s_cand[k], s, z, x, y);
+      const float v = s_val[k];
+      if (is_peak(a, s, z, x, y, v)) emit_peak(a, s, z, x, y, v);
     }
+    __syncthreads();
   }
 }
 
@@ -341,10 +358,10 @@ extern "C" int mfish_nms_compact_f32(const float* cube_dev, int64_t ns, int64_t 
   cudaStream_t st = as_stream(stream);
   MFISH_CUDA(cudaMemsetAsync(count_dev, 0, sizeof(uint32_t), st));
   NmsArgs a{cube_dev, (int)ns, (int)nz, (int)nx, (int)ny, threshold, out_idx_dev, out_val_dev, count_dev, capacity};
-  int64_t total = ns * nz * nx * ((ny + 3) / 4);
-  int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 32);
+  int64_t nchunks = (ns * nz * nx * ny + NMS_CHUNK - 1) / NMS_CHUNK;
+  int blocks = (int)std::min<int64_t>(nchunks, (int64_t)num_sms() * 32);
   ProfScope prof("nms_compact", st);
-  nms_compact_kernel<<<blocks, 256, 0, st>>>(a);
+  nms_compact_kernel<<<blocks, NMS_THREADS, 0, st>>>(a);
   count_launch(1);
   return check_launch("nms_compact");
 }

@@ -1,0 +1,9 @@
+python -m pytest tests -m gpu -x -q 2>&1 | tail -6 > gpurun_out/pytest_gpu.log; tail -3 gpurun_out/pytest_gpu.log
+python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c2_b.json 2> gpurun_out/bench_c2_b.err; echo bench=$?; python - <<'PY'
+import json
+d=json.load(open('gpurun_out/bench_c2_b.json'))
+print('value',d['value'],'ms',d['ms_per_step'],'e2e',d['e2e']['value'])
+for k,v in d['kernels'].items(): print(f"  {k:24s} {v['ms']:.3f} ms  frac {v.get('frac',0):.3f}")
+PY
+tail -3 gpurun_out/bench_c2_b.err
+python tools/prof_step.py C2 > gpurun_out/plain_prof.log 2>&1 && ncu --set full --clock-control none --import-source on -k 'regex:edt_envelope|nms_compact|edt_scan' -s 4 -c 4 -f -o gpurun_out/prof_r1_c2_d python tools/prof_step.py C2 > gpurun_out/ncu_full.log 2>&1; echo ncu=$?
