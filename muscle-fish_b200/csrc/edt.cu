@@ -164,26 +164,31 @@ __device__ __forceinline__ double u2d(uint32_t v) {
 // non-negative double < 2^31 holding an integer -> int32, without F2I
 __device__ __forceinline__ int32_t d2i_exact(double v) { return __double2loint(v + 4503599627370496.0); }
 
-// raw input value -> (valid, integer payload).  u16 rows hold |dy| (squared here).
+// raw input value -> integer payload; the per-type sentinel marks "no site" (never a valid payload).
+// u16 rows hold |dy| (squared here: at most 65534^2 < 0xFFFFFFFF).
 template <typename TIn>
-__device__ __forceinline__ bool edt_raw(const TIn* p, uint32_t& v);
+struct EdtRaw;
 template <>
-__device__ __forceinline__ bool edt_raw<uint16_t>(const uint16_t* p, uint32_t& v) {
-  const uint32_t d = __ldg(p);
-  v = d * d;
-  return d != EDT_INF_U16;
-}
+struct EdtRaw<uint16_t> {
+  static constexpr uint32_t kNone = 0xFFFFFFFFu;
+  static __device__ __forceinline__ uint32_t load(const uint16_t* p) {
+    const uint32_t d = __ldg(p);
+    return d == EDT_INF_U16 ? kNone : d * d;
+  }
+};
 template <>
-__device__ __forceinline__ bool edt_raw<int32_t>(const int32_t* p, uint32_t& v) {
-  v = (uint32_t)__ldg(p);
-  return v != (uint32_t)EDT_INF_I32;
-}
+struct EdtRaw<int32_t> {
+  static constexpr uint32_t kNone = (uint32_t)EDT_INF_I32;
+  static __device__ __forceinline__ uint32_t load(const int32_t* p) { return (uint32_t)__ldg(p); }
+};
 template <>
-__device__ __forceinline__ bool edt_raw<float>(const float* p, uint32_t& v) {
-  const float f = __ldg(p);
-  v = __float_as_uint(f);
-  return f < INFINITY;
-}
+struct EdtRaw<float> {
+  static constexpr uint32_t kNone = 0x7F800000u;  // +inf
+  static __device__ __forceinline__ uint32_t load(const float* p) {
+    const float f = __ldg(p);
+    return f < INFINITY ? __float_as_uint(f) : kNone;
+  }
+};
 template <typename TIn>
 __device__ __forceinline__ double edt_value(uint32_t v) {
   return u2d(v);
@@ -197,226 +202,239 @@ template <typename TIn, typename LinkT>
 struct EnvArgs {
   const TIn* in;
   LinkT* link;
-  void* out;        // int32 / float, by OUT
-  int32_t* out_sq;  // optional exact integer squared distance (EDT_OUT_DIST only)
+  void* out;        // int32 / float, by OUT (may be null for EDT_OUT_DIST with SQ == 2)
+  int32_t* out_sq;  // exact integer squared distance (EDT_OUT_DIST, SQ >= 1)
   int64_t inner;
   int64_t outer_stride;
   int64_t stride;
   int L;
-  double sin;        // F = sin * input value            (float64 arithmetic only)
-  double w2;         // squared spacing of this axis     (float64 arithmetic only)
-  double inv_w2;     // 1 / w2
+  double sG;         // G(u) = sG * raw(u) + u^2          (float64 arithmetic only)
+  double w2;         // squared spacing of this axis       (float64 arithmetic only)
   double out_scale;  // EDT_OUT_DIST: dist = sqrt(val * out_scale)
   float out_mul;     // (float)sqrt(out_scale)
 };
 
 constexpr int ENV_THREADS = 128;
-constexpr int ENV_BATCH = 8;
+constexpr int ENV_BATCH = 8;  // elements per software-pipelined input batch
 
-// INT = true : unit weights, every quantity an integer < 2^31 -> hull tests are int32 x int32 ->
-//              int64 products (one IMAD.WIDE each), no floating point at all.
-// INT = false: float64 hull tests (exact whenever the operands are integers < 2^53).
-// IdxT: element offsets inside a line bundle (uint32 when the volume has < 2^32 elements, so an
-//       address is one IMAD.WIDE.U32 on top of the base pointer).
-template <typename TIn, typename LinkT, int OUT, bool INT, typename IdxT>
+// Arithmetic of the hull tests.  With G(u) = F(u)/w2 + u^2, site b is hidden by (a, q) iff
+//     (Gb - Ga) (q - b)  >=  (Gq - Gb) (b - a).
+// The kernel keeps A = Gb - Ga and B = b - a of the two top entries as state, so a test costs one
+// subtraction, two products and a compare, and a push re-uses the test's own operands as the
+// next (A, B).
+//  INT : unit weights, every quantity an integer < 2^31 -> int32 differences, int64 products
+//        (one IMAD.WIDE each), no floating point at all.
+//  F64 : float64 (exact whenever the operands are integers < 2^53; conversions through the
+//        2^52 trick, never the I2F/F2I pipe).
+template <bool INT>
+struct Hull;
+
+template <>
+struct Hull<true> {
+  using G = int32_t;   // G values and their differences
+  using B = int32_t;   // index differences
+  using W = long long;
+  template <typename TIn>
+  static __device__ __forceinline__ G make(uint32_t raw, int u, double, double) {
+    return (G)(raw + (uint32_t)(u * u));
+  }
+  static __device__ __forceinline__ B idiff(int hi, int lo) { return hi - lo; }
+  static __device__ __forceinline__ bool hidden(G A, B Bb, G dG, B dq) { return (W)A * (W)dq >= (W)dG * (W)Bb; }
+};
+
+template <>
+struct Hull<false> {
+  using G = double;
+  using B = double;
+  using W = double;
+  template <typename TIn>
+  static __device__ __forceinline__ G make(uint32_t raw, int u, double ud, double sG) {
+    return fma(sG, edt_value<TIn>(raw), ud * ud);
+  }
+  static __device__ __forceinline__ B idiff(int hi, int lo) { return u2d((uint32_t)(hi - lo)); }
+  static __device__ __forceinline__ bool hidden(G A, B Bb, G dG, B dq) { return A * dq >= dG * Bb; }
+};
+
+// OUT: EDT_OUT_I32 (squared, int32) / EDT_OUT_F32 (squared, float) / EDT_OUT_DIST (sqrt, float)
+// SQ : EDT_OUT_DIST only -- 0 distances, 1 distances + int32 squares, 2 int32 squares only
+// IdxT: element offsets inside a line bundle (uint32 when the volume has < 2^32 elements)
+template <typename TIn, typename LinkT, int OUT, int SQ, bool INT, typename IdxT>
 __global__ void __launch_bounds__(ENV_THREADS) edt_envelope_kernel(const EnvArgs<TIn, LinkT> a) {
+  using H = Hull<INT>;
+  using GT = typename H::G;
+  using BT = typename H::B;
+  using WT = typename H::W;
+  using R = EdtRaw<TIn>;
   const int64_t i = (int64_t)blockIdx.x * ENV_THREADS + threadIdx.x;
   if (i >= a.inner) return;
   const int64_t base = (int64_t)blockIdx.y * a.outer_stride + i;
   const TIn* __restrict__ in = a.in + base;
   LinkT* __restrict__ link = a.link + base;
-  int32_t* __restrict__ out_i = reinterpret_cast<int32_t*>(a.out) + base;
-  float* __restrict__ out_f = reinterpret_cast<float*>(a.out) + base;
-  int32_t* __restrict__ out_sq = a.out_sq ? a.out_sq + base : nullptr;
-  const bool has_out = a.out != nullptr;
   const IdxT st = (IdxT)a.stride;
   const int L = a.L;
-  using GT = typename std::conditional<INT, int32_t, double>::type;
-  const double sin = a.sin, inv_w2 = a.inv_w2, w2 = a.w2;
-  const double sG = sin * inv_w2;  // G(u) = F(u)/w2 + u^2 = sG * raw + u^2
+  const double sG = a.sG;
 
-  auto makeG = [&](uint32_t raw, int u) -> GT {
-    if (INT) return (GT)(int32_t)(raw + (uint32_t)(u * u));
-    return (GT)fma(sG, edt_value<TIn>(raw), u2d((uint32_t)(u * u)));
-  };
-  // site `top` is hidden by (sec, q)  <=>  (Gtop - Gsec)(q - top) >= (Gq - Gtop)(top - sec)
-  auto hidden = [&](GT Gsec, GT Gtop, GT Gq, int sec, int top, int q) -> bool {
-    if (INT) {
-      const long long lhs = (long long)((int32_t)Gtop - (int32_t)Gsec) * (long long)(q - top);
-      const long long rhs = (long long)((int32_t)Gq - (int32_t)Gtop) * (long long)(top - sec);
-      return lhs >= rhs;
-    }
-    const double lhs = ((double)Gtop - (double)Gsec) * u2d((uint32_t)(q - top));
-    const double rhs = ((double)Gq - (double)Gtop) * u2d((uint32_t)(top - sec));
-    return lhs >= rhs;
-  };
-
-  // The top three hull entries live in registers (t0 = top); deeper ones are re-read through the
-  // link chain only when a burst of pops runs the cache dry.  EDT_UNKNOWN = "not cached".
-  constexpr int EDT_UNKNOWN = -2;
-  int t0 = EDT_NO_SITE, t1 = EDT_NO_SITE, t2 = EDT_NO_SITE;
-  GT G0 = 0, G1 = 0, G2 = 0;
-
-  const TIn* __restrict__ pin = in;
-  LinkT* __restrict__ plink = link;
-  for (int q0 = 0; q0 < L; q0 += ENV_BATCH) {
-    uint32_t raw[ENV_BATCH];
-    bool ok[ENV_BATCH];
+  // ---- forward sweep: build the hull as an in-place linked stack (link[q] = entry below q).
+  // Registers hold the two top entries (t0 above t1) and A = G0 - G1, B = t0 - t1.
+  // Input is software-pipelined: batch k+1 is in flight (registers) while batch k, parked in this
+  // thread's own shared-memory column, is consumed by a rolled loop.
+  __shared__ uint32_t s_raw[ENV_BATCH][ENV_THREADS];
+  int t0 = EDT_NO_SITE, t1 = EDT_NO_SITE;
+  GT G0 = 0, A = 0;
+  BT Bb = 0;
+  {
+    uint32_t nb[ENV_BATCH];
 #pragma unroll
-    for (int u = 0; u < ENV_BATCH; ++u) {
-      ok[u] = false;
-      raw[u] = 0;
-      if (q0 + u < L) ok[u] = edt_raw<TIn>(pin + (IdxT)u * st, raw[u]);
-    }
+    for (int u = 0; u < ENV_BATCH; ++u) nb[u] = u < L ? R::load(in + (IdxT)u * st) : R::kNone;
+    LinkT* __restrict__ plink = link;
+    const TIn* __restrict__ pnext = in + (IdxT)ENV_BATCH * st;
+    double qd = 0.0;
+#pragma unroll 1
+    for (int q0 = 0; q0 < L; q0 += ENV_BATCH) {
 #pragma unroll
-    for (int u = 0; u < ENV_BATCH; ++u) {
-      if (ok[u]) {
-        const int q = q0 + u;
-        const GT Gq = makeG(raw[u], q);
-        while (t0 != EDT_NO_SITE) {
-          if (t1 == EDT_UNKNOWN) {
+      for (int u = 0; u < ENV_BATCH; ++u) s_raw[u][threadIdx.x] = nb[u];
+#pragma unroll
+      for (int u = 0; u < ENV_BATCH; ++u)
+        nb[u] = (q0 + ENV_BATCH + u < L) ? R::load(pnext + (IdxT)u * st) : R::kNone;
+      pnext += (IdxT)ENV_BATCH * st;
+      const int qe = min(L, q0 + ENV_BATCH);
+#pragma unroll 1
+      for (int q = q0; q < qe; ++q, plink += st, qd += 1.0) {
+        const uint32_t rq = s_raw[q - q0][threadIdx.x];
+        if (rq == R::kNone) continue;
+        const GT Gq = H::template make<TIn>(rq, q, qd, sG);
+        GT dG = Gq - G0;
+        BT dq = H::idiff(q, t0);
+        if (t1 != EDT_NO_SITE && H::hidden(A, Bb, dG, dq)) {
+          // pop until the top is visible again (rare: ~0.5 pops per voxel, usually one at a time)
+          do {
+            t0 = t1;
+            G0 = G0 - A;  // = G1
             t1 = (int)link[(IdxT)t0 * st];
-            if (t1 != EDT_NO_SITE) {
-              uint32_t r;
-              edt_raw<TIn>(in + (IdxT)t1 * st, r);
-              G1 = makeG(r, t1);
-            }
-          }
-          if (t1 == EDT_NO_SITE || !hidden(G1, G0, Gq, t1, t0, q)) break;
-          t0 = t1;
-          G0 = G1;
-          t1 = t2;
-          G1 = G2;
-          t2 = EDT_UNKNOWN;
+            dG = Gq - G0;
+            dq = H::idiff(q, t0);
+            if (t1 == EDT_NO_SITE) break;
+            const GT G1 = H::template make<TIn>(R::load(in + (IdxT)t1 * st), t1, u2d((uint32_t)t1), sG);
+            A = G0 - G1;
+            Bb = H::idiff(t0, t1);
+          } while (H::hidden(A, Bb, dG, dq));
         }
-        plink[(IdxT)u * st] = (LinkT)t0;
-        t2 = t1;
-        G2 = G1;
+        *plink = (LinkT)t0;
         t1 = t0;
-        G1 = G0;
         t0 = q;
         G0 = Gq;
+        A = dG;
+        Bb = dq;
       }
     }
-    pin += (IdxT)ENV_BATCH * st;
-    plink += (IdxT)ENV_BATCH * st;
   }
 
-  // backward sweep over the hull.  Parabola u at p (divided by w2) is G(u) - 2 p u + p^2, so with
-  //   D(p) = (Gprev - Gcur) + 2 p (cur - prev)     prev is at least as good as cur  <=>  D(p) <= 0
+  // ---- backward sweep over the hull.  Parabola u at p (divided by w2) is G(u) - 2 p u + p^2:
+  //   D(p) = (Gprev - Gcur) + 2 p (cur - prev) = -A + p * 2B   prev at least as good  <=>  D(p) <= 0
   //   val(p) = F(cur) + w2 (p - cur)^2
-  // both are advanced incrementally as p steps down (exact for integer-valued operands):
-  //   D(p-1) = D(p) - 2 (cur - prev),   val(p-1) = val(p) - e(p),  e(p) = w2 (2 (p-cur) - 1),  e(p-1) = e(p) - 2 w2
-  int cur = t0, prev = t1;
-  GT Gcur = G0, Gprev = G1;
-  if (cur != EDT_NO_SITE && prev == EDT_UNKNOWN) {
-    prev = (int)link[(IdxT)cur * st];
-    if (prev != EDT_NO_SITE) {
-      uint32_t r;
-      edt_raw<TIn>(in + (IdxT)prev * st, r);
-      Gprev = makeG(r, prev);
-    }
-  }
-  // one entry ahead: index of the entry below prev, plus its payload and its own link, are
-  // requested when prev is entered and consumed only at the next hull move
-  int nxt = EDT_NO_SITE;
-  uint32_t nxt_raw = 0;
-  int nxt_link = EDT_NO_SITE;
-  auto prefetch_below = [&](int idx) {  // idx = entry whose link names the new nxt
-    nxt = EDT_NO_SITE;
-    if (idx != EDT_NO_SITE) nxt = (int)link[(IdxT)idx * st];
-  };
-  auto request_nxt = [&]() {
-    if (nxt != EDT_NO_SITE) {
-      edt_raw<TIn>(in + (IdxT)nxt * st, nxt_raw);
-      nxt_link = (int)link[(IdxT)nxt * st];
-    }
-  };
-  prefetch_below(prev);
-  request_nxt();
+  float* __restrict__ out_f = reinterpret_cast<float*>(a.out) + base;
+  int32_t* __restrict__ out_i = reinterpret_cast<int32_t*>(a.out) + base;
+  int32_t* __restrict__ out_sq = a.out_sq + base;
   IdxT o = (IdxT)(L - 1) * st;
-  if (cur == EDT_NO_SITE) {  // no site on this line
+  if (t0 == EDT_NO_SITE) {  // no site on this line
+#pragma unroll 1
     for (int p = L - 1; p >= 0; --p, o -= st) {
-      if (OUT == EDT_OUT_I32) {
-        out_i[o] = EDT_INF_I32;
-      } else {
-        if (has_out) out_f[o] = INFINITY;
-        if (OUT == EDT_OUT_DIST && out_sq) out_sq[o] = EDT_INF_I32;
-      }
+      if (OUT == EDT_OUT_I32) out_i[o] = EDT_INF_I32;
+      if (OUT == EDT_OUT_F32 || (OUT == EDT_OUT_DIST && SQ != 2)) out_f[o] = INFINITY;
+      if (OUT == EDT_OUT_DIST && SQ != 0) out_sq[o] = EDT_INF_I32;
     }
     return;
   }
-  using WT = typename std::conditional<INT, long long, double>::type;
+  int cur = t0, prev = t1;
+  GT Gcur = G0;
+  // one entry ahead: index, payload and link of the entry below prev are requested when prev is
+  // entered and consumed only at the next hull move
+  int nxt = EDT_NO_SITE, nxt_link = EDT_NO_SITE;
+  uint32_t nxt_raw = 0;
+  if (prev != EDT_NO_SITE) nxt = (int)link[(IdxT)prev * st];
+  if (nxt != EDT_NO_SITE) {
+    nxt_raw = R::load(in + (IdxT)nxt * st);
+    nxt_link = (int)link[(IdxT)nxt * st];
+  }
+  const double w2s = a.w2 * a.out_scale;  // F64 + EDT_OUT_DIST: the output scale is folded in
+  const double w2 = (OUT == EDT_OUT_DIST) ? w2s : a.w2;
   const float out_mul = a.out_mul;
-  // INT: D and val advance incrementally (exact integers).  float64: both are re-evaluated from
-  // cached per-pair constants with one fma each (an incremental sum would cancel catastrophically
-  // when val falls from far-field magnitudes to ~0 along a run).
-  WT D = 0, Dstep = 0, Gdiff = 0;  // valid while prev != EDT_NO_SITE
-  WT val = 0, e = 0;
+  // INT: D and val advance incrementally (exact integers).  F64: both are re-evaluated from cached
+  // per-pair constants with one fma each (an incremental sum would cancel catastrophically when
+  // val falls from far-field magnitudes to ~0 along a run).
+  WT D = 1, Dstep = 0, Gdiff = 1;
+  int32_t val = 0, e = 0;
   double Fcur = 0.0, curd = 0.0;
-  auto enter = [&](int p) {  // (re)initialise the running quantities for the pair (prev, cur) at p
-    const int dp = p - cur;
+  double pd = u2d((uint32_t)(L - 1));
+  auto enter = [&](int p, GT Aa, BT Ba) {  // pair (prev, cur) at p;  Aa = Gcur - Gprev, Ba = cur - prev
     if (INT) {
-      val = (WT)((int32_t)Gcur - cur * cur + dp * dp);
-      e = (WT)(2 * dp - 1);
+      const int dp = p - cur;
+      val = (int32_t)Gcur - cur * cur + dp * dp;
+      e = 2 * dp - 1;
+      D = 1;
+      Dstep = 0;
       if (prev != EDT_NO_SITE) {
-        Dstep = (WT)(2 * (cur - prev));
-        D = (WT)((int32_t)Gprev - (int32_t)Gcur) + (long long)p * (long long)Dstep;
+        Dstep = (WT)(2 * (int32_t)Ba);
+        D = (WT)p * Dstep - (WT)(int32_t)Aa;
       }
     } else {
       curd = u2d((uint32_t)cur);
       Fcur = ((double)Gcur - curd * curd) * w2;
+      Dstep = 0;
+      Gdiff = 1;  // D stays positive: no entry below
       if (prev != EDT_NO_SITE) {
-        Dstep = (WT)u2d((uint32_t)(2 * (cur - prev)));
-        Gdiff = (WT)((double)Gprev - (double)Gcur);
+        Dstep = (WT)((double)Ba + (double)Ba);
+        Gdiff = (WT)(-(double)Aa);
       }
     }
   };
-  enter(L - 1);
-  double pd = u2d((uint32_t)(L - 1));
+  enter(L - 1, A, Bb);
+#pragma unroll 1
   for (int p = L - 1; p >= 0; --p, o -= st) {
     if (!INT) D = (WT)fma(pd, (double)Dstep, (double)Gdiff);
-    while (prev != EDT_NO_SITE && D <= (WT)0) {  // move down the hull
-      cur = prev;
-      Gcur = Gprev;
-      prev = nxt;
-      if (prev != EDT_NO_SITE) Gprev = makeG(nxt_raw, prev);
-      nxt = (prev != EDT_NO_SITE) ? nxt_link : EDT_NO_SITE;
-      request_nxt();
-      enter(p);
-      if (!INT) D = (WT)fma(pd, (double)Dstep, (double)Gdiff);
+    if (D <= (WT)0) {
+      do {  // move down the hull (D > 0 whenever prev does not exist)
+        const GT Gprev = Gcur - A;
+        cur = prev;
+        Gcur = Gprev;
+        prev = nxt;
+        if (prev != EDT_NO_SITE) {
+          const GT Gp = H::template make<TIn>(nxt_raw, prev, u2d((uint32_t)prev), sG);
+          A = Gcur - Gp;
+          Bb = H::idiff(cur, prev);
+          nxt = nxt_link;
+          if (nxt != EDT_NO_SITE) {
+            nxt_raw = R::load(in + (IdxT)nxt * st);
+            nxt_link = (int)link[(IdxT)nxt * st];
+          }
+        }
+        enter(p, A, Bb);
+        if (!INT) D = (WT)fma(pd, (double)Dstep, (double)Gdiff);
+      } while (D <= (WT)0);
     }
     if (INT) {
-      const int32_t v32 = (int32_t)val;
-      if (OUT == EDT_OUT_I32) {
-        out_i[o] = v32;
-      } else if (OUT == EDT_OUT_F32) {
-        out_f[o] = (float)v32;
-      } else {
+      if (OUT == EDT_OUT_I32) out_i[o] = val;
+      if (OUT == EDT_OUT_F32) out_f[o] = (float)val;
+      if (OUT == EDT_OUT_DIST) {
         // float32 sqrt of the (exact) integer: |rel err| < 1e-7 after the two roundings
-        if (has_out) out_f[o] = sqrtf((float)v32) * out_mul;
-        if (out_sq) out_sq[o] = v32;
+        if (SQ != 2) out_f[o] = sqrtf((float)val) * out_mul;
+        if (SQ != 0) out_sq[o] = val;
       }
       val -= e;
-      e -= (WT)2;
+      e -= 2;
       D -= Dstep;
     } else {
       const double dpd = pd - curd;
-      const double v = fma(w2, dpd * dpd, Fcur);
-      if (OUT == EDT_OUT_I32) {
-        out_i[o] = d2i_exact(v);
-      } else if (OUT == EDT_OUT_F32) {
-        out_f[o] = (float)v;
-      } else {
-        if (has_out) out_f[o] = sqrtf((float)(v * a.out_scale));
-        if (out_sq) out_sq[o] = d2i_exact(v);
-      }
+      const double v = fma(w2, dpd * dpd, Fcur);  // squared distance (x out_scale for EDT_OUT_DIST)
+      if (OUT == EDT_OUT_I32) out_i[o] = d2i_exact(v);
+      if (OUT == EDT_OUT_F32) out_f[o] = (float)v;
+      if (OUT == EDT_OUT_DIST) out_f[o] = sqrtf((float)v);
       pd -= 1.0;
     }
   }
 }
 
-template <typename TIn, typename LinkT, int OUT, bool INT>
+template <typename TIn, typename LinkT, int OUT, int SQ, bool INT>
 static int launch_env(const TIn* in, void* link, void* out, int32_t* out_sq, int axis, int64_t nz, int64_t nx,
                       int64_t ny, double sin, double w2, double out_scale, cudaStream_t st) {
   EnvArgs<TIn, LinkT> a;
@@ -438,9 +456,8 @@ static int launch_env(const TIn* in, void* link, void* out, int32_t* out_sq, int
     a.L = (int)nx;
     nouter = nz;
   }
-  a.sin = sin;
+  a.sG = sin / w2;
   a.w2 = w2;
-  a.inv_w2 = 1.0 / w2;
   a.out_scale = out_scale;
   a.out_mul = (float)sqrt(out_scale);
   int64_t bx = (a.inner + ENV_THREADS - 1) / ENV_THREADS;
@@ -448,26 +465,19 @@ static int launch_env(const TIn* in, void* link, void* out, int32_t* out_sq, int
   dim3 grid((unsigned)bx, (unsigned)nouter);
   ProfScope prof(axis == MFISH_AXIS_Z ? "edt_envelope_z" : "edt_envelope_x", st);
   if (nz * nx * ny < (1ll << 32))
-    edt_envelope_kernel<TIn, LinkT, OUT, INT, uint32_t><<<grid, ENV_THREADS, 0, st>>>(a);
+    edt_envelope_kernel<TIn, LinkT, OUT, SQ, INT, uint32_t><<<grid, ENV_THREADS, 0, st>>>(a);
   else
-    edt_envelope_kernel<TIn, LinkT, OUT, INT, int64_t><<<grid, ENV_THREADS, 0, st>>>(a);
+    edt_envelope_kernel<TIn, LinkT, OUT, SQ, INT, int64_t><<<grid, ENV_THREADS, 0, st>>>(a);
   count_launch(1);
   return check_launch("edt_envelope");
 }
 
-// int_arith: unit weights and max(F) + L^2 < 2^31 (checked by the caller)
-template <typename TIn, int OUT>
-static int launch_env_link(const TIn* in, void* link, bool link16, bool int_arith, void* out, int32_t* out_sq,
-                           int axis, int64_t nz, int64_t nx, int64_t ny, double sin, double w2, double out_scale,
-                           cudaStream_t st) {
-  if (int_arith) {
-    if (link16)
-      return launch_env<TIn, int16_t, OUT, true>(in, link, out, out_sq, axis, nz, nx, ny, sin, w2, out_scale, st);
-    return launch_env<TIn, int32_t, OUT, true>(in, link, out, out_sq, axis, nz, nx, ny, sin, w2, out_scale, st);
-  }
+template <typename TIn, int OUT, int SQ, bool INT>
+static int launch_env_l(const TIn* in, void* link, bool link16, void* out, int32_t* out_sq, int axis, int64_t nz,
+                        int64_t nx, int64_t ny, double sin, double w2, double out_scale, cudaStream_t st) {
   if (link16)
-    return launch_env<TIn, int16_t, OUT, false>(in, link, out, out_sq, axis, nz, nx, ny, sin, w2, out_scale, st);
-  return launch_env<TIn, int32_t, OUT, false>(in, link, out, out_sq, axis, nz, nx, ny, sin, w2, out_scale, st);
+    return launch_env<TIn, int16_t, OUT, SQ, INT>(in, link, out, out_sq, axis, nz, nx, ny, sin, w2, out_scale, st);
+  return launch_env<TIn, int32_t, OUT, SQ, INT>(in, link, out, out_sq, axis, nz, nx, ny, sin, w2, out_scale, st);
 }
 
 static inline int64_t align256(int64_t v) { return (v + 255) & ~int64_t(255); }
@@ -531,12 +541,15 @@ extern "C" int mfish_edt_inplane_u8(const uint8_t* mask_dev, int64_t nz, int64_t
     *f2_kind_host = MFISH_EDT_F2_I32;
     // all-integer hull tests need max(F) + L^2 = (ny-1)^2 + nx^2 below 2^31
     const bool int_arith = (double)(ny - 1) * (ny - 1) + (double)nx * nx < 2147483000.0;
-    return launch_env_link<uint16_t, EDT_OUT_I32>(dy, link, link16, int_arith, f2_out_dev, nullptr, MFISH_AXIS_X, nz,
-                                                  nx, ny, 1.0, 1.0, 1.0, st);
+    if (int_arith)
+      return launch_env_l<uint16_t, EDT_OUT_I32, 0, true>(dy, link, link16, f2_out_dev, nullptr, MFISH_AXIS_X, nz, nx,
+                                                          ny, 1.0, 1.0, 1.0, st);
+    return launch_env_l<uint16_t, EDT_OUT_I32, 0, false>(dy, link, link16, f2_out_dev, nullptr, MFISH_AXIS_X, nz, nx,
+                                                         ny, 1.0, 1.0, 1.0, st);
   }
   *f2_kind_host = MFISH_EDT_F2_F32;
-  return launch_env_link<uint16_t, EDT_OUT_F32>(dy, link, link16, false, f2_out_dev, nullptr, MFISH_AXIS_X, nz, nx,
-                                                ny, wy * wy, wx * wx, 1.0, st);
+  return launch_env_l<uint16_t, EDT_OUT_F32, 0, false>(dy, link, link16, f2_out_dev, nullptr, MFISH_AXIS_X, nz, nx, ny,
+                                                       wy * wy, wx * wx, 1.0, st);
 }
 
 // pass 3 along z.  link_ws_dev: nz*nx*ny*4 bytes of scratch.
@@ -564,17 +577,29 @@ extern "C" int mfish_edt_zpass(const void* f2_dev, int f2_kind, int64_t nz, int6
   const bool link16 = nz <= 32767;
   if (f2_kind == MFISH_EDT_F2_I32) {
     const int32_t* f2 = reinterpret_cast<const int32_t*>(f2_dev);
-    if (iso) {  // keep integers, scale once at the end: dist = sqrt(sq * w^2)
+    if (iso) {  // keep integers, scale once at the end: dist = sqrt(sq) * w
       const double gmax = (double)(nx - 1) * (nx - 1) + (double)(ny - 1) * (ny - 1) + (double)nz * nz;
-      return launch_env_link<int32_t, EDT_OUT_DIST>(f2, link_ws_dev, link16, gmax < 2147483000.0, out_dist_dev,
-                                                    out_sq_dev, MFISH_AXIS_Z, nz, nx, ny, 1.0, 1.0, wz * wz, st);
+      const double sc = wz * wz;
+      if (gmax < 2147483000.0) {
+        if (out_dist_dev && out_sq_dev)
+          return launch_env_l<int32_t, EDT_OUT_DIST, 1, true>(f2, link_ws_dev, link16, out_dist_dev, out_sq_dev,
+                                                              MFISH_AXIS_Z, nz, nx, ny, 1.0, 1.0, sc, st);
+        if (out_sq_dev)
+          return launch_env_l<int32_t, EDT_OUT_DIST, 2, true>(f2, link_ws_dev, link16, nullptr, out_sq_dev,
+                                                              MFISH_AXIS_Z, nz, nx, ny, 1.0, 1.0, sc, st);
+        return launch_env_l<int32_t, EDT_OUT_DIST, 0, true>(f2, link_ws_dev, link16, out_dist_dev, nullptr,
+                                                            MFISH_AXIS_Z, nz, nx, ny, 1.0, 1.0, sc, st);
+      }
+      MFISH_REQUIRE(!out_sq_dev, "edt: volume too large for int32 squared distances");
+      return launch_env_l<int32_t, EDT_OUT_DIST, 0, false>(f2, link_ws_dev, link16, out_dist_dev, nullptr,
+                                                           MFISH_AXIS_Z, nz, nx, ny, 1.0, 1.0, sc, st);
     }
-    return launch_env_link<int32_t, EDT_OUT_DIST>(f2, link_ws_dev, link16, false, out_dist_dev, nullptr,
-                                                  MFISH_AXIS_Z, nz, nx, ny, wx * wx, wz * wz, 1.0, st);
+    return launch_env_l<int32_t, EDT_OUT_DIST, 0, false>(f2, link_ws_dev, link16, out_dist_dev, nullptr, MFISH_AXIS_Z,
+                                                         nz, nx, ny, wx * wx, wz * wz, 1.0, st);
   }
-  return launch_env_link<float, EDT_OUT_DIST>(reinterpret_cast<const float*>(f2_dev), link_ws_dev, link16, false,
-                                              out_dist_dev, nullptr, MFISH_AXIS_Z, nz, nx, ny, 1.0, wz * wz, 1.0,
-                                              st);
+  return launch_env_l<float, EDT_OUT_DIST, 0, false>(reinterpret_cast<const float*>(f2_dev), link_ws_dev, link16,
+                                                     out_dist_dev, nullptr, MFISH_AXIS_Z, nz, nx, ny, 1.0, wz * wz, 1.0,
+                                                     st);
 }
 
 extern "C" int mfish_edt3d_u8(const uint8_t* mask_dev, int64_t nz, int64_t nx, int64_t ny,
