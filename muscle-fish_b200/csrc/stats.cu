@@ -121,46 +121,96 @@ __global__ void qsel_init_kernel(QWs* ws, double q) {
   }
 }
 
-// single thread: locate the bins holding ranks k[0], k[1]; narrow the prefixes; clear hist
+// one block of QBINS/8 threads: locate the bins holding ranks k[0], k[1] (block-wide prefix sum
+// over the histogram), narrow the prefixes, clear the histogram for the next pass
+constexpr int QSCAN_THREADS = QBINS / 8;
+
 template <int PASS>
-__global__ void qsel_scan_kernel(QWs* ws, float* out, double* info) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__global__ void __launch_bounds__(QSCAN_THREADS) qsel_scan_kernel(QWs* ws, float* out, double* info) {
+  __shared__ unsigned long long s_part[2][QSCAN_THREADS];
+  __shared__ unsigned long long s_tot[2];
+  __shared__ int s_bin[2];
+  __shared__ unsigned long long s_before[2];
   QState& s = ws->st;
+  const int t = threadIdx.x;
   const int nb = PASS == 2 ? 1024 : QBINS;
   const bool same = (PASS == 0) || (s.prefix[0] == s.prefix[1]);
-  if (PASS == 0) {
-    unsigned long long n = 0;
-    for (int i = 0; i < nb; ++i) n += ws->hist[0][i];
-    s.n = n;
-    if (n == 0) {
-      out[0] = out[1] = nanf("");
-      info[0] = 0.0;
-      info[1] = 0.0;
-    } else {
-      // numpy method 'linear': virtual index = (n - 1) * q
-      double vi = (double)(n - 1) * s.q;
-      double fl = floor(vi);
-      s.gamma = vi - fl;
-      long long k0 = (long long)fl;
-      k0 = k0 < 0 ? 0 : (k0 > (long long)n - 1 ? (long long)n - 1 : k0);
-      long long k1 = k0 + 1 > (long long)n - 1 ? (long long)n - 1 : k0 + 1;
-      s.k[0] = (unsigned long long)k0;
-      s.k[1] = (unsigned long long)k1;
+  // per-thread sums of 8 consecutive bins, then an inclusive scan of the partials (Hillis-Steele)
+  unsigned long long loc[2][8];
+  for (int j = 0; j < 2; ++j) {
+    const uint32_t* h = ws->hist[(same ? 0 : j)];
+    unsigned long long acc = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int bin = 8 * t + i;
+      const unsigned long long c = bin < nb ? h[bin] : 0ull;
+      loc[j][i] = c;
+      acc += c;
+    }
+    s_part[j][t] = acc;
+  }
+  __syncthreads();
+  for (int o = 1; o < QSCAN_THREADS; o <<= 1) {
+    unsigned long long v0 = t >= o ? s_part[0][t - o] : 0ull;
+    unsigned long long v1 = t >= o ? s_part[1][t - o] : 0ull;
+    __syncthreads();
+    s_part[0][t] += v0;
+    s_part[1][t] += v1;
+    __syncthreads();
+  }
+  if (t == 0) {
+    s_tot[0] = s_part[0][QSCAN_THREADS - 1];
+    s_tot[1] = s_part[1][QSCAN_THREADS - 1];
+    s_bin[0] = s_bin[1] = nb - 1;  // unreachable default when counts are consistent
+    s_before[0] = s_before[1] = 0;
+    if (PASS == 0) {
+      const unsigned long long n = s_tot[0];
+      s.n = n;
+      if (n == 0) {
+        out[0] = out[1] = nanf("");
+        info[0] = 0.0;
+        info[1] = 0.0;
+      } else {
+        // numpy method 'linear': virtual index = (n - 1) * q
+        double vi = (double)(n - 1) * s.q;
+        double fl = floor(vi);
+        s.gamma = vi - fl;
+        long long k0 = (long long)fl;
+        k0 = k0 < 0 ? 0 : (k0 > (long long)n - 1 ? (long long)n - 1 : k0);
+        long long k1 = k0 + 1 > (long long)n - 1 ? (long long)n - 1 : k0 + 1;
+        s.k[0] = (unsigned long long)k0;
+        s.k[1] = (unsigned long long)k1;
+      }
     }
   }
-  if (s.n != 0) {
+  __syncthreads();
+  const unsigned long long n_all = s.n;
+  if (n_all != 0) {
     for (int j = 0; j < 2; ++j) {
-      const uint32_t* h = ws->hist[(same ? 0 : j)];
-      unsigned long long cum = 0;
-      int b = 0;
-      for (; b < nb; ++b) {
-        unsigned long long c = h[b];
-        if (s.k[j] < cum + c) break;
-        cum += c;
+      // this thread owns bins [8t, 8t+8): exclusive prefix = inclusive partial - own sum
+      unsigned long long own = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) own += loc[j][i];
+      unsigned long long cum = s_part[j][t] - own;
+      const unsigned long long k = s.k[j];
+      if (k >= cum && k < cum + own) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (k >= cum && k < cum + loc[j][i]) {
+            s_bin[j] = 8 * t + i;
+            s_before[j] = cum;
+          }
+          cum += loc[j][i];
+        }
       }
-      if (b >= nb) b = nb - 1;  // unreachable when counts are consistent
-      s.k[j] -= cum;
-      s.prefix[j] = PASS == 0 ? (uint32_t)b : ((s.prefix[j] << (PASS == 2 ? 10 : 11)) | (uint32_t)b);
+    }
+  }
+  __syncthreads();
+  if (t == 0 && n_all != 0) {
+    for (int j = 0; j < 2; ++j) {
+      const int bsel = s_bin[j];
+      s.k[j] -= s_before[j];
+      s.prefix[j] = PASS == 0 ? (uint32_t)bsel : ((s.prefix[j] << (PASS == 2 ? 10 : 11)) | (uint32_t)bsel);
     }
     if (PASS == 2) {
       out[0] = key_to_f32(s.prefix[0]);
@@ -169,7 +219,8 @@ __global__ void qsel_scan_kernel(QWs* ws, float* out, double* info) {
       info[1] = (double)s.n;
     }
   }
-  for (int i = 0; i < 2 * QBINS; ++i) (&ws->hist[0][0])[i] = 0;
+  __syncthreads();
+  for (int i = t; i < 2 * QBINS; i += QSCAN_THREADS) (&ws->hist[0][0])[i] = 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -328,11 +379,11 @@ extern "C" int mfish_qsel_scan(int pass, void* ws_dev, float* out_dev, double* i
   cudaStream_t st = as_stream(stream);
   QWs* ws = reinterpret_cast<QWs*>(ws_dev);
   if (pass == 0)
-    qsel_scan_kernel<0><<<1, 32, 0, st>>>(ws, out_dev, info_dev);
+    qsel_scan_kernel<0><<<1, QSCAN_THREADS, 0, st>>>(ws, out_dev, info_dev);
   else if (pass == 1)
-    qsel_scan_kernel<1><<<1, 32, 0, st>>>(ws, out_dev, info_dev);
+    qsel_scan_kernel<1><<<1, QSCAN_THREADS, 0, st>>>(ws, out_dev, info_dev);
   else
-    qsel_scan_kernel<2><<<1, 32, 0, st>>>(ws, out_dev, info_dev);
+    qsel_scan_kernel<2><<<1, QSCAN_THREADS, 0, st>>>(ws, out_dev, info_dev);
   count_launch(1);
   return check_launch("qsel_scan");
 }

@@ -61,6 +61,15 @@ def host_to_device(arr) -> torch.Tensor:
 
 
 _COPY_STREAMS = {}
+_SIDE_STREAMS = {}
+
+
+def _side_stream():
+    dev = torch.cuda.current_device()
+    st = _SIDE_STREAMS.get(dev)
+    if st is None:
+        st = _SIDE_STREAMS[dev] = torch.cuda.Stream()
+    return st
 
 
 def host_to_device_many(arrs):
@@ -264,27 +273,44 @@ def gaussian(vol: Volume, sigma_xyz, mode="nearest") -> torch.Tensor:
 _DEFAULT_CAPACITY = 1 << 20
 
 
-def detect_peaks(cube: torch.Tensor, threshold: float, capacity: int | None = None):
-    """peak_local_max on the cube: returns (raster_idx int64[n], value float32[n]) on the device,
-    unordered.  Raster index is over the reference's (x, y, z, s) cube."""
-    if cube.dim() == 3:
-        cube = cube.unsqueeze(0)
+def _launch_peaks(cube, thr, cap):
     ns, nz, nx, ny = cube.shape
     dev = cube.device
-    thr = max(float(threshold), 0.0)  # threshold_rel = 0.0  =>  max(t, 0 * cube.max()), cube.max() >= 0
+    count = torch.zeros(1, dtype=torch.int32, device=dev)
+    idx = WS.get("pk_idx", (cap,), torch.int64, dev)
+    val = WS.get("pk_val", (cap,), torch.float32, dev)
+    L.check(L.lib().mfish_nms_compact_f32(cube.data_ptr(), ns, nz, nx, ny, thr, idx.data_ptr(), val.data_ptr(),
+                                          count.data_ptr(), cap, _stream()))
+    return idx, val, count
+
+
+def detect_peaks_async(cube: torch.Tensor, threshold: float, capacity: int | None = None):
+    """Launch peak_local_max on the cube; ``finish()`` of the returned handle waits for the count
+    (the only host synchronisation) and returns (raster_idx int64[n], value float32[n]) on the
+    device, unordered.  Raster index is over the reference's (x, y, z, s) cube."""
+    if cube.dim() == 3:
+        cube = cube.unsqueeze(0)
     if float(threshold) < 0:
         raise ValueError("negative thresholds are not supported (reference zero-pads the scale axis)")
+    thr = max(float(threshold), 0.0)  # threshold_rel = 0.0  =>  max(t, 0 * cube.max()), cube.max() >= 0
     cap = int(capacity or max(_DEFAULT_CAPACITY, cube.numel() // 512))
-    count = torch.zeros(1, dtype=torch.int32, device=dev)
-    while True:
-        idx = WS.get("pk_idx", (cap,), torch.int64, dev)
-        val = WS.get("pk_val", (cap,), torch.float32, dev)
-        L.check(L.lib().mfish_nms_compact_f32(cube.data_ptr(), ns, nz, nx, ny, thr, idx.data_ptr(), val.data_ptr(),
-                                              count.data_ptr(), cap, _stream()))
-        n = int(count.item()) & 0xFFFFFFFF
-        if n <= cap:
-            return idx[:n], val[:n]
-        cap = int(n * 1.25) + 1024
+    state = {"h": _launch_peaks(cube, thr, cap), "cap": cap}
+
+    def finish():
+        while True:
+            idx, val, count = state["h"]
+            n = int(count.item()) & 0xFFFFFFFF
+            if n <= state["cap"]:
+                return idx[:n], val[:n]
+            state["cap"] = int(n * 1.25) + 1024
+            state["h"] = _launch_peaks(cube, thr, state["cap"])
+
+    return finish
+
+
+def detect_peaks(cube: torch.Tensor, threshold: float, capacity: int | None = None):
+    """peak_local_max on the cube: (raster_idx int64[n], value float32[n]) on the device, unordered."""
+    return detect_peaks_async(cube, threshold, capacity)()
 
 
 def rank_prune_equal(idx, val, dims_sxyz, cutoff_sq: int):
@@ -354,16 +380,21 @@ def prune_unequal_host(n, s_idx, sigmas, pairs):
     return sig
 
 
-def blob_log(vol: Volume, min_sigma, max_sigma, num_sigma, threshold, overlap=0.5, cube=None):
+def blob_log(vol: Volume, min_sigma, max_sigma, num_sigma, threshold, overlap=0.5, cube=None, before_sync=None):
     """skimage.feature.blob_log on the device.  Returns host float64 array (N, 4) rows
-    [x, y, z, sigma] in peak_local_max order (descending response)."""
+    [x, y, z, sigma] in peak_local_max order (descending response).  ``before_sync`` (optional
+    callable) is run after the filters and the peak detection have been queued and before the host
+    waits for the peak count -- callers queue independent device work there."""
     sigmas = T.sigma_list(min_sigma, max_sigma, num_sigma)
     if cube is None:
         cube = log_cube(vol, sigmas)
     ns = len(sigmas)
     nz, nx, ny = vol.data.shape
     dims = (ns, nx, ny, nz)
-    idx, val = detect_peaks(cube, threshold)
+    peaks = detect_peaks_async(cube, threshold)
+    if before_sync is not None:
+        before_sync()
+    idx, val = peaks()
     if idx.numel() == 0:
         return np.empty((0, 3))
     if ns == 1:
@@ -424,9 +455,9 @@ def blur_at_points(vol: Volume, spots_xyz, sigma_xyz=(3, 3, 0.3), mode="nearest"
     return out.cpu().numpy()
 
 
-def masked_percentile(vol: Volume, mask: torch.Tensor, q_percent: float) -> float:
-    """np.percentile(normalize(img)[mask], q) finished in float64 on the host from the two
-    order statistics the device selects."""
+def masked_percentile_async(vol: Volume, mask: torch.Tensor, q_percent: float):
+    """Launch the masked radix select; the returned ``finish()`` reads the two order statistics and
+    completes np.percentile(normalize(img)[mask], q) in float64 on the host."""
     dev = vol.data.device
     ws = WS.get("qws", (L.QUANTILE_WS_BYTES,), torch.uint8, dev)
     out = torch.empty(2, dtype=torch.float32, device=dev)
@@ -434,16 +465,25 @@ def masked_percentile(vol: Volume, mask: torch.Tensor, q_percent: float) -> floa
     L.check(L.lib().mfish_masked_quantile_f32(vol.data.data_ptr(), mask.data_ptr(), vol.data.numel(),
                                               float(q_percent) / 100.0, ws.data_ptr(), out.data_ptr(),
                                               info.data_ptr(), _stream()))
-    v0, v1 = out.tolist()
-    gamma, n = info.tolist()
-    if n == 0:
-        raise IndexError("percentile of an empty selection (mask selects no voxel)")
-    if vol.minmax is not None:
-        lo, hi = vol.minmax_host()
-        a, b = T.interp01(np.array([v0, v1], dtype=np.float64), lo, hi)
-    else:
-        a, b = float(v0), float(v1)
-    return T.lerp(float(a), float(b), float(gamma))
+
+    def finish():
+        v0, v1 = out.tolist()
+        gamma, n = info.tolist()
+        if n == 0:
+            raise IndexError("percentile of an empty selection (mask selects no voxel)")
+        if vol.minmax is not None:
+            lo, hi = vol.minmax_host()
+            a, b = T.interp01(np.array([v0, v1], dtype=np.float64), lo, hi)
+        else:
+            a, b = float(v0), float(v1)
+        return T.lerp(float(a), float(b), float(gamma))
+
+    return finish
+
+
+def masked_percentile(vol: Volume, mask: torch.Tensor, q_percent: float) -> float:
+    """np.percentile(normalize(img)[mask], q): exact order statistics selected on the device."""
+    return masked_percentile_async(vol, mask, q_percent)()
 
 
 def masked_quantile_distributed(vol: torch.Tensor, mask: torch.Tensor, q: float, reduce_hist):
@@ -568,11 +608,22 @@ def analyze_stack(img_zxy: torch.Tensor, fiber_zxy: torch.Tensor, notnuc_zxy: to
     t = timer or _NoTimer()
     nz, nx, ny = img_zxy.shape
     dims = (1, nx, ny, nz)
+    # everything that does not depend on the spot list is queued first, so the host round trips of
+    # the list handling (count, D2H, decode) overlap the remaining device work
     mm = t.run("minmax", minmax, img_zxy)
     vol = Volume(img_zxy, mm)
     log = WS.get("log_out", img_zxy.shape, torch.float32, img_zxy.device)
     t.run("log3d", log_volume, vol, sigma, log)
-    idx, val = t.run("nms", detect_peaks, log, t_spot)
+    peaks = t.run("nms", detect_peaks_async, log, t_spot)
+    baseline_f = t.run("quantile", masked_percentile_async, vol, fiber_zxy, 25)
+    # the distance transform runs on a side stream, after the streaming kernels above, so that the
+    # small kernels and host round trips of the spot-list handling proceed while it runs
+    main = torch.cuda.current_stream()
+    side = _side_stream()
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        dist = t.run("edt", edt, notnuc_zxy, sampling_xyz)
+    idx, val = peaks()
     spots = np.empty((0, 4))
     if idx.numel():
         cutoff = max(T.prune_cutoff_sq(float(sigma), None, 0.5), 0)
@@ -582,13 +633,14 @@ def analyze_stack(img_zxy: torch.Tensor, fiber_zxy: torch.Tensor, notnuc_zxy: to
         spots = np.stack([x, y, z, np.full(len(x), float(sigma))], axis=1).astype(np.float64)
     if len(spots):
         spots = spots[gather(fiber_zxy, spots) != 0]
-    baseline = t.run("quantile", masked_percentile, vol, fiber_zxy, 25)
     inten = t.run("blur_pts", blur_at_points, vol, spots, (3, 3, 0.3), "nearest")
+    baseline = baseline_f()
     if snr is None and len(spots):
         thresh = np.percentile(inten, 90) / (baseline * np.sqrt(10))
         snr = max(thresh, np.sqrt(10))
     keep = (inten / baseline > snr) if len(spots) else np.zeros(0, bool)
-    dist = t.run("edt", edt, notnuc_zxy, sampling_xyz)
+    main.wait_stream(side)
+    dist.record_stream(main)
     spot_dist = gather(dist, spots[keep]).astype(np.float64) if keep.any() else np.empty(0)
     return {"spots": spots[keep], "spots_masked": spots, "intensity": inten, "baseline": baseline, "snr": snr,
             "spot_dist": spot_dist, "dist": dist}

@@ -77,7 +77,13 @@ def find_spots_snrfilter(img_fish, snr=None, sigma=1., t_spot=0.025, mask=None, 
     ``z_first``) and the per-spot table ``[['spot_id','x','y','z','intensity','SNR'], ...]``.
     """
     vol, m = _prep(img_fish, mask, z_first)
-    spots = D.blob_log(vol, sigma, sigma, 1, t_spot)
+    pending = {}
+
+    def queue_baseline():  # P25 of the fibre voxels does not depend on the spots: queue it early
+        if m is not None:
+            pending["baseline"] = D.masked_percentile_async(vol, m.get(), 25)
+
+    spots = D.blob_log(vol, sigma, sigma, 1, t_spot, before_sync=queue_baseline)
 
     if mask is not None:
         if len(spots) == 0:
@@ -90,8 +96,8 @@ def find_spots_snrfilter(img_fish, snr=None, sigma=1., t_spot=0.025, mask=None, 
         # np.logical_not(None) masks every voxel in the reference, so the percentile below is
         # taken over an empty selection and fails (modules/muscle_fish.py:355-356)
         raise IndexError("find_spots_snrfilter needs a mask: percentile of an empty selection")
-    baseline = D.masked_percentile(vol, m.get(), 25)
     spot_int = D.blur_at_points(vol, spots_masked, (3, 3, 0.3), mode="nearest")
+    baseline = pending["baseline"]()
 
     if snr is None:
         thresh = np.percentile(spot_int, 90) / (baseline * np.sqrt(10))
