@@ -11,6 +11,8 @@
 //                         every voxel is read once and written once.  8 / 12 / 16 / 12 B/voxel for
 //                         ops G / GD / MID / LAST.
 // Taps live in the kernel parameter block (constant bank) so every FFMA has two register sources.
+#include <stdlib.h>
+
 #include <algorithm>
 #include <type_traits>
 
@@ -391,6 +393,260 @@ __global__ void __launch_bounds__(STHREADS) conv_strided_generic_kernel(const SG
 }
 
 // --------------------------------------------------------------------------------------------
+// fused y + z pass of the LoG: in -> (C = Gz Gy in, F = (Dz Gy + Gz Dy) in), R4 + W8 bytes per voxel
+// (the separate y and z passes move 12 + 16).
+//
+// One block owns a 512-voxel y segment of one x row and walks z.  Each input plane's row segment
+// (+ halo) is brought into shared memory by the TMA unit (cp.async.bulk + mbarrier, YZ_STAGES
+// planes in flight, issued by one elected thread), normalised in place, convolved along y from a
+// register window (2 outputs per thread), and pushed into a (2R+1)-deep register ring of packed
+// float2 values; the z convolution runs on the ring with packed FFMA2 / FADD2.
+// --------------------------------------------------------------------------------------------
+constexpr int YZ_THREADS = 256;
+constexpr int YZ_SEG = 2 * YZ_THREADS;
+constexpr int YZ_STAGES = 8;
+
+__device__ __forceinline__ float2 fma2(float a, float2 b, float2 c) {
+  float2 aa = make_float2(a, a);
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&aa);
+  unsigned long long rb = *reinterpret_cast<unsigned long long*>(&b);
+  unsigned long long rc = *reinterpret_cast<unsigned long long*>(&c);
+  unsigned long long rd;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 mul2(float a, float2 b) {
+  float2 aa = make_float2(a, a);
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&aa);
+  unsigned long long rb = *reinterpret_cast<unsigned long long*>(&b);
+  unsigned long long rd;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a);
+  unsigned long long rb = *reinterpret_cast<unsigned long long*>(&b);
+  unsigned long long rd;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2*>(&rd);
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// TMA bulk copy global -> shared, completion signalled on the mbarrier (16-byte aligned, size % 16 == 0)
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, unsigned bytes,
+                                            unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int R>
+struct YZArgs {
+  const float* in;
+  float* outC;
+  float* outF;
+  int nz, nx, ny, nseg, bmode;
+  const float* mm;
+  Taps<R> t;
+};
+
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Stages cycle through full (TMA bytes landed) / empty (all warps have copied their window to
+// registers) mbarriers; there is no block-wide barrier in the plane loop.  Thread 0 doubles as the
+// TMA producer: at step p it refills the stage of step p - 1, which the other warps have normally
+// released long before, so its wait is free.
+constexpr int YZ_CONSUMER_WARPS = YZ_THREADS / 32;
+
+// Front half of one step, shared by all ring positions (kept out of line: the plane loop is
+// unrolled by the ring depth and must stay inside the instruction cache): wait for the stage, write
+// the row-end boundary extension if this warp needs it, copy the window to registers, release the
+// stage, normalise, y pass.  Returns (G*in, G*in', D*in, D*in') for the thread's two outputs.
+template <int R>
+__device__ __noinline__ float4 yz_front(float* row, unsigned long long* full_bar, unsigned long long* empty_bar,
+                                        unsigned parity, int wbeg, int dstL, int srcL, int dstR, int srcR, float sc,
+                                        float noff, const Taps<R>* __restrict__ taps) {
+  constexpr int W = 2 * R + 1;
+  mbar_wait(full_bar, parity);
+  if (dstL >= 0) row[dstL] = row[srcL];
+  if (dstR >= 0) row[dstR] = row[srcR];
+  __syncwarp();
+  float w[W + 1];
+  const float2* wp = reinterpret_cast<const float2*>(row + wbeg);
+#pragma unroll
+  for (int j = 0; j < (W + 1) / 2; ++j) {
+    const float2 v = wp[j];
+    w[2 * j] = v.x;
+    w[2 * j + 1] = v.y;
+  }
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(empty_bar);  // this warp no longer needs the stage
+#pragma unroll
+  for (int j = 0; j <= W; ++j) w[j] = fmaf(w[j], sc, noff);  // su.normalize_image folded into the load
+  const float tg0 = taps->g[0], td0 = taps->d[0];
+  float g0 = tg0 * w[R], g1 = tg0 * w[R + 1];
+  float d0 = td0 * w[R], d1 = td0 * w[R + 1];
+#pragma unroll
+  for (int k = 1; k <= R; ++k) {
+    const float tg = taps->g[k], td = taps->d[k];
+    const float s0 = w[R - k] + w[R + k];
+    const float s1 = w[R + 1 - k] + w[R + 1 + k];
+    g0 = fmaf(tg, s0, g0);
+    g1 = fmaf(tg, s1, g1);
+    d0 = fmaf(td, s0, d0);
+    d1 = fmaf(td, s1, d1);
+  }
+  return make_float4(g0, g1, d0, d1);
+}
+
+// Producer step (one thread per block, out of line for the same reason): once every warp has
+// released the stage of step q, fetch the row segment of step q + YZ_STAGES into it.
+__device__ __noinline__ void yz_refill(const float* in_row_lo, int64_t plane, int nz, int bmode, int R, int q, int P,
+                                       float* stage_dst0, int stage_floats, unsigned long long* full,
+                                       unsigned long long* empty, unsigned bytes, bool wait_empty) {
+  const int p = wait_empty ? q + YZ_STAGES : q;
+  if (p >= P) return;
+  const int stg = p % YZ_STAGES;
+  if (wait_empty) mbar_wait(&empty[stg], (unsigned)((q / YZ_STAGES) & 1));
+  const int zs = bmode == MFISH_BOUNDARY_NEAREST ? bmap<MFISH_BOUNDARY_NEAREST>(p - R, nz)
+                                                 : bmap<MFISH_BOUNDARY_REFLECT>(p - R, nz);
+  mbar_expect_tx(&full[stg], bytes);
+  tma_load_1d(stage_dst0 + (size_t)stg * stage_floats, in_row_lo + (int64_t)zs * plane, bytes, &full[stg]);
+}
+
+template <int R>
+__global__ void __launch_bounds__(YZ_THREADS, 2) conv_yz_kernel(const __grid_constant__ YZArgs<R> a) {
+  constexpr int RP = (R + 3) & ~3;  // halo rounded up to 16 bytes
+  constexpr int W = 2 * R + 1;      // ring depth = taps
+  constexpr int ROW = YZ_SEG + 2 * RP;
+  __shared__ __align__(128) float s_in[YZ_STAGES][ROW];
+  __shared__ __align__(8) unsigned long long s_full[YZ_STAGES];
+  __shared__ __align__(8) unsigned long long s_empty[YZ_STAGES];
+
+  const int tid = threadIdx.x;
+  const int x = blockIdx.x / a.nseg;
+  const int seg0 = (blockIdx.x - x * a.nseg) * YZ_SEG;
+  const int ny = a.ny, nz = a.nz, nx = a.nx;
+  const int row0 = seg0 - RP;  // y of smem index 0
+  const int lo = max(row0, 0), hi = min(seg0 + YZ_SEG + RP, ny);
+  const int P = nz + 2 * R;  // planes walked: source plane of step p is bmap(p - R)
+  const int bmode = a.bmode;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < YZ_STAGES; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], YZ_CONSUMER_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const unsigned bytes = (unsigned)(hi - lo) * 4u;
+  const float* in_row_lo = a.in + (int64_t)x * ny + lo;  // + zs * plane
+  const int64_t plane = (int64_t)nx * ny;
+  float* stage_dst0 = &s_in[0][lo - row0];
+  if (tid == 0) {
+    for (int p = 0; p < YZ_STAGES; ++p)
+      yz_refill(in_row_lo, plane, nz, bmode, R, p, P, stage_dst0, ROW, s_full, s_empty, bytes, false);
+  }
+
+  float mn, sc;
+  bool degen;
+  load_norm(a.mm, mn, sc, degen);
+  float noff = -mn * sc;  // normalised = v * sc + noff
+  if (degen) {            // constant image: np.interp gives 1 everywhere
+    sc = 0.f;
+    noff = 1.f;
+  }
+  const int y0 = seg0 + 2 * tid;
+  const bool active = y0 < ny;  // ny % 4 == 0, so a float2 never straddles the row end
+  // window of this thread: smem indices [wbeg, wbeg + W].  In a row-end segment the TMA fetch stops at
+  // the row end; the warps whose windows reach past it write the boundary extension (R values,
+  // taken from the fetched range) into the stage themselves before loading their windows.
+  const int wbeg = 2 * tid + (RP - R);
+  const int lane = tid & 31;
+  const int wfirst = 2 * (tid - lane) + (RP - R);          // first smem index the warp reads
+  const int wlast = 2 * (tid - lane + 31) + (RP - R) + W;  // last one
+  int dstL = -1, srcL = 0, dstR = -1, srcR = 0;
+  if ((lo != row0) && (row0 + wfirst < lo) && lane < R) {
+    const int y = lo - 1 - lane;
+    const int yy = bmode == MFISH_BOUNDARY_NEAREST ? bmap1<MFISH_BOUNDARY_NEAREST>(y, ny)
+                                                   : bmap1<MFISH_BOUNDARY_REFLECT>(y, ny);
+    dstL = y - row0;
+    srcL = yy - row0;
+  }
+  if ((hi != seg0 + YZ_SEG + RP) && (row0 + wlast >= hi) && (row0 + wfirst < hi + R) && lane < R) {
+    const int y = hi + lane;
+    const int yy = bmode == MFISH_BOUNDARY_NEAREST ? bmap1<MFISH_BOUNDARY_NEAREST>(y, ny)
+                                                   : bmap1<MFISH_BOUNDARY_REFLECT>(y, ny);
+    dstR = y - row0;
+    srcR = yy - row0;
+  }
+  float2 A2[W], B2[W];
+#pragma unroll
+  for (int i = 0; i < W; ++i) A2[i] = B2[i] = make_float2(0.f, 0.f);
+  float2* __restrict__ outC = reinterpret_cast<float2*>(a.outC + ((int64_t)x * ny + y0));
+  float2* __restrict__ outF = reinterpret_cast<float2*>(a.outF + ((int64_t)x * ny + y0));
+  const int64_t plane2 = (int64_t)nx * ny / 2;  // float2 elements per z plane
+
+  for (int p0 = 0; p0 < P; p0 += W) {
+#pragma unroll
+    for (int u = 0; u < W; ++u) {
+      const int p = p0 + u;
+      if (p < P) {
+        const int stg = p % YZ_STAGES;
+        const float4 gd = yz_front<R>(s_in[stg], &s_full[stg], &s_empty[stg], (unsigned)((p / YZ_STAGES) & 1), wbeg,
+                                      dstL, srcL, dstR, srcR, sc, noff, &a.t);
+        A2[u] = make_float2(gd.x, gd.y);
+        B2[u] = make_float2(gd.z, gd.w);
+        if (tid == 0 && p >= 1)
+          yz_refill(in_row_lo, plane, nz, bmode, R, p - 1, P, stage_dst0, ROW, s_full, s_empty, bytes, true);
+        // z pass on the ring: the centre of the window that ends at step p is step p - R
+        if (p >= 2 * R && active) {
+          const int c = (u - R + W) % W;
+          float2 C = mul2(a.t.g[0], A2[c]);
+          float2 F = fma2(a.t.g[0], B2[c], mul2(a.t.d[0], A2[c]));
+#pragma unroll
+          for (int k = 1; k <= R; ++k) {
+            const float2 sA = add2(A2[(c - k + W) % W], A2[(c + k) % W]);
+            const float2 sB = add2(B2[(c - k + W) % W], B2[(c + k) % W]);
+            C = fma2(a.t.g[k], sA, C);
+            F = fma2(a.t.d[k], sA, F);
+            F = fma2(a.t.g[k], sB, F);
+          }
+          const int64_t o = (int64_t)(p - 2 * R) * plane2;
+          outC[o] = C;
+          outF[o] = F;
+        }
+      }
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------
 // host-side dispatch
 // --------------------------------------------------------------------------------------------
 template <int R>
@@ -613,6 +869,31 @@ int run_pass(const PassDesc& p) {
   return launch_generic(p);
 }
 
+// The fused, TMA-staged y+z pass is correct (same parity tests) but measured 2.9-3.4 ms against 2.93 ms for
+// the separate y and z kernels on the 2048x2048x100 stack: 125 registers cap it at 16 warps per SM and the
+// ring-unrolled body (50-98 KB of SASS) misses the instruction cache.  It stays opt-in until it wins.
+static const bool g_disable_fused_yz = getenv("MFISH_FUSED_YZ") == nullptr;
+
+template <int R>
+static int launch_yz(const float* in, float* outC, float* outF, int64_t nz, int64_t nx, int64_t ny, const double* g,
+                     const double* d, int radius, const float* mm, cudaStream_t st) {
+  YZArgs<R> a;
+  a.in = in;
+  a.outC = outC;
+  a.outF = outF;
+  a.nz = (int)nz;
+  a.nx = (int)nx;
+  a.ny = (int)ny;
+  a.nseg = (int)((ny + YZ_SEG - 1) / YZ_SEG);
+  a.bmode = MFISH_BOUNDARY_REFLECT;
+  a.mm = mm;
+  fill_taps<R>(a.t, g, d, radius);
+  ProfScope prof("conv_yz_fused", st);
+  conv_yz_kernel<R><<<(unsigned)(nx * a.nseg), YZ_THREADS, 0, st>>>(a);
+  count_launch(1);
+  return check_launch("conv_yz");
+}
+
 // Host-side taps, identical formula to muscle-fish_b200/taps.py (scipy _gaussian_kernel1d).
 static void host_taps(double sigma, std::vector<double>& g, std::vector<double>& d, int& radius) {
   radius = (int)(4.0 * sigma + 0.5);
@@ -694,15 +975,27 @@ extern "C" int mfish_log3d_f32(const float* in_dev, float* out_dev, float* tmp1_
   int radius;
   host_taps(sigma, g, d, radius);
   cudaStream_t st = as_stream(stream);
-  // y: in -> (A = G in, B = D in)
-  PassDesc py{in_dev, nullptr, out_dev, tmp1_dev, nz, nx, ny, MFISH_AXIS_Y, g.data(), d.data(), radius,
-              MFISH_BOUNDARY_REFLECT, MFISH_CONV_GD, 1.0f, norm_minmax_dev, st};
-  int rc = run_pass(py);
-  if (rc != MFISH_OK) return rc;
-  // z: (A, B) -> (C = G A, F = D A + G B)
-  PassDesc pz{out_dev, tmp1_dev, tmp2_dev, tmp3_dev, nz, nx, ny, MFISH_AXIS_Z, g.data(), d.data(), radius,
-              MFISH_BOUNDARY_REFLECT, MFISH_CONV_MID, 1.0f, nullptr, st};
-  rc = run_pass(pz);
+  int rc = MFISH_ERR_UNSUPPORTED;
+  // fused y+z pass (TMA staged) when the rows allow 16-byte bulk copies
+  const bool fuse_ok = (ny % 4 == 0) && ny >= 32 && aligned16(in_dev) && aligned16(tmp2_dev) && aligned16(tmp3_dev) &&
+                       nz < (1 << 20) && nx * ((ny + YZ_SEG - 1) / YZ_SEG) < (1ll << 31) && !g_disable_fused_yz;
+  if (fuse_ok && radius == 8)
+    rc = launch_yz<8>(in_dev, tmp2_dev, tmp3_dev, nz, nx, ny, g.data(), d.data(), radius, norm_minmax_dev, st);
+  else if (fuse_ok && radius == 4)
+    rc = launch_yz<4>(in_dev, tmp2_dev, tmp3_dev, nz, nx, ny, g.data(), d.data(), radius, norm_minmax_dev, st);
+  else if (fuse_ok && radius == 6)
+    rc = launch_yz<6>(in_dev, tmp2_dev, tmp3_dev, nz, nx, ny, g.data(), d.data(), radius, norm_minmax_dev, st);
+  if (rc == MFISH_ERR_UNSUPPORTED) {
+    // y: in -> (A = G in, B = D in)
+    PassDesc py{in_dev, nullptr, out_dev, tmp1_dev, nz, nx, ny, MFISH_AXIS_Y, g.data(), d.data(), radius,
+                MFISH_BOUNDARY_REFLECT, MFISH_CONV_GD, 1.0f, norm_minmax_dev, st};
+    rc = run_pass(py);
+    if (rc != MFISH_OK) return rc;
+    // z: (A, B) -> (C = G A, F = D A + G B)
+    PassDesc pz{out_dev, tmp1_dev, tmp2_dev, tmp3_dev, nz, nx, ny, MFISH_AXIS_Z, g.data(), d.data(), radius,
+                MFISH_BOUNDARY_REFLECT, MFISH_CONV_MID, 1.0f, nullptr, st};
+    rc = run_pass(pz);
+  }
   if (rc != MFISH_OK) return rc;
   // x: (C, F) -> -sigma^2 (D C + G F)
   PassDesc px{tmp2_dev, tmp3_dev, out_dev, nullptr, nz, nx, ny, MFISH_AXIS_X, g.data(), d.data(), radius,
