@@ -30,6 +30,27 @@ import torch.distributed as dist
 from . import taps as T
 
 
+# optional wall-clock phase accounting (tools/bench_slab.py --phases)
+PHASES = None
+
+
+class _phase:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if PHASES is not None:
+            torch.cuda.synchronize()
+            import time
+            self.t0 = time.perf_counter()
+
+    def __exit__(self, *exc):
+        if PHASES is not None:
+            import time
+            torch.cuda.synchronize()
+            PHASES[self.name] = PHASES.get(self.name, 0.0) + time.perf_counter() - self.t0
+
+
 # ------------------------------------------------------------------------------ partitioning
 def shard_stacks(n_stacks: int, rank: int, world: int):
     """Stack indices of this rank: round-robin, like one SLURM job per image."""
@@ -217,29 +238,34 @@ def slab_find_spots_snrfilter(img_slab: torch.Tensor, mask_slab: torch.Tensor, l
     dev = img_slab.device
     nz, nx, ny = lay.nz, lay.nx, lay.ny
     # 1. global min / max
-    mm = ops.minmax(img_slab).clone()
-    lo_hi = mm.to(torch.float32)
-    lo_t, hi_t = lo_hi[0:1].clone(), lo_hi[1:2].clone()
-    dist.all_reduce(lo_t, op=dist.ReduceOp.MIN, group=group)
-    dist.all_reduce(hi_t, op=dist.ReduceOp.MAX, group=group)
-    mm = torch.cat([lo_t, hi_t])
-    lo_v, hi_v = float(lo_t.item()), float(hi_t.item())
+    with _phase("minmax"):
+        mm = ops.minmax(img_slab).clone()
+        lo_hi = mm.to(torch.float32)
+        lo_t, hi_t = lo_hi[0:1].clone(), lo_hi[1:2].clone()
+        dist.all_reduce(lo_t, op=dist.ReduceOp.MIN, group=group)
+        dist.all_reduce(hi_t, op=dist.ReduceOp.MAX, group=group)
+        mm = torch.cat([lo_t, hi_t])
+        lo_v, hi_v = float(lo_t.item()), float(hi_t.item())
     # 2. halo of raw input: r planes for the z filter pass + 1 plane of LoG for the NMS
     radius = T.gaussian_radius(sigma)
-    ext, lo, hi = exchange_halo(img_slab, radius + 1, lay, group)
+    with _phase("halo"):
+        ext, lo, hi = exchange_halo(img_slab, radius + 1, lay, group)
     # 3. LoG on the extended slab (planes within `radius` of an interior cut are contaminated by the
     #    boundary rule and are not used); reflect applies only at the global faces
-    log_ext = ops.log(ext, mm, sigma)
+    with _phase("log"):
+        log_ext = ops.log(ext, mm, sigma)
     a = radius if lo else 0
     b = log_ext.shape[0] - (radius if hi else 0)
-    zxy, val = ops.peaks(log_ext[a:b], t_spot)
+    with _phase("peaks"):
+        zxy, val = ops.peaks(log_ext[a:b], t_spot)
     zg = zxy[:, 0] + a - lo + lay.z0
     own = (zg >= lay.z0) & (zg < lay.z1)
     mine = np.stack([zg[own], zxy[own, 1], zxy[own, 2]], axis=1).astype(np.int64)
     vals = np.asarray(val)[own].astype(np.float32)
     # 4. all-gather the peak lists, prune identically everywhere
-    gathered = [None] * lay.world
-    dist.all_gather_object(gathered, (mine, vals), group=group)
+    with _phase("gather_peaks"):
+        gathered = [None] * lay.world
+        dist.all_gather_object(gathered, (mine, vals), group=group)
     all_zxy = np.concatenate([g[0] for g in gathered], axis=0) if gathered else mine
     all_val = np.concatenate([g[1] for g in gathered], axis=0)
     empty = {"spots": np.empty((0, 4)), "spots_masked": np.empty((0, 4)), "intensity": np.empty(0),
@@ -247,7 +273,8 @@ def slab_find_spots_snrfilter(img_slab: torch.Tensor, mask_slab: torch.Tensor, l
     if len(all_zxy) == 0:
         return empty
     cutoff = max(T.prune_cutoff_sq(float(sigma), None, 0.5), 0)
-    raster_ranked, alive = ops.rank_prune(all_zxy, all_val, (nz, nx, ny), cutoff)
+    with _phase("prune"):
+        raster_ranked, alive = ops.rank_prune(all_zxy, all_val, (nz, nx, ny), cutoff)
     raster_ranked = raster_ranked[alive]
     z = raster_ranked % nz
     t = raster_ranked // nz
@@ -257,9 +284,10 @@ def slab_find_spots_snrfilter(img_slab: torch.Tensor, mask_slab: torch.Tensor, l
     ownz = (z >= lay.z0) & (z < lay.z1)
     local = np.stack([z[ownz] - lay.z0, x[ownz], y[ownz]], axis=1)
     inmask = np.zeros(len(z), dtype=np.int32)
-    if ownz.any():
-        inmask[ownz] = (ops.gather_u8(mask_slab, local) != 0).astype(np.int32)
-    inmask = _allreduce_np(inmask, dev, group=group) > 0
+    with _phase("mask"):
+        if ownz.any():
+            inmask[ownz] = (ops.gather_u8(mask_slab, local) != 0).astype(np.int32)
+        inmask = _allreduce_np(inmask, dev, group=group) > 0
     x, y, z = x[inmask], y[inmask], z[inmask]
     spots = np.stack([x, y, z, np.full(len(x), float(sigma))], axis=1).astype(np.float64)
     if len(spots) == 0:
@@ -267,7 +295,8 @@ def slab_find_spots_snrfilter(img_slab: torch.Tensor, mask_slab: torch.Tensor, l
     # 6. P25 baseline over the (global) mask
     def reduce_hist(h):
         dist.all_reduce(h, op=dist.ReduceOp.SUM, group=group)
-    v0, v1, gamma, n = ops.masked_quantile(img_slab, mask_slab, 0.25, reduce_hist)
+    with _phase("quantile"):
+        v0, v1, gamma, n = ops.masked_quantile(img_slab, mask_slab, 0.25, reduce_hist)
     if n == 0:
         raise IndexError("percentile of an empty selection (mask selects no voxel)")
     a01 = T.interp01(np.array([v0, v1], dtype=np.float64), lo_v, hi_v)
@@ -275,10 +304,11 @@ def slab_find_spots_snrfilter(img_slab: torch.Tensor, mask_slab: torch.Tensor, l
     # 7. blurred intensity at the spots: owners evaluate on their extended raw slab
     ownz = (z >= lay.z0) & (z < lay.z1)
     inten = np.zeros(len(z), dtype=np.float64)
-    if ownz.any():
-        loc = np.stack([z[ownz] - lay.z0 + lo, x[ownz], y[ownz]], axis=1)
-        inten[ownz] = ops.blur_at_points(ext, mm, loc, (3, 3, 0.3))
-    inten = _allreduce_np(inten, dev, group=group)
+    with _phase("blur"):
+        if ownz.any():
+            loc = np.stack([z[ownz] - lay.z0 + lo, x[ownz], y[ownz]], axis=1)
+            inten[ownz] = ops.blur_at_points(ext, mm, loc, (3, 3, 0.3))
+        inten = _allreduce_np(inten, dev, group=group)
     if snr is None:
         thresh = np.percentile(inten, 90) / (baseline * np.sqrt(10))
         snr = max(thresh, np.sqrt(10))
@@ -292,9 +322,12 @@ def slab_edt(notnuc_slab: torch.Tensor, lay: SlabLayout, sampling_xyz=(1.0, 1.0,
     z-slab decomposed mask.  Returns the distance map in x-slab layout ``[nz][nx_local][ny]`` (or
     back in z-slab layout when ``back_to_z``)."""
     ops = ops or DeviceOps()
-    f2, kind = ops.edt_inplane(notnuc_slab, sampling_xyz)
-    f2x = repartition_z_to_x(f2, lay, group)
-    dx = ops.edt_zpass(f2x, kind, sampling_xyz)
+    with _phase("edt_inplane"):
+        f2, kind = ops.edt_inplane(notnuc_slab, sampling_xyz)
+    with _phase("edt_all_to_all"):
+        f2x = repartition_z_to_x(f2, lay, group)
+    with _phase("edt_zpass"):
+        dx = ops.edt_zpass(f2x, kind, sampling_xyz)
     return repartition_x_to_z(dx, lay, group) if back_to_z else dx
 
 

@@ -108,8 +108,12 @@ def make_config(name, **over):
     return make_stack(**kw)
 
 
-def make_stack_device(shape, n_spots, n_nuclei, seed, device="cuda", z_first=True):
+def make_stack_device(shape, n_spots, n_nuclei, seed, device="cuda", z_first=True, z_range=None):
     """Same distribution drawn on the GPU with torch (bench inputs only).
+
+    ``z_range=(z0, z1)`` draws only those planes of the stack (one z-slab of a mosaic): spots,
+    fibre and nuclei are the global ones, so neighbouring slabs are consistent; only the noise
+    stream is per-slab.
 
     Returns float32 image and uint8 masks as torch tensors on ``device`` in
     (z, x, y) order when ``z_first`` else (x, y, z).  Spot/nucleus centres
@@ -119,15 +123,19 @@ def make_stack_device(shape, n_spots, n_nuclei, seed, device="cuda", z_first=Tru
     import torch
 
     X, Y, Z = shape
+    za, zb = (0, Z) if z_range is None else (int(z_range[0]), int(z_range[1]))
+    ZL = zb - za
     rng = np.random.default_rng(seed)
     g = torch.Generator(device=device)
-    g.manual_seed(int(seed))
-    img = torch.empty((Z, X, Y), dtype=torch.float32, device=device)
+    g.manual_seed(int(seed) + 7919 * za)
+    img = torch.empty((ZL, X, Y), dtype=torch.float32, device=device)
     img.normal_(100.0, 10.0, generator=g)
     y0, y1, z0, z1 = _fiber_bounds(shape)
-    fiber = torch.zeros((Z, X, Y), dtype=torch.uint8, device=device)
-    fiber[z0:z1, :, y0:y1] = 1
-    img[z0:z1, :, y0:y1] += 60.0
+    fiber = torch.zeros((ZL, X, Y), dtype=torch.uint8, device=device)
+    fz0, fz1 = max(z0, za) - za, min(z1, zb) - za
+    if fz1 > fz0:
+        fiber[fz0:fz1, :, y0:y1] = 1
+        img[fz0:fz1, :, y0:y1] += 60.0
 
     mxy = min(10, max(2, (y1 - y0) // 8))
     mz = min(3, max(1, (z1 - z0) // 8))
@@ -136,6 +144,9 @@ def make_stack_device(shape, n_spots, n_nuclei, seed, device="cuda", z_first=Tru
     cz = rng.uniform(z0 + mz, z1 - mz, n_spots)
     amp = rng.uniform(300.0, 1500.0, n_spots)
     hx, hz = 6, 3
+    near = (cz >= za - hz - 1) & (cz <= zb + hz + 1)  # spots that can touch this slab
+    cx, cy, cz, amp = cx[near], cy[near], cz[near], amp[near]
+    n_spots = int(near.sum())
     flat = img.view(-1)
     ox = torch.arange(-hx, hx + 1, device=device)
     oz = torch.arange(-hz, hz + 1, device=device)
@@ -154,14 +165,14 @@ def make_stack_device(shape, n_spots, n_nuclei, seed, device="cuda", z_first=Tru
         gz = torch.exp(-0.5 * ((zs - tcz[:, None]) / SPOT_SIGMA_Z) ** 2)
         gx = gx * ((xs >= 0) & (xs < X))
         gy = gy * ((ys >= 0) & (ys < Y))
-        gz = gz * ((zs >= 0) & (zs < Z))
+        gz = gz * ((zs >= za) & (zs < zb))
         val = (tam[:, None, None, None] * gz[:, :, None, None] * gx[:, None, :, None]
                * gy[:, None, None, :]).to(torch.float32)
-        lin = ((zs.clamp(0, Z - 1)[:, :, None, None] * X + xs.clamp(0, X - 1)[:, None, :, None]) * Y
+        lin = (((zs - za).clamp(0, ZL - 1)[:, :, None, None] * X + xs.clamp(0, X - 1)[:, None, :, None]) * Y
                + ys.clamp(0, Y - 1)[:, None, None, :])
         flat.index_add_(0, lin.reshape(-1), val.reshape(-1))
 
-    nuc = torch.zeros((Z, X, Y), dtype=torch.uint8, device=device)
+    nuc = torch.zeros((ZL, X, Y), dtype=torch.uint8, device=device)
     a, b, c = NUC_SEMI
     a = min(a, X / 4.0)
     b = min(b, (y1 - y0) / 4.0)
@@ -172,12 +183,14 @@ def make_stack_device(shape, n_spots, n_nuclei, seed, device="cuda", z_first=Tru
     for i in range(n_nuclei):
         xa, xb = max(0, int(ncx[i] - a) - 1), min(X, int(ncx[i] + a) + 2)
         ya, yb = max(0, int(ncy[i] - b) - 1), min(Y, int(ncy[i] + b) + 2)
-        za, zb = max(0, int(ncz[i] - c) - 1), min(Z, int(ncz[i] + c) + 2)
+        na, nb = max(za, int(ncz[i] - c) - 1), min(zb, int(ncz[i] + c) + 2)
+        if nb <= na:
+            continue
         gx = ((torch.arange(xa, xb, device=device) - ncx[i]) / a) ** 2
         gy = ((torch.arange(ya, yb, device=device) - ncy[i]) / b) ** 2
-        gz = ((torch.arange(za, zb, device=device) - ncz[i]) / c) ** 2
+        gz = ((torch.arange(na, nb, device=device) - ncz[i]) / c) ** 2
         inside = (gz[:, None, None] + gx[None, :, None] + gy[None, None, :]) <= 1.0
-        nuc[za:zb, xa:xb, ya:yb] |= inside.to(torch.uint8)
+        nuc[na - za:nb - za, xa:xb, ya:yb] |= inside.to(torch.uint8)
 
     if not z_first:
         img = img.permute(1, 2, 0).contiguous()
