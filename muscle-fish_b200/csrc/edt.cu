@@ -289,19 +289,9 @@ __global__ void __launch_bounds__(ENV_THREADS) edt_envelope_kernel(const EnvArgs
     LinkT* __restrict__ plink = link;
     const TIn* __restrict__ pnext = in + (IdxT)ENV_BATCH * st;
     double qd = 0.0;
-#pragma unroll 1
-    for (int q0 = 0; q0 < L; q0 += ENV_BATCH) {
-#pragma unroll
-      for (int u = 0; u < ENV_BATCH; ++u) s_raw[u][threadIdx.x] = nb[u];
-#pragma unroll
-      for (int u = 0; u < ENV_BATCH; ++u)
-        nb[u] = (q0 + ENV_BATCH + u < L) ? R::load(pnext + (IdxT)u * st) : R::kNone;
-      pnext += (IdxT)ENV_BATCH * st;
-      const int qe = min(L, q0 + ENV_BATCH);
-#pragma unroll 1
-      for (int q = q0; q < qe; ++q, plink += st, qd += 1.0) {
-        const uint32_t rq = s_raw[q - q0][threadIdx.x];
-        if (rq == R::kNone) continue;
+    // one hull step for site q with payload rq (skipped for "no site")
+    auto step = [&](uint32_t rq, int q) {
+      if (rq != R::kNone) {
         const GT Gq = H::template make<TIn>(rq, q, qd, sG);
         GT dG = Gq - G0;
         BT dq = H::idiff(q, t0);
@@ -326,22 +316,47 @@ __global__ void __launch_bounds__(ENV_THREADS) edt_envelope_kernel(const EnvArgs
         A = dG;
         Bb = dq;
       }
+      plink += st;
+      qd += 1.0;
+    };
+    int q0 = 0;
+#pragma unroll 1
+    for (; q0 + 2 * ENV_BATCH <= L; q0 += ENV_BATCH) {  // full batch, and a full batch to prefetch
+#pragma unroll
+      for (int u = 0; u < ENV_BATCH; ++u) s_raw[u][threadIdx.x] = nb[u];
+#pragma unroll
+      for (int u = 0; u < ENV_BATCH; ++u) nb[u] = R::load(pnext + (IdxT)u * st);
+      pnext += (IdxT)ENV_BATCH * st;
+#pragma unroll 4
+      for (int u = 0; u < ENV_BATCH; ++u) step(s_raw[u][threadIdx.x], q0 + u);
+    }
+#pragma unroll 1
+    for (; q0 < L; q0 += ENV_BATCH) {  // the last one or two batches, bounds-checked
+#pragma unroll
+      for (int u = 0; u < ENV_BATCH; ++u) s_raw[u][threadIdx.x] = nb[u];
+#pragma unroll
+      for (int u = 0; u < ENV_BATCH; ++u)
+        nb[u] = (q0 + ENV_BATCH + u < L) ? R::load(pnext + (IdxT)u * st) : R::kNone;
+      pnext += (IdxT)ENV_BATCH * st;
+      const int qe = min(L, q0 + ENV_BATCH);
+#pragma unroll 1
+      for (int q = q0; q < qe; ++q) step(s_raw[q - q0][threadIdx.x], q);
     }
   }
 
   // ---- backward sweep over the hull.  Parabola u at p (divided by w2) is G(u) - 2 p u + p^2:
   //   D(p) = (Gprev - Gcur) + 2 p (cur - prev) = -A + p * 2B   prev at least as good  <=>  D(p) <= 0
   //   val(p) = F(cur) + w2 (p - cur)^2
-  float* __restrict__ out_f = reinterpret_cast<float*>(a.out) + base;
-  int32_t* __restrict__ out_i = reinterpret_cast<int32_t*>(a.out) + base;
-  int32_t* __restrict__ out_sq = a.out_sq + base;
-  IdxT o = (IdxT)(L - 1) * st;
+  // output pointers walk backwards with p (element L-1 first)
+  float* __restrict__ out_f = reinterpret_cast<float*>(a.out) + base + (IdxT)(L - 1) * st;
+  int32_t* __restrict__ out_i = reinterpret_cast<int32_t*>(a.out) + base + (IdxT)(L - 1) * st;
+  int32_t* __restrict__ out_sq = a.out_sq + base + (IdxT)(L - 1) * st;
   if (t0 == EDT_NO_SITE) {  // no site on this line
 #pragma unroll 1
-    for (int p = L - 1; p >= 0; --p, o -= st) {
-      if (OUT == EDT_OUT_I32) out_i[o] = EDT_INF_I32;
-      if (OUT == EDT_OUT_F32 || (OUT == EDT_OUT_DIST && SQ != 2)) out_f[o] = INFINITY;
-      if (OUT == EDT_OUT_DIST && SQ != 0) out_sq[o] = EDT_INF_I32;
+    for (int p = L - 1; p >= 0; --p, out_i -= st, out_f -= st, out_sq -= st) {
+      if (OUT == EDT_OUT_I32) *out_i = EDT_INF_I32;
+      if (OUT == EDT_OUT_F32 || (OUT == EDT_OUT_DIST && SQ != 2)) *out_f = INFINITY;
+      if (OUT == EDT_OUT_DIST && SQ != 0) *out_sq = EDT_INF_I32;
     }
     return;
   }
@@ -389,8 +404,8 @@ __global__ void __launch_bounds__(ENV_THREADS) edt_envelope_kernel(const EnvArgs
     }
   };
   enter(L - 1, A, Bb);
-#pragma unroll 1
-  for (int p = L - 1; p >= 0; --p, o -= st) {
+#pragma unroll 2
+  for (int p = L - 1; p >= 0; --p, out_i -= st, out_f -= st, out_sq -= st) {
     if (!INT) D = (WT)fma(pd, (double)Dstep, (double)Gdiff);
     if (D <= (WT)0) {
       do {  // move down the hull (D > 0 whenever prev does not exist)
@@ -413,12 +428,12 @@ __global__ void __launch_bounds__(ENV_THREADS) edt_envelope_kernel(const EnvArgs
       } while (D <= (WT)0);
     }
     if (INT) {
-      if (OUT == EDT_OUT_I32) out_i[o] = val;
-      if (OUT == EDT_OUT_F32) out_f[o] = (float)val;
+      if (OUT == EDT_OUT_I32) *out_i = val;
+      if (OUT == EDT_OUT_F32) *out_f = (float)val;
       if (OUT == EDT_OUT_DIST) {
         // float32 sqrt of the (exact) integer: |rel err| < 1e-7 after the two roundings
-        if (SQ != 2) out_f[o] = sqrtf((float)val) * out_mul;
-        if (SQ != 0) out_sq[o] = val;
+        if (SQ != 2) *out_f = sqrtf((float)val) * out_mul;
+        if (SQ != 0) *out_sq = val;
       }
       val -= e;
       e -= 2;
@@ -426,9 +441,9 @@ __global__ void __launch_bounds__(ENV_THREADS) edt_envelope_kernel(const EnvArgs
     } else {
       const double dpd = pd - curd;
       const double v = fma(w2, dpd * dpd, Fcur);  // squared distance (x out_scale for EDT_OUT_DIST)
-      if (OUT == EDT_OUT_I32) out_i[o] = d2i_exact(v);
-      if (OUT == EDT_OUT_F32) out_f[o] = (float)v;
-      if (OUT == EDT_OUT_DIST) out_f[o] = sqrtf((float)v);
+      if (OUT == EDT_OUT_I32) *out_i = d2i_exact(v);
+      if (OUT == EDT_OUT_F32) *out_f = (float)v;
+      if (OUT == EDT_OUT_DIST) *out_f = sqrtf((float)v);
       pd -= 1.0;
     }
   }
