@@ -435,6 +435,35 @@ def gather(vol: torch.Tensor, spots_xyz) -> np.ndarray:
     return out.cpu().numpy()
 
 
+def gather_points(vol: torch.Tensor, pts_zxy: torch.Tensor) -> torch.Tensor:
+    """vol[z, x, y] at device points (int32 [n, 3] rows (z, x, y)); result stays on the device."""
+    n = pts_zxy.shape[0]
+    out = torch.empty(n, dtype=vol.dtype, device=vol.device)
+    if n:
+        nz, nx, ny = vol.shape
+        fn = L.lib().mfish_gather_f32 if vol.dtype == torch.float32 else L.lib().mfish_gather_u8
+        L.check(fn(vol.data_ptr(), nz, nx, ny, pts_zxy.data_ptr(), n, out.data_ptr(), _stream()))
+    return out
+
+
+def blur_at_points_dev(vol: Volume, pts_zxy: torch.Tensor, sigma_xyz=(3, 3, 0.3), mode="nearest") -> torch.Tensor:
+    """``blur_at_points`` for device points (int32 [n, 3] rows (z, x, y)); float64 result on the device."""
+    n = pts_zxy.shape[0]
+    out = torch.empty(n, dtype=torch.float64, device=vol.data.device)
+    if n:
+        nz, nx, ny = vol.data.shape
+        sx, sy, sz = [float(s) for s in sigma_xyz]
+        tz, rz = T.gaussian_taps(sz)
+        tx, rx = T.gaussian_taps(sx)
+        ty, ry = T.gaussian_taps(sy)
+        b = {"nearest": L.BOUNDARY_NEAREST, "reflect": L.BOUNDARY_REFLECT}[mode]
+        L.check(L.lib().mfish_blur_at_points(vol.data.data_ptr(), nz, nx, ny, pts_zxy.data_ptr(), n, L.darray(tz), rz,
+                                             L.darray(tx), rx, L.darray(ty), ry, b,
+                                             vol.minmax.data_ptr() if vol.minmax is not None else None,
+                                             out.data_ptr(), _stream()))
+    return out
+
+
 def blur_at_points(vol: Volume, spots_xyz, sigma_xyz=(3, 3, 0.3), mode="nearest") -> np.ndarray:
     """skimage.filters.gaussian(normalize(img), sigma)[spot] in float64 at the given spots only."""
     n = len(spots_xyz)
@@ -541,14 +570,14 @@ def edt(mask_zxy: torch.Tensor, sampling_xyz=None, want_sq=False):
     return (dist, sq) if want_sq else dist
 
 
-def edt_inplane(mask_zxy: torch.Tensor, sampling_xyz=None):
+def edt_inplane(mask_zxy: torch.Tensor, sampling_xyz=None, out: torch.Tensor | None = None):
     """y and x passes only: squared in-plane distance [nz,nx,ny] (int32 or float32) + its kind."""
     import ctypes
     nz, nx, ny = mask_zxy.shape
     dev = mask_zxy.device
     sx, sy, sz = [float(s) for s in (sampling_xyz or (1.0, 1.0, 1.0))]
     ws = WS.get("edt_ws", (int(L.lib().mfish_edt_workspace_bytes(nz, nx, ny)),), torch.uint8, dev)
-    f2 = torch.empty((nz, nx, ny), dtype=torch.int32, device=dev)
+    f2 = out if out is not None else torch.empty((nz, nx, ny), dtype=torch.int32, device=dev)
     kind = ctypes.c_int(-1)
     L.check(L.lib().mfish_edt_inplane_u8(mask_zxy.data_ptr(), nz, nx, ny, L.darray([sz, sx, sy]), f2.data_ptr(),
                                          ctypes.byref(kind), ws.data_ptr(), _stream()))
@@ -557,13 +586,14 @@ def edt_inplane(mask_zxy: torch.Tensor, sampling_xyz=None):
     return f2, kind.value
 
 
-def edt_zpass(f2: torch.Tensor, kind: int, sampling_xyz=None):
+def edt_zpass(f2: torch.Tensor, kind: int, sampling_xyz=None, out: torch.Tensor | None = None):
     """z pass on (possibly re-partitioned) in-plane squared distances -> float32 distances."""
     nz, nx, ny = f2.shape
     dev = f2.device
     sx, sy, sz = [float(s) for s in (sampling_xyz or (1.0, 1.0, 1.0))]
     link = WS.get("edt_link", (nz * nx * ny,), torch.int32, dev)
-    out = torch.empty((nz, nx, ny), dtype=torch.float32, device=dev)
+    if out is None:
+        out = torch.empty((nz, nx, ny), dtype=torch.float32, device=dev)
     f2 = f2.contiguous()
     L.check(L.lib().mfish_edt_zpass(f2.data_ptr(), int(kind), nz, nx, ny, L.darray([sz, sx, sy]), out.data_ptr(), None,
                                     link.data_ptr(), _stream()))

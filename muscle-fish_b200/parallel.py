@@ -51,6 +51,25 @@ class _phase:
             PHASES[self.name] = PHASES.get(self.name, 0.0) + time.perf_counter() - self.t0
 
 
+# Large per-step temporaries (extended slabs, re-partition buffers) are cached by (tag, shape): a
+# slab step alternates multi-GB buffers of different sizes, and letting them churn through the
+# caching allocator costs cudaMalloc/cudaFree round trips every step.  A cached buffer is valid
+# until the next call that uses the same tag.
+_BUFS = {}
+
+
+def _buf(tag, shape, dtype, device):
+    k = (tag, tuple(shape), dtype, str(device))
+    b = _BUFS.get(k)
+    if b is None:
+        b = _BUFS[k] = torch.empty(shape, dtype=dtype, device=device)
+    return b
+
+
+def clear_buffers():
+    _BUFS.clear()
+
+
 # ------------------------------------------------------------------------------ partitioning
 def shard_stacks(n_stacks: int, rank: int, world: int):
     """Stack indices of this rank: round-robin, like one SLURM job per image."""
@@ -110,7 +129,7 @@ def exchange_halo(slab: torch.Tensor, halo: int, lay: SlabLayout, group=None):
     lo = halo if r > 0 else 0
     hi = halo if r < P - 1 else 0
     nzl = slab.shape[0]
-    ext = torch.empty((lo + nzl + hi,) + tuple(slab.shape[1:]), dtype=slab.dtype, device=slab.device)
+    ext = _buf("halo_ext", (lo + nzl + hi,) + tuple(slab.shape[1:]), slab.dtype, slab.device)
     ext[lo:lo + nzl] = slab
     ops = []
     send_lo = send_hi = None
@@ -133,15 +152,17 @@ def repartition_z_to_x(t: torch.Tensor, lay: SlabLayout, group=None) -> torch.Te
     if P == 1:
         return t
     ny = lay.ny
-    out = torch.empty((lay.nz, lay.x1 - lay.x0, ny), dtype=t.dtype, device=t.device)
-    sends = [t[:, b:e, :].contiguous() for (b, e) in lay.xb]
+    out = _buf("z2x_out", (lay.nz, lay.x1 - lay.x0, ny), t.dtype, t.device)
     ops = []
     for s in range(P):
         if s == r:
             continue
-        ops.append(dist.P2POp(dist.isend, sends[s], s, group))
+        b, e = lay.xb[s]
+        snd = _buf(f"z2x_send{s}", (t.shape[0], e - b, ny), t.dtype, t.device)
+        snd.copy_(t[:, b:e, :])
+        ops.append(dist.P2POp(dist.isend, snd, s, group))
         ops.append(dist.P2POp(dist.irecv, out[lay.zb[s][0]:lay.zb[s][1]], s, group))
-    out[lay.z0:lay.z1] = sends[r]
+    out[lay.z0:lay.z1] = t[:, lay.x0:lay.x1, :]
     if ops:
         for w in dist.batch_isend_irecv(ops):
             w.wait()
@@ -153,8 +174,9 @@ def repartition_x_to_z(t: torch.Tensor, lay: SlabLayout, group=None) -> torch.Te
     P, r = lay.world, lay.rank
     if P == 1:
         return t
-    out = torch.empty((lay.z1 - lay.z0, lay.nx, lay.ny), dtype=t.dtype, device=t.device)
-    recvs = [torch.empty((lay.z1 - lay.z0, e - b, lay.ny), dtype=t.dtype, device=t.device) for (b, e) in lay.xb]
+    out = _buf("x2z_out", (lay.z1 - lay.z0, lay.nx, lay.ny), t.dtype, t.device)
+    recvs = [_buf(f"x2z_recv{i}", (lay.z1 - lay.z0, e - b, lay.ny), t.dtype, t.device)
+             for i, (b, e) in enumerate(lay.xb)]
     ops = []
     for s in range(P):
         if s == r:
@@ -189,43 +211,40 @@ class DeviceOps:
         return self.D.minmax(slab)
 
     def log(self, ext, mm, sigma):
-        return self.D.log_volume(self.D.Volume(ext, mm), sigma)
+        out = _buf("log_ext", ext.shape, torch.float32, ext.device)
+        return self.D.log_volume(self.D.Volume(ext, mm), sigma, out=out)
 
+    # The list-handling ops take and return tensors on the volume's device, so a slab step makes
+    # one device->host copy at the very end.  Points are int64 [n, 3] rows (z, x, y).
     def peaks(self, log_ext, thr):
-        """-> int64 array [n, 3] of (z, x, y) in `log_ext` coordinates and float32 values"""
-        idx, val = self.D.detect_peaks(log_ext, thr)
-        nz, nx, ny = log_ext.shape
-        x, y, z, _ = self.D.decode_raster(idx.cpu().numpy(), (1, nx, ny, nz))
-        return np.stack([z, x, y], axis=1), val.cpu().numpy()
+        """-> (raster int64 [n] over the (x, y, z) order of `log_ext`, value float32 [n])"""
+        return self.D.detect_peaks(log_ext, thr)
 
-    def rank_prune(self, zxy, val, dims_zxy, cutoff_sq):
-        """global peaks -> (order, alive): rank order (descending value, raster ties) and survivors"""
+    def rank_prune(self, raster, val, dims_zxy, cutoff_sq):
+        """global peaks -> (raster in rank order, alive bool): descending value, raster ties"""
         nz, nx, ny = dims_zxy
-        dev = torch.device("cuda", torch.cuda.current_device())
-        raster = (zxy[:, 1].astype(np.int64) * ny + zxy[:, 2]) * nz + zxy[:, 0]
-        idx = torch.from_numpy(raster).to(dev)
-        v = torch.from_numpy(np.ascontiguousarray(val, dtype=np.float32)).to(dev)
-        idx_r, _, alive = self.D.rank_prune_equal(idx, v, (1, nx, ny, nz), cutoff_sq)
-        return idx_r.cpu().numpy(), alive.cpu().numpy().astype(bool)
+        idx_r, _, alive = self.D.rank_prune_equal(raster.contiguous(), val.contiguous(), (1, nx, ny, nz), cutoff_sq)
+        return idx_r, alive.bool()
 
     def gather_u8(self, vol, zxy):
-        return self.D.gather(vol, zxy[:, [1, 2, 0]])
+        return self.D.gather_points(vol, zxy.to(torch.int32).contiguous())
 
     def gather_f32(self, vol, zxy):
-        return self.D.gather(vol, zxy[:, [1, 2, 0]])
+        return self.D.gather_points(vol, zxy.to(torch.int32).contiguous())
 
     def blur_at_points(self, ext, mm, zxy, sigma_xyz):
-        return self.D.blur_at_points(self.D.Volume(ext, mm), zxy[:, [1, 2, 0]].astype(np.float64), sigma_xyz, "nearest")
+        return self.D.blur_at_points_dev(self.D.Volume(ext, mm), zxy.to(torch.int32).contiguous(), sigma_xyz,
+                                         "nearest")
 
     # masked radix select in three passes; `reduce` all-reduces the histogram between hist and scan
     def masked_quantile(self, vol, mask, q, reduce):
         return self.D.masked_quantile_distributed(vol, mask, q, reduce)
 
     def edt_inplane(self, mask, sampling_xyz):
-        return self.D.edt_inplane(mask, sampling_xyz)
+        return self.D.edt_inplane(mask, sampling_xyz, out=_buf("edt_f2", mask.shape, torch.int32, mask.device))
 
     def edt_zpass(self, f2, kind, sampling_xyz):
-        return self.D.edt_zpass(f2, kind, sampling_xyz)
+        return self.D.edt_zpass(f2, kind, sampling_xyz, out=_buf("edt_dist", f2.shape, torch.float32, f2.device))
 
 
 # ------------------------------------------------------------------------ slab-mode pipeline
@@ -234,7 +253,8 @@ def slab_find_spots_snrfilter(img_slab: torch.Tensor, mask_slab: torch.Tensor, l
     """``find_spots_snrfilter`` (modules/muscle_fish.py:281-402) on a z-slab decomposed mosaic.
     ``img_slab`` float32 / ``mask_slab`` uint8, both ``[nz_local][nx][ny]``.  Every rank returns the
     same global result: dict(spots (N,4) float64 [x,y,z,sigma], spots_masked, intensity, baseline, snr)."""
-    ops = ops or DeviceOps()
+    with _phase("setup"):
+        ops = ops or DeviceOps()
     dev = img_slab.device
     nz, nx, ny = lay.nz, lay.nx, lay.ny
     # 1. global min / max
@@ -256,42 +276,57 @@ def slab_find_spots_snrfilter(img_slab: torch.Tensor, mask_slab: torch.Tensor, l
         log_ext = ops.log(ext, mm, sigma)
     a = radius if lo else 0
     b = log_ext.shape[0] - (radius if hi else 0)
+    nzs = b - a
     with _phase("peaks"):
-        zxy, val = ops.peaks(log_ext[a:b], t_spot)
-    zg = zxy[:, 0] + a - lo + lay.z0
-    own = (zg >= lay.z0) & (zg < lay.z1)
-    mine = np.stack([zg[own], zxy[own, 1], zxy[own, 2]], axis=1).astype(np.int64)
-    vals = np.asarray(val)[own].astype(np.float32)
-    # 4. all-gather the peak lists, prune identically everywhere
+        ras_l, val = ops.peaks(log_ext[a:b], t_spot)
+        # local raster ((x*ny + y)*nzs + zs) -> global raster ((x*ny + y)*nz + zg); keep own planes
+        zs = ras_l % nzs
+        xy = ras_l // nzs
+        zg = zs + (a - lo + lay.z0)
+        own = (zg >= lay.z0) & (zg < lay.z1)
+        ras_g = (xy * nz + zg)[own]
+        val = val[own]
+    # 4. all-gather the peak lists (padded to the longest), prune identically everywhere
     with _phase("gather_peaks"):
-        gathered = [None] * lay.world
-        dist.all_gather_object(gathered, (mine, vals), group=group)
-    all_zxy = np.concatenate([g[0] for g in gathered], axis=0) if gathered else mine
-    all_val = np.concatenate([g[1] for g in gathered], axis=0)
-    empty = {"spots": np.empty((0, 4)), "spots_masked": np.empty((0, 4)), "intensity": np.empty(0),
-             "baseline": None, "snr": snr}
-    if len(all_zxy) == 0:
-        return empty
+        n_loc = torch.tensor([ras_g.numel()], dtype=torch.int64, device=dev)
+        counts = [torch.zeros_like(n_loc) for _ in range(lay.world)]
+        dist.all_gather(counts, n_loc, group=group)
+        counts = [int(c.item()) for c in counts]
+        nmax = max(counts)
+        empty = {"spots": np.empty((0, 4)), "spots_masked": np.empty((0, 4)), "intensity": np.empty(0),
+                 "baseline": None, "snr": snr}
+        if nmax == 0:
+            return empty
+        pad_r = torch.zeros(nmax, dtype=torch.int64, device=dev)
+        pad_v = torch.zeros(nmax, dtype=torch.float32, device=dev)
+        pad_r[:ras_g.numel()] = ras_g
+        pad_v[:val.numel()] = val
+        all_r = [torch.empty_like(pad_r) for _ in range(lay.world)]
+        all_v = [torch.empty_like(pad_v) for _ in range(lay.world)]
+        dist.all_gather(all_r, pad_r, group=group)
+        dist.all_gather(all_v, pad_v, group=group)
+        all_r = torch.cat([t[:c] for t, c in zip(all_r, counts)])
+        all_v = torch.cat([t[:c] for t, c in zip(all_v, counts)])
     cutoff = max(T.prune_cutoff_sq(float(sigma), None, 0.5), 0)
     with _phase("prune"):
-        raster_ranked, alive = ops.rank_prune(all_zxy, all_val, (nz, nx, ny), cutoff)
-    raster_ranked = raster_ranked[alive]
-    z = raster_ranked % nz
-    t = raster_ranked // nz
-    y = t % ny
-    x = t // ny
-    # 5. mask filter: the owner of each spot looks it up
+        ranked, alive = ops.rank_prune(all_r, all_v, (nz, nx, ny), cutoff)
+        ranked = ranked[alive]
+    with _phase("decode"):
+        z = ranked % nz
+        t = ranked // nz
+        y = t % ny
+        x = t // ny
+    # 5. mask filter + 7. blurred intensity: the owner of each spot (its z-slab) evaluates both on its
+    #    mask slab / extended raw slab; one all-reduce carries them to every rank
     ownz = (z >= lay.z0) & (z < lay.z1)
-    local = np.stack([z[ownz] - lay.z0, x[ownz], y[ownz]], axis=1)
-    inmask = np.zeros(len(z), dtype=np.int32)
-    with _phase("mask"):
-        if ownz.any():
-            inmask[ownz] = (ops.gather_u8(mask_slab, local) != 0).astype(np.int32)
-        inmask = _allreduce_np(inmask, dev, group=group) > 0
-    x, y, z = x[inmask], y[inmask], z[inmask]
-    spots = np.stack([x, y, z, np.full(len(x), float(sigma))], axis=1).astype(np.float64)
-    if len(spots) == 0:
-        return empty
+    with _phase("mask_blur"):
+        both = torch.zeros((2, ranked.numel()), dtype=torch.float64, device=dev)
+        if bool(ownz.any()):
+            zo, xo, yo = z[ownz], x[ownz], y[ownz]
+            inm = ops.gather_u8(mask_slab, torch.stack([zo - lay.z0, xo, yo], dim=1))
+            both[0, ownz] = (inm != 0).to(torch.float64)
+            both[1, ownz] = ops.blur_at_points(ext, mm, torch.stack([zo - lay.z0 + lo, xo, yo], dim=1), (3, 3, 0.3))
+        dist.all_reduce(both, op=dist.ReduceOp.SUM, group=group)
     # 6. P25 baseline over the (global) mask
     def reduce_hist(h):
         dist.all_reduce(h, op=dist.ReduceOp.SUM, group=group)
@@ -301,18 +336,31 @@ def slab_find_spots_snrfilter(img_slab: torch.Tensor, mask_slab: torch.Tensor, l
         raise IndexError("percentile of an empty selection (mask selects no voxel)")
     a01 = T.interp01(np.array([v0, v1], dtype=np.float64), lo_v, hi_v)
     baseline = T.lerp(float(a01[0]), float(a01[1]), float(gamma))
-    # 7. blurred intensity at the spots: owners evaluate on their extended raw slab
-    ownz = (z >= lay.z0) & (z < lay.z1)
-    inten = np.zeros(len(z), dtype=np.float64)
-    with _phase("blur"):
-        if ownz.any():
-            loc = np.stack([z[ownz] - lay.z0 + lo, x[ownz], y[ownz]], axis=1)
-            inten[ownz] = ops.blur_at_points(ext, mm, loc, (3, 3, 0.3))
-        inten = _allreduce_np(inten, dev, group=group)
-    if snr is None:
-        thresh = np.percentile(inten, 90) / (baseline * np.sqrt(10))
-        snr = max(thresh, np.sqrt(10))
-    keep = inten / baseline > snr
+    # mask filter, P90 of the intensities and the SNR cut stay on the device; only compact results
+    # (int32 coordinates + float64 intensities of the masked spots) cross to the host
+    with _phase("select"):
+        sel = both[0] > 0
+        xyz = torch.stack([x[sel], y[sel], z[sel]], dim=1).to(torch.int32)
+        inten_d = both[1][sel]
+        nm = int(inten_d.numel())
+        if nm == 0:
+            return empty
+        if snr is None:
+            # np.percentile(inten, 90), method 'linear': two order statistics + lerp on the host
+            srt = torch.sort(inten_d).values
+            _, k, g = T.percentile_virtual_index(nm, 90)
+            pair = srt[[k, min(k + 1, nm - 1)]].tolist()
+            thresh = T.lerp(pair[0], pair[1], g) / (baseline * np.sqrt(10))
+            snr = max(thresh, np.sqrt(10))
+        keep_d = inten_d / baseline > snr
+    with _phase("d2h"):
+        xyz_h = xyz.cpu().numpy()
+        inten = inten_d.cpu().numpy()
+        keep = keep_d.cpu().numpy()
+    with _phase("host_tail"):
+        spots = np.empty((nm, 4), dtype=np.float64)
+        spots[:, :3] = xyz_h
+        spots[:, 3] = float(sigma)
     return {"spots": spots[keep], "spots_masked": spots, "intensity": inten, "baseline": baseline, "snr": snr}
 
 
@@ -335,12 +383,15 @@ def slab_spot_distances(dist_xslab: torch.Tensor, spots_xyz: np.ndarray, lay: Sl
     """EDT value at each spot (the interpn gather of nocodazole/fish_analysis_noco.py:297-298) from the
     x-slab partitioned distance map; every rank gets the full vector."""
     ops = ops or DeviceOps()
-    s = np.asarray(spots_xyz)
-    out = np.zeros(len(s), dtype=np.float64)
-    if len(s):
-        x = s[:, 0].astype(np.int64)
+    dev = dist_xslab.device
+    s = torch.as_tensor(np.ascontiguousarray(np.asarray(spots_xyz)[:, :3]).astype(np.int64)).to(dev)
+    out = torch.zeros(s.shape[0], dtype=torch.float64, device=dev)
+    if s.shape[0]:
+        x = s[:, 0]
         own = (x >= lay.x0) & (x < lay.x1)
-        if own.any():
-            loc = np.stack([s[own, 2].astype(np.int64), x[own] - lay.x0, s[own, 1].astype(np.int64)], axis=1)
-            out[own] = ops.gather_f32(dist_xslab, loc).astype(np.float64)
-    return _allreduce_np(out, dist_xslab.device, group=group)
+        if bool(own.any()):
+            so = s[own]
+            loc = torch.stack([so[:, 2], so[:, 0] - lay.x0, so[:, 1]], dim=1)
+            out[own] = ops.gather_f32(dist_xslab, loc).to(torch.float64)
+    dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
+    return out.cpu().numpy()

@@ -39,23 +39,27 @@ class OracleOps:
 
     def peaks(self, log_ext, thr):
         cube = log_ext.numpy()
-        pk = oracle.peak_local_max(cube[..., None], threshold_abs=thr)
-        return pk[:, :3].astype(np.int64), cube[tuple(pk[:, :3].T)].astype(np.float32)
+        nzs, nx, ny = cube.shape
+        pk = oracle.peak_local_max(cube[..., None], threshold_abs=thr)[:, :3]
+        raster = (pk[:, 1].astype(np.int64) * ny + pk[:, 2]) * nzs + pk[:, 0]
+        return torch.from_numpy(raster), torch.from_numpy(cube[tuple(pk.T)].astype(np.float32))
 
-    def rank_prune(self, zxy, val, dims_zxy, cutoff_sq):
+    def rank_prune(self, raster, val, dims_zxy, cutoff_sq):
         nz, nx, ny = dims_zxy
-        raster = (zxy[:, 1].astype(np.int64) * ny + zxy[:, 2]) * nz + zxy[:, 0]
+        raster, val = raster.numpy(), val.numpy()
         order = np.lexsort((raster, -val.astype(np.float64)))
         r = raster[order]
-        blobs = np.stack([zxy[order, 1], zxy[order, 2], zxy[order, 0], np.full(len(r), self.sigma)], 1).astype(float)
+        z, t = r % nz, r // nz
+        y, x = t % ny, t // ny
+        blobs = np.stack([x, y, z, np.full(len(r), self.sigma)], 1).astype(float)
         assert T.prune_cutoff_sq(self.sigma) == cutoff_sq
         kept = oracle.prune_blobs(blobs, 0.5, pair_order="sorted")
         keyset = {tuple(k[:3].astype(int)) for k in kept}
         alive = np.array([tuple(b[:3].astype(int)) in keyset for b in blobs], dtype=bool)
-        return r, alive
+        return torch.from_numpy(r), torch.from_numpy(alive)
 
     def gather_u8(self, vol, zxy):
-        return vol.numpy()[tuple(zxy.T)]
+        return torch.from_numpy(vol.numpy()[tuple(zxy.numpy().T)])
 
     gather_f32 = gather_u8
 
@@ -63,7 +67,7 @@ class OracleOps:
         lo, hi = [float(v) for v in mm]
         a = (ext.numpy().astype(np.float64) - lo) * (1.0 / (hi - lo))
         sx, sy, sz = sigma_xyz
-        return oracle.gaussian(a, (sz, sx, sy))[tuple(zxy.T)]
+        return torch.from_numpy(oracle.gaussian(a, (sz, sx, sy))[tuple(zxy.numpy().T)])
 
     def masked_quantile(self, vol, mask, q, reduce):
         """three-pass 11/11/10-bit radix select on the monotone float key, histograms reduced"""

@@ -14,6 +14,7 @@ ap.add_argument("--nuclei", type=int, default=4000)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--warmup", type=int, default=1)
 ap.add_argument("--phases", action="store_true")
+ap.add_argument("--cprofile", action="store_true")
 args = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -44,10 +45,15 @@ if args.phases:
     P.PHASES = {}
 t0 = time.perf_counter()
 parts = {}
+if args.cprofile and rank == 0:
+    import cProfile, pstats
+    pr = cProfile.Profile(); pr.enable()
 for _ in range(args.steps):
     res, sd, t = step()
     for k, v in t.items():
         parts[k] = parts.get(k, 0.0) + v
+if args.cprofile and rank == 0:
+    pr.disable(); pstats.Stats(pr, stream=sys.stderr).sort_stats("cumtime").print_stats(30)
 dist.barrier(); torch.cuda.synchronize()
 dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
 dist.all_reduce(dt, op=dist.ReduceOp.MAX)
