@@ -131,6 +131,13 @@ int mfish_log3d_f32(const float* in_dev, float* out_dev, float* tmp1_dev, float*
                     float* tmp3_dev, int64_t nz, int64_t nx, int64_t ny, double sigma,
                     const float* norm_minmax_dev, void* stream);
 
+/* The same for the planes [out_z0, out_z1) of a z-extended slab only (z-slab mosaics: the planes
+ * within `radius` of an interior cut see the boundary rule instead of real neighbours and are not
+ * wanted).  Planes outside the range of out_dev are left unspecified.        */
+int mfish_log3d_range_f32(const float* in_dev, float* out_dev, float* tmp1_dev, float* tmp2_dev,
+                          float* tmp3_dev, int64_t nz, int64_t nx, int64_t ny, double sigma,
+                          const float* norm_minmax_dev, int64_t out_z0, int64_t out_z1, void* stream);
+
 /* ---- spot detection --------------------------------------------------- *
  * skimage.feature.peak_local_max(cube, threshold_abs=t, footprint=ones(3^4))
  * as blob_log calls it: v > t and v >= every in-volume neighbour in

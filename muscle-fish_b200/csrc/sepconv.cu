@@ -231,6 +231,8 @@ struct SArgs {
   int64_t outer_stride;  // elements between bundles
   int stride;            // elements between successive samples along the axis (< 2^31)
   int L;                 // samples along the axis (>= R)
+  int out_begin;         // outputs are produced for [out_begin, out_end) only (inputs: the whole line)
+  int out_end;
   int chunk_len;         // samples handled per blockIdx.z
   int bmode;
   float scale;
@@ -253,8 +255,8 @@ __global__ void __launch_bounds__(STHREADS) conv_strided_kernel(const SArgs<R> a
   const int64_t i = (int64_t)blockIdx.x * STHREADS + threadIdx.x;
   if (i >= a.inner) return;
   const unsigned i0 = (unsigned)((int64_t)blockIdx.y * a.outer_stride + i);
-  const int kb = blockIdx.z * a.chunk_len;
-  const int ke = min(a.L, kb + a.chunk_len);
+  const int kb = a.out_begin + blockIdx.z * a.chunk_len;
+  const int ke = min(a.out_end, kb + a.chunk_len);
   if (kb >= ke) return;
   const int L = a.L;
   const int st = a.stride;
@@ -350,6 +352,7 @@ struct SGenArgs {
   float* out1;
   int64_t inner, stride, outer_stride;
   int L, bmode, radius, op;
+  int out_begin;
   float scale;
   const float* taps_g;
   const float* taps_d;
@@ -368,7 +371,7 @@ __global__ void __launch_bounds__(STHREADS) conv_strided_generic_kernel(const SG
   __syncthreads();
   const int64_t i = (int64_t)blockIdx.x * STHREADS + threadIdx.x;
   if (i >= a.inner) return;
-  const int k = blockIdx.z;
+  const int k = a.out_begin + blockIdx.z;
   const int64_t base = (int64_t)blockIdx.y * a.outer_stride + i;
   const float* __restrict__ p0 = a.in0 + base;
   const float* __restrict__ p1 = a.in1 ? a.in1 + base : nullptr;
@@ -670,6 +673,8 @@ struct PassDesc {
   float scale;
   const float* mm;
   cudaStream_t st;
+  int out_begin = 0;  // z axis only: produce outputs for [out_begin, out_end); out_end < 0 = whole line
+  int out_end = -1;
 };
 
 static int upload_taps(const PassDesc& p, float** dg, float** dd) {
@@ -733,14 +738,17 @@ static int launch_strided(const PassDesc& p) {
   }
   a.bmode = p.boundary;
   a.scale = p.scale;
+  a.out_begin = p.out_begin;
+  a.out_end = p.out_end < 0 ? a.L : p.out_end;
+  const int nout = a.out_end - a.out_begin;
   fill_taps<R>(a.t, p.g, p.d, p.radius);
   // split long lines into chunks until the grid holds >= ~4 waves of threads
   int64_t bx = (a.inner + STHREADS - 1) / STHREADS;
   int64_t want = (int64_t)num_sms() * 16 * 2;  // blocks
   int chunks = 1;
   const int min_chunk = std::max(64, 8 * R);
-  while (bx * nouter * chunks < want && a.L / (chunks * 2) >= min_chunk) chunks *= 2;
-  a.chunk_len = (a.L + chunks - 1) / chunks;
+  while (bx * nouter * chunks < want && nout / (chunks * 2) >= min_chunk) chunks *= 2;
+  a.chunk_len = (nout + chunks - 1) / chunks;
   MFISH_REQUIRE(bx < (1ll << 31) && nouter < 65536, "sepconv(strided): grid too large");
   dim3 grid((unsigned)bx, (unsigned)nouter, (unsigned)chunks);
   static const char* const names[2][4] = {{"conv_z_g", "conv_z_gd", "conv_z_mid", "conv_z_last"},
@@ -809,9 +817,11 @@ static int launch_generic(const PassDesc& p) {
     a.scale = p.scale;
     a.taps_g = dg;
     a.taps_d = dd;
+    a.out_begin = p.out_begin;
+    const int nout = (p.out_end < 0 ? a.L : p.out_end) - p.out_begin;
     int64_t bx = (a.inner + STHREADS - 1) / STHREADS;
     MFISH_REQUIRE(nouter < 65536 && a.L < 65536, "sepconv(generic): grid too large");
-    dim3 grid((unsigned)bx, (unsigned)nouter, (unsigned)a.L);
+    dim3 grid((unsigned)bx, (unsigned)nouter, (unsigned)nout);
     size_t smem = (size_t)2 * (p.radius + 1) * sizeof(float);
     conv_strided_generic_kernel<<<grid, STHREADS, smem, p.st>>>(a);
   }
@@ -847,6 +857,9 @@ int run_pass(const PassDesc& p) {
                 "sepconv: bad boundary mode");
   MFISH_REQUIRE(p.out0 != p.in0 && p.out0 != p.in1 && (!two_out || (p.out1 != p.in0 && p.out1 != p.in1)),
                 "sepconv: in-place operation is not supported");
+  MFISH_REQUIRE(p.out_end < 0 || (p.axis == MFISH_AXIS_Z && p.out_begin >= 0 && p.out_begin < p.out_end &&
+                                  p.out_end <= p.nz),
+                "sepconv: bad output range");
   if (p.axis == MFISH_AXIS_Y) {
     if (two_in) {
       set_error("sepconv: ops MID/LAST are implemented for the z and x axes only");
@@ -966,19 +979,24 @@ extern "C" int mfish_gaussian3d_f32(const float* in_dev, float* out_dev, float* 
   return MFISH_OK;
 }
 
-extern "C" int mfish_log3d_f32(const float* in_dev, float* out_dev, float* tmp1_dev, float* tmp2_dev,
-                               float* tmp3_dev, int64_t nz, int64_t nx, int64_t ny, double sigma,
-                               const float* norm_minmax_dev, void* stream) {
+// LoG of the planes [out_z0, out_z1) of a z-extended slab: the y pass runs on every plane, the z pass
+// produces only the requested planes (its inputs reach `radius` planes further), the x pass runs on those.
+extern "C" int mfish_log3d_range_f32(const float* in_dev, float* out_dev, float* tmp1_dev, float* tmp2_dev,
+                                     float* tmp3_dev, int64_t nz, int64_t nx, int64_t ny, double sigma,
+                                     const float* norm_minmax_dev, int64_t out_z0, int64_t out_z1, void* stream) {
   MFISH_REQUIRE(in_dev && out_dev && tmp1_dev && tmp2_dev && tmp3_dev, "log3d: null pointer");
   MFISH_REQUIRE(sigma > 0.0, "log3d: sigma must be positive");
+  MFISH_REQUIRE(out_z0 >= 0 && out_z0 < out_z1 && out_z1 <= nz, "log3d: bad plane range");
   std::vector<double> g, d;
   int radius;
   host_taps(sigma, g, d, radius);
   cudaStream_t st = as_stream(stream);
+  const bool whole = (out_z0 == 0 && out_z1 == nz);
   int rc = MFISH_ERR_UNSUPPORTED;
   // fused y+z pass (TMA staged) when the rows allow 16-byte bulk copies
-  const bool fuse_ok = (ny % 4 == 0) && ny >= 32 && aligned16(in_dev) && aligned16(tmp2_dev) && aligned16(tmp3_dev) &&
-                       nz < (1 << 20) && nx * ((ny + YZ_SEG - 1) / YZ_SEG) < (1ll << 31) && !g_disable_fused_yz;
+  const bool fuse_ok = whole && (ny % 4 == 0) && ny >= 32 && aligned16(in_dev) && aligned16(tmp2_dev) &&
+                       aligned16(tmp3_dev) && nz < (1 << 20) && nx * ((ny + YZ_SEG - 1) / YZ_SEG) < (1ll << 31) &&
+                       !g_disable_fused_yz;
   if (fuse_ok && radius == 8)
     rc = launch_yz<8>(in_dev, tmp2_dev, tmp3_dev, nz, nx, ny, g.data(), d.data(), radius, norm_minmax_dev, st);
   else if (fuse_ok && radius == 4)
@@ -994,11 +1012,23 @@ extern "C" int mfish_log3d_f32(const float* in_dev, float* out_dev, float* tmp1_
     // z: (A, B) -> (C = G A, F = D A + G B)
     PassDesc pz{out_dev, tmp1_dev, tmp2_dev, tmp3_dev, nz, nx, ny, MFISH_AXIS_Z, g.data(), d.data(), radius,
                 MFISH_BOUNDARY_REFLECT, MFISH_CONV_MID, 1.0f, nullptr, st};
+    if (!whole) {
+      pz.out_begin = (int)out_z0;
+      pz.out_end = (int)out_z1;
+    }
     rc = run_pass(pz);
   }
   if (rc != MFISH_OK) return rc;
-  // x: (C, F) -> -sigma^2 (D C + G F)
-  PassDesc px{tmp2_dev, tmp3_dev, out_dev, nullptr, nz, nx, ny, MFISH_AXIS_X, g.data(), d.data(), radius,
-              MFISH_BOUNDARY_REFLECT, MFISH_CONV_LAST, (float)(-(sigma * sigma)), nullptr, st};
+  // x: (C, F) -> -sigma^2 (D C + G F), on the requested planes only
+  const int64_t off = out_z0 * nx * ny;
+  PassDesc px{tmp2_dev + off, tmp3_dev + off, out_dev + off, nullptr, out_z1 - out_z0, nx, ny, MFISH_AXIS_X, g.data(),
+              d.data(), radius, MFISH_BOUNDARY_REFLECT, MFISH_CONV_LAST, (float)(-(sigma * sigma)), nullptr, st};
   return run_pass(px);
+}
+
+extern "C" int mfish_log3d_f32(const float* in_dev, float* out_dev, float* tmp1_dev, float* tmp2_dev,
+                               float* tmp3_dev, int64_t nz, int64_t nx, int64_t ny, double sigma,
+                               const float* norm_minmax_dev, void* stream) {
+  return mfish_log3d_range_f32(in_dev, out_dev, tmp1_dev, tmp2_dev, tmp3_dev, nz, nx, ny, sigma, norm_minmax_dev, 0,
+                               nz, stream);
 }

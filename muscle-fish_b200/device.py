@@ -228,8 +228,9 @@ class Workspace:
 WS = Workspace()
 
 
-def log_volume(vol: Volume, sigma: float, out: torch.Tensor | None = None) -> torch.Tensor:
-    """-sigma^2 * gaussian_laplace(normalize(img), sigma): one scale of blob_log's cube."""
+def log_volume(vol: Volume, sigma: float, out: torch.Tensor | None = None, z_range=None) -> torch.Tensor:
+    """-sigma^2 * gaussian_laplace(normalize(img), sigma): one scale of blob_log's cube.
+    ``z_range=(z0, z1)``: only those planes of the result are computed (z-extended slabs)."""
     d = vol.data
     shp, dev = d.shape, d.device
     if out is None:
@@ -238,9 +239,11 @@ def log_volume(vol: Volume, sigma: float, out: torch.Tensor | None = None) -> to
     t2 = WS.get("log2", shp, torch.float32, dev)
     t3 = WS.get("log3", shp, torch.float32, dev)
     nz, nx, ny = shp
-    L.check(L.lib().mfish_log3d_f32(d.data_ptr(), out.data_ptr(), t1.data_ptr(), t2.data_ptr(), t3.data_ptr(),
-                                    nz, nx, ny, float(sigma),
-                                    vol.minmax.data_ptr() if vol.minmax is not None else None, _stream()))
+    z0, z1 = (0, nz) if z_range is None else (int(z_range[0]), int(z_range[1]))
+    L.check(L.lib().mfish_log3d_range_f32(d.data_ptr(), out.data_ptr(), t1.data_ptr(), t2.data_ptr(), t3.data_ptr(),
+                                          nz, nx, ny, float(sigma),
+                                          vol.minmax.data_ptr() if vol.minmax is not None else None, z0, z1,
+                                          _stream()))
     return out
 
 

@@ -210,9 +210,9 @@ class DeviceOps:
     def minmax(self, slab):
         return self.D.minmax(slab)
 
-    def log(self, ext, mm, sigma):
+    def log(self, ext, mm, sigma, z_range=None):
         out = _buf("log_ext", ext.shape, torch.float32, ext.device)
-        return self.D.log_volume(self.D.Volume(ext, mm), sigma, out=out)
+        return self.D.log_volume(self.D.Volume(ext, mm), sigma, out=out, z_range=z_range)
 
     # The list-handling ops take and return tensors on the volume's device, so a slab step makes
     # one device->host copy at the very end.  Points are int64 [n, 3] rows (z, x, y).
@@ -272,10 +272,10 @@ def slab_find_spots_snrfilter(img_slab: torch.Tensor, mask_slab: torch.Tensor, l
         ext, lo, hi = exchange_halo(img_slab, radius + 1, lay, group)
     # 3. LoG on the extended slab (planes within `radius` of an interior cut are contaminated by the
     #    boundary rule and are not used); reflect applies only at the global faces
-    with _phase("log"):
-        log_ext = ops.log(ext, mm, sigma)
     a = radius if lo else 0
-    b = log_ext.shape[0] - (radius if hi else 0)
+    b = ext.shape[0] - (radius if hi else 0)
+    with _phase("log"):
+        log_ext = ops.log(ext, mm, sigma, z_range=(a, b))
     nzs = b - a
     with _phase("peaks"):
         ras_l, val = ops.peaks(log_ext[a:b], t_spot)

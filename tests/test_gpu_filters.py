@@ -182,3 +182,17 @@ def test_golden_filters(golden):
         assert _rel_err(got, golden[key]) < REL_TOL
     got = _zxy_to_xyz(D.gaussian(vol, (3, 3, 0.3)))
     assert _rel_err(got, golden["blur_3_3_03"]) < REL_TOL
+
+
+@pytest.mark.parametrize("sigma", [1.0, 2.0, 5.5])
+def test_log_volume_plane_range_equals_full(sigma):
+    """z-slab mosaics compute only the planes that have real neighbours on both sides"""
+    import torch
+    from muscle_fish_b200 import device as D
+    rng = np.random.default_rng(9)
+    a = rng.random((40, 36, 31)).astype(np.float32)
+    vol = D.ingest(a)
+    full = D.log_volume(vol, sigma).clone()
+    for z0, z1 in ((0, 31), (8, 23), (0, 12), (20, 31), (15, 16)):
+        part = D.log_volume(vol, sigma, z_range=(z0, z1))
+        assert torch.equal(part[z0:z1], full[z0:z1]), (z0, z1)

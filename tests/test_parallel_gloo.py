@@ -32,7 +32,7 @@ class OracleOps:
     def minmax(self, slab):
         return torch.stack([slab.min(), slab.max()]).to(torch.float32)
 
-    def log(self, ext, mm, sigma):
+    def log(self, ext, mm, sigma, z_range=None):
         lo, hi = [float(v) for v in mm]
         a = (ext.numpy().astype(np.float64) - lo) * (1.0 / (hi - lo))
         return torch.from_numpy((-ndi.gaussian_laplace(a, sigma) * sigma ** 2))
