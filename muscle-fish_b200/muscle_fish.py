@@ -111,9 +111,10 @@ def find_spots_snrfilter(img_fish, snr=None, sigma=1., t_spot=0.025, mask=None, 
     spots_filtered = spots_masked[ratio > snr]
     if z_first:
         spots_filtered = spots_filtered[:, [2, 0, 1, 3]]
-    rows = np.column_stack([spots_masked[:, 0:3], spot_int, ratio]).tolist()
-    spot_data = [['spot_id', 'x', 'y', 'z', 'intensity', 'SNR']]
-    spot_data.extend([c] + r for c, r in enumerate(rows))
+    spot_data = np.column_stack([np.zeros(len(spot_int)), spots_masked[:, 0:3], spot_int, ratio]).tolist()
+    for c, r in enumerate(spot_data):
+        r[0] = c  # integer spot id, as the reference's enumerate()
+    spot_data.insert(0, ['spot_id', 'x', 'y', 'z', 'intensity', 'SNR'])
     return _nonempty(spots_filtered), spot_data
 
 
