@@ -172,6 +172,13 @@ int mfish_overlap_pairs(const int64_t* idx_ranked_dev, int64_t n, int64_t ns, in
 int mfish_masked_quantile_f32(const float* vol_dev, const uint8_t* mask_dev, int64_t n, double q,
                               void* ws_dev, float* out_dev, double* info_dev, void* stream);
 
+/* The same two order statistics from ONE full pass: a 1/64 sample brackets the wanted ranks, one pass
+ * counts what lies below the bracket and collects what lies inside, the exact ranks are selected among
+ * the collected values.  info_dev = {gamma, n_masked, status}: status 1 means the bracket missed (checked
+ * on the device) and the caller must fall back to mfish_masked_quantile_f32; status 0 is exact.          */
+int mfish_masked_quantile_fast_f32(const float* vol_dev, const uint8_t* mask_dev, int64_t n, double q,
+                                   void* ws_dev, float* out_dev, double* info_dev, void* stream);
+
 /* the same select in its three steps, for a z-slab decomposed volume: after every
  * mfish_qsel_hist the caller all-reduces (sum) the first 2*2048 uint32 of ws_dev
  * across the slabs, then calls mfish_qsel_scan; passes 0, 1, 2 in order.      */

@@ -50,6 +50,7 @@ SIGNATURES = {
     "mfish_rank_prune": (_i, [_p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p, _p, _p]),
     "mfish_overlap_pairs": (_i, [_p, _i64, _i64, _i64, _i64, _i64, _p, _p, _p, _i64, _p]),
     "mfish_masked_quantile_f32": (_i, [_p, _p, _i64, _d, _p, _p, _p, _p]),
+    "mfish_masked_quantile_fast_f32": (_i, [_p, _p, _i64, _d, _p, _p, _p, _p]),
     "mfish_qsel_begin": (_i, [_p, _d, _p]),
     "mfish_qsel_hist": (_i, [_p, _p, _i64, _i, _p, _p]),
     "mfish_qsel_scan": (_i, [_i, _p, _p, _p, _p]),

@@ -14,16 +14,29 @@ namespace mfish {
 // masked radix select
 // ------------------------------------------------------------------------------------------
 constexpr int QBINS = 2048;
+enum { QMODE_QUANTILE = 0, QMODE_BRACKET = 1, QMODE_RANKS = 2 };
 struct QState {
   uint32_t prefix[2];
   unsigned long long k[2];
   unsigned long long n;
   double gamma;
   double q;
+  int mode;  // how qsel_scan_kernel<0> chooses the two ranks
+};
+// bracketed select (mfish_masked_quantile_f32): control block shared by its kernels
+constexpr int QSEG = 64;  // the candidate buffer is filled through QSEG independent cursors
+struct QCtl {
+  unsigned int seg_count[QSEG * 32];  // one cursor per 128-byte line (entry i * 32)
+  unsigned long long n_masked, n_below, n_cand;
+  float v_lo, v_hi;    // candidates are the masked values in [v_lo, v_hi]
+  int lo_open, hi_open;
+  int status;          // 0: exact result delivered, 1: bracket missed, run the three-pass select
+  unsigned long long cap;
 };
 struct QWs {
   uint32_t hist[2][QBINS];
   QState st;
+  QCtl ctl;
 };
 static_assert(sizeof(QWs) <= MFISH_QUANTILE_WS_BYTES, "quantile workspace too small");
 
@@ -46,10 +59,15 @@ __device__ __forceinline__ void qsel_digits(uint32_t key, const uint32_t pfx0, c
   }
 }
 
+// sample: 0 = every voxel; S > 0 = one 128-byte group (32 voxels) out of every S groups.
+// m may be null (every voxel selected); n_dev (optional) caps n by a device-side count.
 template <int PASS>
 __global__ void __launch_bounds__(256) qsel_hist_kernel(const float* __restrict__ v,
-                                                        const uint8_t* __restrict__ m, int64_t n, QWs* ws) {
+                                                        const uint8_t* __restrict__ m, int64_t n, QWs* ws,
+                                                        int sample, const unsigned long long* n_dev) {
   __shared__ uint32_t sh[2][QBINS];
+  if (ws->ctl.status != 0 && n_dev != nullptr) return;  // bracket missed: the candidate passes are moot
+  if (n_dev != nullptr) n = min((long long)n, (long long)*n_dev);
   for (int i = threadIdx.x; i < 2 * QBINS; i += blockDim.x) (&sh[0][0])[i] = 0;
   __syncthreads();
   const uint32_t pfx0 = PASS == 0 ? 0u : ws->st.prefix[0];
@@ -84,18 +102,41 @@ __global__ void __launch_bounds__(256) qsel_hist_kernel(const float* __restrict_
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const bool vec = aligned16_dev(v) && ((reinterpret_cast<uintptr_t>(m) & 3u) == 0);
   const int64_t n4 = vec ? n / 4 : 0;
-  for (int64_t i = tid; i < n4; i += stride) {
-    const uchar4 mk = __ldg(reinterpret_cast<const uchar4*>(m) + i);
-    if (mk.x | mk.y | mk.z | mk.w) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(v) + i);
-      if (mk.x) push(a.x);
-      if (mk.y) push(a.y);
-      if (mk.z) push(a.z);
-      if (mk.w) push(a.w);
+  if (sample > 0 && vec) {
+    // groups of 8 float4 (128 B): one pseudo-randomly placed group out of every `sample` consecutive
+    // ones (a plain stride would alias with the row length and sample a single column of the volume)
+    const int64_t ngroups = (n4 + 7) / 8;
+    const int64_t nwin = (ngroups + sample - 1) / sample;
+    const int64_t wtid = tid >> 3, wstride = stride >> 3;  // 8 threads share a group
+    const int sub = (int)(tid & 7);
+    for (int64_t w = wtid; w < nwin; w += wstride) {
+      const int64_t g = w * sample + (int64_t)((((uint32_t)w * 0x9E3779B1u) >> 16) % (uint32_t)sample);
+      const int64_t i = g * 8 + sub;
+      if (i < n4) {
+        const uchar4 mk = m ? __ldg(reinterpret_cast<const uchar4*>(m) + i) : make_uchar4(1, 1, 1, 1);
+        if (mk.x | mk.y | mk.z | mk.w) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(v) + i);
+          if (mk.x) push(a.x);
+          if (mk.y) push(a.y);
+          if (mk.z) push(a.z);
+          if (mk.w) push(a.w);
+        }
+      }
     }
-  }
-  for (int64_t i = n4 * 4 + tid; i < n; i += stride) {
-    if (m[i]) push(v[i]);
+  } else {
+    for (int64_t i = tid; i < n4; i += stride) {
+      const uchar4 mk = m ? __ldg(reinterpret_cast<const uchar4*>(m) + i) : make_uchar4(1, 1, 1, 1);
+      if (mk.x | mk.y | mk.z | mk.w) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(v) + i);
+        if (mk.x) push(a.x);
+        if (mk.y) push(a.y);
+        if (mk.z) push(a.z);
+        if (mk.w) push(a.w);
+      }
+    }
+    for (int64_t i = n4 * 4 + tid; i < n; i += stride) {
+      if (!m || m[i]) push(v[i]);
+    }
   }
   if (run_c0) atomicAdd(&sh[0][run_d0], run_c0);
   if (run_c1) atomicAdd(&sh[1][run_d1], run_c1);
@@ -110,7 +151,7 @@ __global__ void __launch_bounds__(256) qsel_hist_kernel(const float* __restrict_
   }
 }
 
-__global__ void qsel_init_kernel(QWs* ws, double q) {
+__global__ void qsel_init_kernel(QWs* ws, double q, int mode) {
   for (int i = threadIdx.x; i < 2 * QBINS; i += blockDim.x) (&ws->hist[0][0])[i] = 0;
   if (threadIdx.x == 0) {
     ws->st.prefix[0] = ws->st.prefix[1] = 0;
@@ -118,6 +159,12 @@ __global__ void qsel_init_kernel(QWs* ws, double q) {
     ws->st.n = 0;
     ws->st.gamma = 0.0;
     ws->st.q = q;
+    ws->st.mode = mode;
+    if (mode != QMODE_RANKS) {
+      ws->ctl.n_masked = ws->ctl.n_below = ws->ctl.n_cand = 0;
+      ws->ctl.status = 0;
+      for (int i = 0; i < QSEG; ++i) ws->ctl.seg_count[i * 32] = 0;
+    }
   }
 }
 
@@ -166,21 +213,44 @@ __global__ void __launch_bounds__(QSCAN_THREADS) qsel_scan_kernel(QWs* ws, float
     if (PASS == 0) {
       const unsigned long long n = s_tot[0];
       s.n = n;
-      if (n == 0) {
-        out[0] = out[1] = nanf("");
-        info[0] = 0.0;
-        info[1] = 0.0;
-      } else {
-        // numpy method 'linear': virtual index = (n - 1) * q
-        double vi = (double)(n - 1) * s.q;
-        double fl = floor(vi);
-        s.gamma = vi - fl;
-        long long k0 = (long long)fl;
-        k0 = k0 < 0 ? 0 : (k0 > (long long)n - 1 ? (long long)n - 1 : k0);
-        long long k1 = k0 + 1 > (long long)n - 1 ? (long long)n - 1 : k0 + 1;
-        s.k[0] = (unsigned long long)k0;
-        s.k[1] = (unsigned long long)k1;
-      }
+      if (s.mode == QMODE_QUANTILE) {
+        if (n == 0) {
+          out[0] = out[1] = nanf("");
+          info[0] = 0.0;
+          info[1] = 0.0;
+        } else {
+          // numpy method 'linear': virtual index = (n - 1) * q
+          double vi = (double)(n - 1) * s.q;
+          double fl = floor(vi);
+          s.gamma = vi - fl;
+          long long k0 = (long long)fl;
+          k0 = k0 < 0 ? 0 : (k0 > (long long)n - 1 ? (long long)n - 1 : k0);
+          long long k1 = k0 + 1 > (long long)n - 1 ? (long long)n - 1 : k0 + 1;
+          s.k[0] = (unsigned long long)k0;
+          s.k[1] = (unsigned long long)k1;
+        }
+      } else if (s.mode == QMODE_BRACKET) {
+        // ranks of the SAMPLE that bracket the wanted population quantile with a wide margin:
+        // 12 standard deviations of the rank of a random sample (cluster sampling is less efficient)
+        ws->ctl.lo_open = ws->ctl.hi_open = 1;
+        if (n >= 4096) {
+          const double r = (double)(n - 1) * s.q;
+          const double delta = 12.0 * sqrt((double)n * s.q * (1.0 - s.q)) + 16.0;
+          const double lo = floor(r - delta), hi = ceil(r + delta);
+          if (lo >= 0.0) {
+            s.k[0] = (unsigned long long)lo;
+            ws->ctl.lo_open = 0;
+          }
+          if (hi <= (double)(n - 1)) {
+            s.k[1] = (unsigned long long)hi;
+            ws->ctl.hi_open = 0;
+          } else {
+            s.k[1] = n - 1;
+          }
+        } else if (n > 0) {
+          s.k[1] = n - 1;
+        }
+      }  // QMODE_RANKS: k[0], k[1] were set by qsel_ranks_kernel
     }
   }
   __syncthreads();
@@ -215,12 +285,154 @@ __global__ void __launch_bounds__(QSCAN_THREADS) qsel_scan_kernel(QWs* ws, float
     if (PASS == 2) {
       out[0] = key_to_f32(s.prefix[0]);
       out[1] = key_to_f32(s.prefix[1]);
-      info[0] = s.gamma;
-      info[1] = (double)s.n;
+      if (s.mode == QMODE_QUANTILE) {
+        info[0] = s.gamma;
+        info[1] = (double)s.n;
+      }
     }
   }
   __syncthreads();
   for (int i = t; i < 2 * QBINS; i += QSCAN_THREADS) (&ws->hist[0][0])[i] = 0;
+}
+
+// bracket -> control block (after the sample select)
+__global__ void qsel_bracket_kernel(QWs* ws, const float* pair) {
+  if (threadIdx.x != 0) return;
+  QCtl& c = ws->ctl;
+  c.v_lo = c.lo_open ? -INFINITY : pair[0];
+  c.v_hi = c.hi_open ? INFINITY : pair[1];
+}
+
+// one full pass: count the masked voxels, those below the bracket, and collect those inside it.
+// The candidate buffer (pre-filled with a huge value) is written through QSEG cursors, each owning
+// cap / QSEG slots, so the appends do not serialise on one counter; unused slots sort to the top.
+__global__ void __launch_bounds__(256) qsel_range_kernel(const float* __restrict__ v, const uint8_t* __restrict__ m,
+                                                         int64_t n, QWs* ws, float* __restrict__ cand) {
+  const float lo = ws->ctl.v_lo, hi = ws->ctl.v_hi;
+  const unsigned seg_cap = (unsigned)(ws->ctl.cap / QSEG);
+  const int seg = blockIdx.x % QSEG;
+  unsigned int* cursor = &ws->ctl.seg_count[seg * 32];
+  float* seg_buf = cand + (size_t)seg * seg_cap;
+  unsigned nm = 0, nb = 0;
+  const int lane = threadIdx.x & 31;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const bool vec = aligned16_dev(v) && ((reinterpret_cast<uintptr_t>(m) & 3u) == 0);
+  const int64_t n4 = vec ? n / 4 : 0;
+  // uniform control flow: every lane classifies its 4 voxels, the warp reserves room for all of its
+  // candidates with ONE atomic (exclusive scan of the per-lane counts), then each lane stores its own
+  const int64_t n4_warp = (n4 + 31) / 32 * 32;  // keep whole warps in the loop for the shuffles
+  for (int64_t i = tid; i < n4_warp; i += stride) {
+    float val[4];
+    unsigned is_c = 0;
+    if (i < n4) {
+      const uchar4 mk = __ldg(reinterpret_cast<const uchar4*>(m) + i);
+      if (mk.x | mk.y | mk.z | mk.w) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(v) + i);
+        val[0] = a.x; val[1] = a.y; val[2] = a.z; val[3] = a.w;
+        const unsigned char mb[4] = {mk.x, mk.y, mk.z, mk.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (mb[k]) {
+            ++nm;
+            if (val[k] < lo) ++nb;
+            else if (val[k] <= hi) is_c |= 1u << k;
+          }
+        }
+      }
+    }
+    const unsigned any = __ballot_sync(0xffffffffu, is_c != 0);
+    if (any) {
+      const unsigned cnt = __popc(is_c);
+      unsigned incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+      unsigned base = 0;
+      if (lane == 0) base = atomicAdd(cursor, total);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      unsigned pos = base + incl - cnt;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (is_c & (1u << k)) {
+          if (pos < seg_cap) seg_buf[pos] = val[k];
+          ++pos;
+        }
+      }
+    }
+  }
+  for (int64_t i = n4 * 4 + tid; i < n; i += stride) {  // scalar tail (unaligned volumes)
+    if (m[i]) {
+      const float x = v[i];
+      ++nm;
+      if (x < lo) {
+        ++nb;
+      } else if (x <= hi) {
+        const unsigned pos = atomicAdd(cursor, 1u);
+        if (pos < seg_cap) seg_buf[pos] = x;
+      }
+    }
+  }
+  // block reduction of the two counters, one atomic pair per block
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    nm += __shfl_xor_sync(0xffffffffu, nm, o);
+    nb += __shfl_xor_sync(0xffffffffu, nb, o);
+  }
+  __shared__ unsigned s_nm[8], s_nb[8];
+  if ((threadIdx.x & 31) == 0) {
+    s_nm[threadIdx.x >> 5] = nm;
+    s_nb[threadIdx.x >> 5] = nb;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long tm = 0, tb = 0;
+    for (int k = 0; k < 8; ++k) {
+      tm += s_nm[k];
+      tb += s_nb[k];
+    }
+    atomicAdd(&ws->ctl.n_masked, tm);
+    atomicAdd(&ws->ctl.n_below, tb);
+  }
+}
+
+// exact ranks of the population quantile, relative to the candidate buffer; verifies the bracket
+__global__ void qsel_ranks_kernel(QWs* ws, float* out, double* info) {
+  if (threadIdx.x != 0) return;
+  QCtl& c = ws->ctl;
+  QState& s = ws->st;
+  const unsigned long long n = c.n_masked;
+  info[1] = (double)n;
+  bool overflow = false;
+  c.n_cand = 0;
+  for (int i = 0; i < QSEG; ++i) {
+    c.n_cand += c.seg_count[i * 32];
+    overflow |= c.seg_count[i * 32] > (unsigned)(c.cap / QSEG);
+  }
+  if (n == 0) {
+    out[0] = out[1] = nanf("");
+    info[0] = 0.0;
+    info[2] = 0.0;
+    c.status = 0;
+    s.k[0] = s.k[1] = 0;
+    return;
+  }
+  const double vi = (double)(n - 1) * s.q;
+  const double fl = floor(vi);
+  long long k0 = (long long)fl;
+  k0 = k0 < 0 ? 0 : (k0 > (long long)n - 1 ? (long long)n - 1 : k0);
+  const long long k1 = k0 + 1 > (long long)n - 1 ? (long long)n - 1 : k0 + 1;
+  s.gamma = vi - fl;
+  info[0] = s.gamma;
+  const bool inside = !overflow && (unsigned long long)k0 >= c.n_below &&
+                      (unsigned long long)k1 < c.n_below + c.n_cand;
+  c.status = inside ? 0 : 1;
+  info[2] = inside ? 0.0 : 1.0;
+  s.k[0] = inside ? (unsigned long long)k0 - c.n_below : 0;
+  s.k[1] = inside ? (unsigned long long)k1 - c.n_below : 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -351,7 +563,7 @@ using namespace mfish;
 // (first 2*2048 uint32 of the workspace) between `hist` and `scan` of every pass.
 extern "C" int mfish_qsel_begin(void* ws_dev, double q, void* stream) {
   MFISH_REQUIRE(ws_dev && q >= 0.0 && q <= 1.0, "qsel_begin: bad arguments");
-  qsel_init_kernel<<<1, 256, 0, as_stream(stream)>>>(reinterpret_cast<QWs*>(ws_dev), q);
+  qsel_init_kernel<<<1, 256, 0, as_stream(stream)>>>(reinterpret_cast<QWs*>(ws_dev), q, QMODE_QUANTILE);
   count_launch(1);
   return check_launch("qsel_begin");
 }
@@ -364,11 +576,11 @@ extern "C" int mfish_qsel_hist(const float* vol_dev, const uint8_t* mask_dev, in
   QWs* ws = reinterpret_cast<QWs*>(ws_dev);
   int blocks = (int)std::min<int64_t>((n / 4 + 255) / 256 + 1, (int64_t)num_sms() * 8);
   if (pass == 0)
-    qsel_hist_kernel<0><<<blocks, 256, 0, st>>>(vol_dev, mask_dev, n, ws);
+    qsel_hist_kernel<0><<<blocks, 256, 0, st>>>(vol_dev, mask_dev, n, ws, 0, nullptr);
   else if (pass == 1)
-    qsel_hist_kernel<1><<<blocks, 256, 0, st>>>(vol_dev, mask_dev, n, ws);
+    qsel_hist_kernel<1><<<blocks, 256, 0, st>>>(vol_dev, mask_dev, n, ws, 0, nullptr);
   else
-    qsel_hist_kernel<2><<<blocks, 256, 0, st>>>(vol_dev, mask_dev, n, ws);
+    qsel_hist_kernel<2><<<blocks, 256, 0, st>>>(vol_dev, mask_dev, n, ws, 0, nullptr);
   count_launch(1);
   return check_launch("qsel_hist");
 }
@@ -398,6 +610,59 @@ extern "C" int mfish_masked_quantile_f32(const float* vol_dev, const uint8_t* ma
     rc = mfish_qsel_hist(vol_dev, mask_dev, n, pass, ws_dev, stream);
     if (rc == MFISH_OK) rc = mfish_qsel_scan(pass, ws_dev, out_dev, info_dev, stream);
   }
+  return rc;
+}
+
+// Bracketed select: the same two order statistics from ONE full pass over the volume.
+//   1. three-pass select on a 1/64 sample (128-byte groups) -> values [v_lo, v_hi] that bracket the
+//      wanted ranks with a 12-sigma margin;
+//   2. one full pass counts the masked voxels below v_lo and collects those inside the bracket;
+//   3. the exact ranks, shifted by the count below, are selected inside the (small) candidate buffer.
+// The bracket is verified on the device; info_dev[2] = 1 means it missed (or the buffer overflowed) and
+// the caller must run mfish_masked_quantile_f32.  info_dev = {gamma, n_masked, status}.
+extern "C" int mfish_masked_quantile_fast_f32(const float* vol_dev, const uint8_t* mask_dev, int64_t n, double q,
+                                              void* ws_dev, float* out_dev, double* info_dev, void* stream) {
+  MFISH_REQUIRE(vol_dev && mask_dev && ws_dev && out_dev && info_dev, "masked_quantile: null pointer");
+  MFISH_REQUIRE(n > 0 && q >= 0.0 && q <= 1.0, "masked_quantile: bad arguments");
+  cudaStream_t st = as_stream(stream);
+  ProfScope prof("masked_quantile_bracketed", st);
+  QWs* ws = reinterpret_cast<QWs*>(ws_dev);
+  const int64_t cap = (std::max<int64_t>(1 << 20, n / 64) + QSEG - 1) / QSEG * QSEG;
+  float* cand = nullptr;
+  float* pair = nullptr;
+  MFISH_CUDA(cudaMallocAsync((void**)&cand, (size_t)cap * sizeof(float), st));
+  MFISH_CUDA(cudaMallocAsync((void**)&pair, 2 * sizeof(float) + 3 * sizeof(double), st));
+  double* dummy = reinterpret_cast<double*>(pair + 2);
+  const int blocks = (int)std::min<int64_t>((n / 4 + 255) / 256 + 1, (int64_t)num_sms() * 8);
+  const int sblocks = (int)std::min<int64_t>((n / 4 / 64 + 255) / 256 + 1, (int64_t)num_sms() * 8);
+  constexpr int SAMPLE = 64;
+  // 1. bracket from the sample
+  qsel_init_kernel<<<1, 256, 0, st>>>(ws, q, QMODE_BRACKET);
+  qsel_hist_kernel<0><<<sblocks, 256, 0, st>>>(vol_dev, mask_dev, n, ws, SAMPLE, nullptr);
+  qsel_scan_kernel<0><<<1, QSCAN_THREADS, 0, st>>>(ws, pair, dummy);
+  qsel_hist_kernel<1><<<sblocks, 256, 0, st>>>(vol_dev, mask_dev, n, ws, SAMPLE, nullptr);
+  qsel_scan_kernel<1><<<1, QSCAN_THREADS, 0, st>>>(ws, pair, dummy);
+  qsel_hist_kernel<2><<<sblocks, 256, 0, st>>>(vol_dev, mask_dev, n, ws, SAMPLE, nullptr);
+  qsel_scan_kernel<2><<<1, QSCAN_THREADS, 0, st>>>(ws, pair, dummy);
+  qsel_bracket_kernel<<<1, 32, 0, st>>>(ws, pair);
+  // 2. the one full pass
+  MFISH_CUDA(cudaMemsetAsync(cand, 0x7f, (size_t)cap * sizeof(float), st));  // 3.39e38: sorts above any voxel
+  MFISH_CUDA(cudaMemcpyAsync(&ws->ctl.cap, &cap, sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+  qsel_range_kernel<<<blocks, 256, 0, st>>>(vol_dev, mask_dev, n, ws, cand);
+  // 3. exact ranks inside the candidates
+  qsel_init_kernel<<<1, 256, 0, st>>>(ws, q, QMODE_RANKS);
+  qsel_ranks_kernel<<<1, 32, 0, st>>>(ws, out_dev, info_dev);
+  const int cblocks = (int)std::min<int64_t>((cap / 4 + 255) / 256 + 1, (int64_t)num_sms() * 4);
+  qsel_hist_kernel<0><<<cblocks, 256, 0, st>>>(cand, nullptr, cap, ws, 0, &ws->ctl.cap);
+  qsel_scan_kernel<0><<<1, QSCAN_THREADS, 0, st>>>(ws, out_dev, info_dev);
+  qsel_hist_kernel<1><<<cblocks, 256, 0, st>>>(cand, nullptr, cap, ws, 0, &ws->ctl.cap);
+  qsel_scan_kernel<1><<<1, QSCAN_THREADS, 0, st>>>(ws, out_dev, info_dev);
+  qsel_hist_kernel<2><<<cblocks, 256, 0, st>>>(cand, nullptr, cap, ws, 0, &ws->ctl.cap);
+  qsel_scan_kernel<2><<<1, QSCAN_THREADS, 0, st>>>(ws, out_dev, info_dev);
+  count_launch(17);
+  int rc = check_launch("masked_quantile_fast");
+  cudaFreeAsync(cand, st);
+  cudaFreeAsync(pair, st);
   return rc;
 }
 

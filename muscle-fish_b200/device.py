@@ -493,14 +493,18 @@ def masked_percentile_async(vol: Volume, mask: torch.Tensor, q_percent: float):
     dev = vol.data.device
     ws = WS.get("qws", (L.QUANTILE_WS_BYTES,), torch.uint8, dev)
     out = torch.empty(2, dtype=torch.float32, device=dev)
-    info = torch.empty(2, dtype=torch.float64, device=dev)
-    L.check(L.lib().mfish_masked_quantile_f32(vol.data.data_ptr(), mask.data_ptr(), vol.data.numel(),
-                                              float(q_percent) / 100.0, ws.data_ptr(), out.data_ptr(),
-                                              info.data_ptr(), _stream()))
+    info = torch.empty(3, dtype=torch.float64, device=dev)
+    q = float(q_percent) / 100.0
+    L.check(L.lib().mfish_masked_quantile_fast_f32(vol.data.data_ptr(), mask.data_ptr(), vol.data.numel(), q,
+                                                   ws.data_ptr(), out.data_ptr(), info.data_ptr(), _stream()))
 
     def finish():
+        gamma, n, status = info.tolist()
+        if status != 0:  # the sample bracket missed (verified on the device): exact three-pass select
+            L.check(L.lib().mfish_masked_quantile_f32(vol.data.data_ptr(), mask.data_ptr(), vol.data.numel(), q,
+                                                      ws.data_ptr(), out.data_ptr(), info.data_ptr(), _stream()))
+            gamma, n = info[:2].tolist()
         v0, v1 = out.tolist()
-        gamma, n = info.tolist()
         if n == 0:
             raise IndexError("percentile of an empty selection (mask selects no voxel)")
         if vol.minmax is not None:

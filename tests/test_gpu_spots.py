@@ -248,6 +248,31 @@ def test_masked_percentile_exact(q):
         D.masked_percentile(vol, D.ingest(np.zeros(a.shape, np.uint8), as_mask=True), q)
 
 
+@pytest.mark.parametrize("kind", ["float", "uint8_ties", "two_values", "sparse_mask"])
+@pytest.mark.parametrize("q", [25, 90, 0.01, 99.99])
+def test_masked_percentile_bracketed_path_exact(kind, q):
+    """large enough for the sampled bracket (one full pass) to engage; heavy ties and skewed data either
+    stay inside the bracket or take the verified fallback -- the result is exact either way"""
+    from muscle_fish_b200 import device as D
+    rng = np.random.default_rng(18)
+    shape = (200, 192, 40)  # 1.5 Mvoxel
+    if kind == "float":
+        a = (rng.standard_normal(shape) * 10 + 160).astype(np.float32)
+        mask = rng.random(shape) < 0.5
+    elif kind == "uint8_ties":
+        a = rng.integers(0, 7, size=shape).astype(np.float32)
+        mask = rng.random(shape) < 0.7
+    elif kind == "two_values":
+        a = np.where(rng.random(shape) < 0.25, 3.0, 900.0).astype(np.float32)
+        mask = np.ones(shape, bool)
+    else:
+        a = (rng.random(shape) * 1e4).astype(np.float32)
+        mask = rng.random(shape) < 0.004
+    vol = D.ingest(a)
+    got = D.masked_percentile(vol, D.ingest(mask, as_mask=True), q)
+    assert got == np.percentile(oracle.normalize_image(a)[mask], q)
+
+
 def test_blur_at_points_matches_dense_blur():
     from muscle_fish_b200 import device as D
     rng = np.random.default_rng(16)
