@@ -381,6 +381,10 @@ __global__ void __launch_bounds__(ENV_THREADS) edt_envelope_kernel(const EnvArgs
   int32_t val = 0, e = 0;
   double Fcur = 0.0, curd = 0.0;
   double pd = u2d((uint32_t)(L - 1));
+  // float64 arithmetic decides which site owns p; the DISTANCE itself (EDT_OUT_DIST) is then evaluated
+  // in float32 -- three roundings of 6e-8 before the square root, well inside the 1e-6 contract
+  float Fcurf = 0.f, curf = 0.f, pf = (float)(L - 1);
+  const float w2f = (float)w2;
   auto enter = [&](int p, GT Aa, BT Ba) {  // pair (prev, cur) at p;  Aa = Gcur - Gprev, Ba = cur - prev
     if (INT) {
       const int dp = p - cur;
@@ -395,6 +399,8 @@ __global__ void __launch_bounds__(ENV_THREADS) edt_envelope_kernel(const EnvArgs
     } else {
       curd = u2d((uint32_t)cur);
       Fcur = ((double)Gcur - curd * curd) * w2;
+      Fcurf = (float)Fcur;
+      curf = (float)cur;
       Dstep = 0;
       Gdiff = 1;  // D stays positive: no entry below
       if (prev != EDT_NO_SITE) {
@@ -404,7 +410,7 @@ __global__ void __launch_bounds__(ENV_THREADS) edt_envelope_kernel(const EnvArgs
     }
   };
   enter(L - 1, A, Bb);
-#pragma unroll 2
+#pragma unroll 4
   for (int p = L - 1; p >= 0; --p, out_i -= st, out_f -= st, out_sq -= st) {
     if (!INT) D = (WT)fma(pd, (double)Dstep, (double)Gdiff);
     if (D <= (WT)0) {
@@ -439,11 +445,16 @@ __global__ void __launch_bounds__(ENV_THREADS) edt_envelope_kernel(const EnvArgs
       e -= 2;
       D -= Dstep;
     } else {
-      const double dpd = pd - curd;
-      const double v = fma(w2, dpd * dpd, Fcur);  // squared distance (x out_scale for EDT_OUT_DIST)
-      if (OUT == EDT_OUT_I32) *out_i = d2i_exact(v);
-      if (OUT == EDT_OUT_F32) *out_f = (float)v;
-      if (OUT == EDT_OUT_DIST) *out_f = sqrtf((float)v);
+      if (OUT == EDT_OUT_DIST) {
+        const float dpf = pf - curf;
+        *out_f = sqrtf(fmaf(w2f, dpf * dpf, Fcurf));  // w2 carries out_scale here
+        pf -= 1.0f;
+      } else {
+        const double dpd = pd - curd;
+        const double v = fma(w2, dpd * dpd, Fcur);  // squared distance
+        if (OUT == EDT_OUT_I32) *out_i = d2i_exact(v);
+        if (OUT == EDT_OUT_F32) *out_f = (float)v;
+      }
       pd -= 1.0;
     }
   }
