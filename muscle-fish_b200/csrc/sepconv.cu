@@ -4,8 +4,10 @@
 //
 // Device layout [z][x][y], y contiguous.
 //  * conv_y_kernel      : contiguous axis.  A 512-voxel row segment + halo is staged in shared
-//                         memory with 128-bit loads; each thread produces 4 consecutive outputs
-//                         from a register window.            R4 + W4 (G) or R4 + W8 (G,D) B/voxel.
+//                         memory by the TMA unit (cp.async.bulk + mbarrier, double-buffered over 4
+//                         rows per block; row-end segments fall back to mapped loads); each thread
+//                         produces 4 consecutive outputs from a register window filled with 128-bit
+//                         shared loads.                      R4 + W4 (G) or R4 + W8 (G,D) B/voxel.
 //  * conv_strided_kernel: z or x axis.  One thread per contiguous-axis position walks the strided
 //                         axis with a (2R+1+D)-deep register ring (D planes of load lookahead), so
 //                         every voxel is read once and written once.  8 / 12 / 16 / 12 B/voxel for
@@ -46,6 +48,38 @@ __device__ __forceinline__ void load_norm(const float* mm, float& mn, float& sc,
 }
 
 // --------------------------------------------------------------------------------------------
+// TMA bulk copy + mbarrier helpers (sm_90+ PTX; SASS: UBLKCP / SYNCS)
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// TMA bulk copy global -> shared, completion signalled on the mbarrier (16-byte aligned, size % 16 == 0)
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, unsigned bytes,
+                                            unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// --------------------------------------------------------------------------------------------
 // contiguous (y) axis
 // --------------------------------------------------------------------------------------------
 constexpr int YSEG = 512;     // outputs per block
@@ -64,16 +98,21 @@ struct YArgs {
   Taps<R> t;
 };
 
+constexpr int YROWS = 4;  // consecutive rows handled by one block (double-buffered stages)
+
 template <int R, int OP>
 __global__ void __launch_bounds__(YTHREADS) conv_y_kernel(const YArgs<R> a) {
   constexpr int RP = (R + 3) & ~3;  // halo rounded up to a float4
   constexpr int NW = 4 + 2 * RP;    // register window per thread
-  __shared__ __align__(16) float buf[YSEG + 2 * RP];
+  constexpr unsigned BYTES = (YSEG + 2 * RP) * sizeof(float);
+  __shared__ __align__(128) float buf[2][YSEG + 2 * RP];
+  __shared__ __align__(8) unsigned long long bar[2];
 
-  const int64_t row = blockIdx.x / a.nseg;
-  const int seg0 = (int)(blockIdx.x - row * a.nseg) * YSEG;
+  const int64_t rblk = blockIdx.x / a.nseg;
+  const int seg0 = (int)(blockIdx.x - rblk * a.nseg) * YSEG;
+  const int64_t row_begin = rblk * YROWS;
+  const int nrow = (int)min((int64_t)YROWS, a.nrows - row_begin);
   const int ny = a.ny;
-  const float* __restrict__ src = a.in + row * ny;
   const int t = threadIdx.x;
 
   float mn, sc;
@@ -81,82 +120,96 @@ __global__ void __launch_bounds__(YTHREADS) conv_y_kernel(const YArgs<R> a) {
   load_norm(a.mm, mn, sc, degen);
 
   const bool vec = ((ny & 3) == 0) && aligned16_dev(a.in);
+  // interior segments: the row segment + halo (raw voxels) is fetched by the TMA unit, one bulk copy
+  // per row, the copy of row i+1 in flight while row i is convolved
   const bool interior = vec && (seg0 - RP >= 0) && (seg0 + YSEG + RP <= ny);
+  const float* __restrict__ seg_src = a.in + row_begin * ny + (seg0 - RP);
   if (interior) {
-    const float4* s4 = reinterpret_cast<const float4*>(src + seg0 - RP);
-    float4* b4 = reinterpret_cast<float4*>(buf);
-    constexpr int N4 = (YSEG + 2 * RP) / 4;
-    for (int j = t; j < N4; j += YTHREADS) {
-      float4 v = __ldg(&s4[j]);
-      v.x = (v.x - mn) * sc;
-      v.y = (v.y - mn) * sc;
-      v.z = (v.z - mn) * sc;
-      v.w = (v.w - mn) * sc;
-      b4[j] = v;
+    if (t == 0) {
+      mbar_init(&bar[0], 1);
+      mbar_init(&bar[1], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-  } else {
-    for (int j = t; j < YSEG + 2 * RP; j += YTHREADS) {
-      int y = seg0 - RP + j;
-      float v = 0.f;
-      // positions further than R outside the row are never read by a valid output
-      if (y >= -R && y < ny + R) {
-        int yy = a.bmode == MFISH_BOUNDARY_NEAREST ? bmap<MFISH_BOUNDARY_NEAREST>(y, ny)
-                                                   : bmap<MFISH_BOUNDARY_REFLECT>(y, ny);
-        v = (__ldg(&src[yy]) - mn) * sc;
-      }
-      buf[j] = v;
+    __syncthreads();
+    if (t == 0) {
+      mbar_expect_tx(&bar[0], BYTES);
+      tma_load_1d(buf[0], seg_src, BYTES, &bar[0]);
     }
   }
-  __syncthreads();
-
   const int y0 = seg0 + 4 * t;
-  if (y0 >= ny) return;
-
-  float w[NW];
-  {
-    const float4* b4 = reinterpret_cast<const float4*>(buf + 4 * t);
-#pragma unroll
-    for (int j = 0; j < NW / 4; ++j) {
-      float4 v = b4[j];
-      w[4 * j + 0] = v.x;
-      w[4 * j + 1] = v.y;
-      w[4 * j + 2] = v.z;
-      w[4 * j + 3] = v.w;
-    }
-  }
-  if (degen) {
-#pragma unroll
-    for (int j = 0; j < NW; ++j) w[j] = 1.0f;
-  }
-  float o0[4], o1[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int c = i + RP;
-    float acc0 = a.t.g[0] * w[c];
-    float acc1 = (OP == MFISH_CONV_GD) ? a.t.d[0] * w[c] : 0.f;
-#pragma unroll
-    for (int k = 1; k <= R; ++k) {
-      float s = w[c - k] + w[c + k];
-      acc0 = fmaf(a.t.g[k], s, acc0);
-      if (OP == MFISH_CONV_GD) acc1 = fmaf(a.t.d[k], s, acc1);
-    }
-    o0[i] = acc0;
-    o1[i] = acc1;
-  }
-  float* __restrict__ d0 = a.out0 + row * ny + y0;
   const bool vst = vec && aligned16_dev(a.out0) && (OP != MFISH_CONV_GD || aligned16_dev(a.out1));
-  if (vst && y0 + 3 < ny) {
-    *reinterpret_cast<float4*>(d0) = make_float4(o0[0], o0[1], o0[2], o0[3]);
-    if (OP == MFISH_CONV_GD)
-      *reinterpret_cast<float4*>(a.out1 + row * ny + y0) = make_float4(o1[0], o1[1], o1[2], o1[3]);
-  } else {
+
+  for (int i = 0; i < nrow; ++i) {
+    const int64_t row = row_begin + i;
+    float* cur = buf[i & 1];
+    if (interior) {
+      if (t == 0 && i + 1 < nrow) {  // the other stage was released by the barrier that ended row i-1
+        mbar_expect_tx(&bar[(i + 1) & 1], BYTES);
+        tma_load_1d(buf[(i + 1) & 1], seg_src + (int64_t)(i + 1) * ny, BYTES, &bar[(i + 1) & 1]);
+      }
+      mbar_wait(&bar[i & 1], (unsigned)((i >> 1) & 1));
+    } else {
+      const float* __restrict__ src = a.in + row * ny;
+      for (int j = t; j < YSEG + 2 * RP; j += YTHREADS) {
+        int y = seg0 - RP + j;
+        float v = 0.f;
+        // positions further than R outside the row are never read by a valid output
+        if (y >= -R && y < ny + R) {
+          int yy = a.bmode == MFISH_BOUNDARY_NEAREST ? bmap<MFISH_BOUNDARY_NEAREST>(y, ny)
+                                                     : bmap<MFISH_BOUNDARY_REFLECT>(y, ny);
+          v = __ldg(&src[yy]);
+        }
+        cur[j] = v;
+      }
+      __syncthreads();
+    }
+    if (y0 < ny) {
+      // register window; su.normalize_image is applied here, on load
+      float w[NW];
+      const float4* b4 = reinterpret_cast<const float4*>(cur + 4 * t);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if (y0 + i < ny) {
-        d0[i] = o0[i];
-        if (OP == MFISH_CONV_GD) a.out1[row * ny + y0 + i] = o1[i];
+      for (int j = 0; j < NW / 4; ++j) {
+        float4 v = b4[j];
+        w[4 * j + 0] = (v.x - mn) * sc;
+        w[4 * j + 1] = (v.y - mn) * sc;
+        w[4 * j + 2] = (v.z - mn) * sc;
+        w[4 * j + 3] = (v.w - mn) * sc;
+      }
+      if (degen) {
+#pragma unroll
+        for (int j = 0; j < NW; ++j) w[j] = 1.0f;
+      }
+      float o0[4], o1[4];
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4) {
+        const int c = k4 + RP;
+        float acc0 = a.t.g[0] * w[c];
+        float acc1 = (OP == MFISH_CONV_GD) ? a.t.d[0] * w[c] : 0.f;
+#pragma unroll
+        for (int k = 1; k <= R; ++k) {
+          float sN = w[c - k] + w[c + k];
+          acc0 = fmaf(a.t.g[k], sN, acc0);
+          if (OP == MFISH_CONV_GD) acc1 = fmaf(a.t.d[k], sN, acc1);
+        }
+        o0[k4] = acc0;
+        o1[k4] = acc1;
+      }
+      float* __restrict__ d0 = a.out0 + row * ny + y0;
+      if (vst && y0 + 3 < ny) {
+        *reinterpret_cast<float4*>(d0) = make_float4(o0[0], o0[1], o0[2], o0[3]);
+        if (OP == MFISH_CONV_GD)
+          *reinterpret_cast<float4*>(a.out1 + row * ny + y0) = make_float4(o1[0], o1[1], o1[2], o1[3]);
+      } else {
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+          if (y0 + k4 < ny) {
+            d0[k4] = o0[k4];
+            if (OP == MFISH_CONV_GD) a.out1[row * ny + y0 + k4] = o1[k4];
+          }
+        }
       }
     }
+    __syncthreads();  // every thread is done with this stage
   }
 }
 
@@ -442,35 +495,6 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) {
   return *reinterpret_cast<float2*>(&rd);
 }
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t"
-      "}" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-// TMA bulk copy global -> shared, completion signalled on the mbarrier (16-byte aligned, size % 16 == 0)
-__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, unsigned bytes,
-                                            unsigned long long* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst_smem)),
-               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
 template <int R>
 struct YZArgs {
   const float* in;
@@ -712,7 +736,7 @@ static int launch_y(const PassDesc& p) {
   a.bmode = p.boundary;
   a.mm = p.mm;
   fill_taps<R>(a.t, p.g, p.d, p.radius);
-  int64_t blocks = a.nrows * a.nseg;
+  int64_t blocks = ((a.nrows + YROWS - 1) / YROWS) * a.nseg;
   MFISH_REQUIRE(blocks < (1ll << 31), "sepconv(y): too many row segments");
   ProfScope prof(p.op == MFISH_CONV_G ? "conv_y_g" : "conv_y_gd", p.st);
   if (p.op == MFISH_CONV_G)
