@@ -249,10 +249,12 @@ class DeviceOps:
 
 # ------------------------------------------------------------------------ slab-mode pipeline
 def slab_find_spots_snrfilter(img_slab: torch.Tensor, mask_slab: torch.Tensor, lay: SlabLayout, sigma=2.0,
-                              t_spot=0.025, snr=None, ops=None, group=None):
+                              t_spot=0.025, snr=None, ops=None, group=None, full_table=True):
     """``find_spots_snrfilter`` (modules/muscle_fish.py:281-402) on a z-slab decomposed mosaic.
     ``img_slab`` float32 / ``mask_slab`` uint8, both ``[nz_local][nx][ny]``.  Every rank returns the
-    same global result: dict(spots (N,4) float64 [x,y,z,sigma], spots_masked, intensity, baseline, snr)."""
+    same global result: dict(spots (N,4) float64 [x,y,z,sigma], spots_masked, intensity, baseline, snr).
+    ``full_table=False`` skips the host copy of the per-spot table of ALL mask-passing spots
+    (``spots_masked`` / ``intensity``, the reference's ``spot_data``) and returns only the kept spots."""
     with _phase("setup"):
         ops = ops or DeviceOps()
     dev = img_slab.device
@@ -353,15 +355,25 @@ def slab_find_spots_snrfilter(img_slab: torch.Tensor, mask_slab: torch.Tensor, l
             thresh = T.lerp(pair[0], pair[1], g) / (baseline * np.sqrt(10))
             snr = max(thresh, np.sqrt(10))
         keep_d = inten_d / baseline > snr
+        kept_d = xyz[keep_d]
+
+    def table(xyz_host):
+        out = np.empty((len(xyz_host), 4), dtype=np.float64)
+        out[:, :3] = xyz_host
+        out[:, 3] = float(sigma)
+        return out
+
     with _phase("d2h"):
-        xyz_h = xyz.cpu().numpy()
-        inten = inten_d.cpu().numpy()
-        keep = keep_d.cpu().numpy()
+        kept_h = kept_d.cpu().numpy()
+        if full_table:
+            xyz_h = xyz.cpu().numpy()
+            inten = inten_d.cpu().numpy()
     with _phase("host_tail"):
-        spots = np.empty((nm, 4), dtype=np.float64)
-        spots[:, :3] = xyz_h
-        spots[:, 3] = float(sigma)
-    return {"spots": spots[keep], "spots_masked": spots, "intensity": inten, "baseline": baseline, "snr": snr}
+        res = {"spots": table(kept_h), "baseline": baseline, "snr": snr, "n_masked": nm}
+        if full_table:
+            res["spots_masked"] = table(xyz_h)
+            res["intensity"] = inten
+    return res
 
 
 def slab_edt(notnuc_slab: torch.Tensor, lay: SlabLayout, sampling_xyz=(1.0, 1.0, 1.0), ops=None, group=None,

@@ -30,7 +30,7 @@ SAMPLING = (0.0577, 0.0577, 0.5)
 def step():
     t = {}
     torch.cuda.synchronize(); t0 = time.perf_counter()
-    res = P.slab_find_spots_snrfilter(img, fib, lay, sigma=2.0, t_spot=0.025)
+    res = P.slab_find_spots_snrfilter(img, fib, lay, sigma=2.0, t_spot=0.025, full_table=False)
     torch.cuda.synchronize(); t["spots"] = time.perf_counter() - t0; t0 = time.perf_counter()
     dmap = P.slab_edt(notnuc, lay, SAMPLING)
     torch.cuda.synchronize(); t["edt"] = time.perf_counter() - t0; t0 = time.perf_counter()
