@@ -138,6 +138,18 @@ int mfish_log3d_range_f32(const float* in_dev, float* out_dev, float* tmp1_dev, 
                           float* tmp3_dev, int64_t nz, int64_t nx, int64_t ny, double sigma,
                           const float* norm_minmax_dev, int64_t out_z0, int64_t out_z1, void* stream);
 
+/* LoG response + thresholded 26-neighbour non-max suppression + compaction in one call (one scale;
+ * skimage.feature.blob_log with num_sigma=1 as modules/muscle_fish.py:333,661 call it).  The x pass of
+ * the LoG appends, next to the volume it writes, every voxel above the threshold that is a maximum
+ * along x (warp ballot + one atomic per warp); the 3x3x3 test then runs on those candidates only.
+ * out_dev receives the LoG volume as mfish_log3d_f32 would write it.  cand_ws_dev: (cand_cap + 1) uint32.
+ * *count_dev == 0xFFFFFFFF: candidate overflow, call mfish_nms_compact_f32 on out_dev.             */
+int mfish_log3d_peaks_f32(const float* in_dev, float* out_dev, float* tmp1_dev, float* tmp2_dev,
+                          float* tmp3_dev, int64_t nz, int64_t nx, int64_t ny, double sigma,
+                          const float* norm_minmax_dev, float threshold, void* cand_ws_dev, int64_t cand_cap,
+                          int64_t* out_idx_dev, float* out_val_dev, uint32_t* count_dev, int64_t capacity,
+                          void* stream);
+
 /* ---- spot detection --------------------------------------------------- *
  * skimage.feature.peak_local_max(cube, threshold_abs=t, footprint=ones(3^4))
  * as blob_log calls it: v > t and v >= every in-volume neighbour in

@@ -46,6 +46,7 @@ SIGNATURES = {
     "mfish_gaussian3d_f32": (_i, [_p, _p, _p, _i64, _i64, _i64, _p, _i, _p, _p]),
     "mfish_log3d_f32": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _d, _p, _p]),
     "mfish_log3d_range_f32": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _d, _p, _i64, _i64, _p]),
+    "mfish_log3d_peaks_f32": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _d, _p, _f, _p, _i64, _p, _p, _p, _i64, _p]),
     "mfish_nms_compact_f32": (_i, [_p, _i64, _i64, _i64, _i64, _f, _p, _p, _p, _i64, _p]),
     "mfish_rank_prune": (_i, [_p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p, _p, _p]),
     "mfish_overlap_pairs": (_i, [_p, _i64, _i64, _i64, _i64, _i64, _p, _p, _p, _i64, _p]),

@@ -158,6 +158,36 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_compact_kernel(const NmsArgs 
   }
 }
 
+// Second half of the fused LoG + NMS path: full neighbourhood test of the candidates the x pass emitted.
+__global__ void __launch_bounds__(256) nms_verify_kernel(const NmsArgs a, const uint32_t* __restrict__ cand,
+                                                         const uint32_t* __restrict__ cand_count, uint32_t cand_cap) {
+  const uint32_t n = *cand_count;
+  if (n > cand_cap) {  // candidate overflow: tell the host to run the stand-alone kernel
+    if (blockIdx.x == 0 && threadIdx.x == 0) *a.count = 0xFFFFFFFFu;
+    return;
+  }
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    int s, z, x, y;
+    nms_decode(a, (int64_t)cand[k], s, z, x, y);
+    const float v = __ldg(a.cube + cand[k]);
+    if (is_peak(a, s, z, x, y, v)) emit_peak(a, s, z, x, y, v);
+  }
+}
+
+int nms_verify_candidates(const float* cube, int64_t nz, int64_t nx, int64_t ny, float thr, const uint32_t* cand,
+                          const uint32_t* cand_count, uint32_t cand_cap, int64_t* out_idx, float* out_val,
+                          uint32_t* count, int64_t capacity, cudaStream_t st) {
+  if (cudaMemsetAsync(count, 0, sizeof(uint32_t), st) != cudaSuccess) {
+    set_error("nms_verify: memset failed");
+    return MFISH_ERR_CUDA;
+  }
+  NmsArgs a{cube, 1, (int)nz, (int)nx, (int)ny, thr, out_idx, out_val, count, capacity};
+  ProfScope prof("nms_verify", st);
+  nms_verify_kernel<<<num_sms() * 4, 256, 0, st>>>(a, cand, cand_count, cand_cap);
+  count_launch(1);
+  return check_launch("nms_verify");
+}
+
 // ------------------------------------------------------------------------------------------
 // ranking + equal-sigma prune
 // ------------------------------------------------------------------------------------------

@@ -296,6 +296,12 @@ struct SArgs {
   int chunk_len;         // samples handled per blockIdx.z
   int bmode;
   float scale;
+  // optional (OP == LAST only): outputs above cand_thr that are not beaten by their two neighbours along
+  // the walked axis are appended (element offset) to cand[]; cand_count may exceed cand_cap (overflow)
+  float cand_thr;
+  uint32_t* cand;
+  uint32_t* cand_count;
+  uint32_t cand_cap;
   Taps<R> t;
 };
 
@@ -306,7 +312,7 @@ __device__ __forceinline__ int bmap1_rt(int i, int n, int bmode) {
                                          : bmap1<MFISH_BOUNDARY_REFLECT>(i, n);
 }
 
-template <int R, int OP>
+template <int R, int OP, bool EMIT = false>
 __global__ void __launch_bounds__(STHREADS, StridedTune<OP>::kMinBlocks) conv_strided_kernel(const SArgs<R> a) {
   constexpr int LOOKAHEAD = StridedTune<OP>::kLookahead;
   constexpr int W = 2 * R + 1;
@@ -327,6 +333,21 @@ __global__ void __launch_bounds__(STHREADS, StridedTune<OP>::kMinBlocks) conv_st
   float* __restrict__ q0 = a.out0;
   float* __restrict__ q1 = a.out1;
   const int klast = ke - 1 + R;  // last plane any output of this chunk needs
+
+  // candidate emission (fused threshold + 1-D non-max test of the LoG response, see SArgs)
+  constexpr bool emit = EMIT && (OP == MFISH_CONV_LAST);
+  float vm1 = -INFINITY, vm2 = -INFINITY;  // the two previous outputs of this thread
+  auto emit_cand = [&](unsigned off, float v) {
+    const unsigned active = __activemask();
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(active) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(a.cand_count, (uint32_t)__popc(active));
+    base = __shfl_sync(active, base, leader);
+    const uint32_t pos = base + __popc(active & ((1u << lane) - 1));
+    if (pos < a.cand_cap) a.cand[pos] = off;
+    (void)v;
+  };
 
   float r0[RS];
   float r1[TWO_IN ? RS : 1];
@@ -349,6 +370,8 @@ __global__ void __launch_bounds__(STHREADS, StridedTune<OP>::kMinBlocks) conv_st
     constexpr bool FAST = decltype(fast_tag)::value;
     const float* __restrict__ p0n = p0 + (unsigned)((R + LOOKAHEAD) * st);
     const float* __restrict__ p1n = TWO_IN ? p1 + (unsigned)((R + LOOKAHEAD) * st) : nullptr;
+    const unsigned off_first = off_k;
+    unsigned cmask = 0;  // bit u: the output BEFORE output u of this sweep is a candidate
 #pragma unroll
     for (int u = 0; u < RS; ++u) {
       const int k = k0 + u;
@@ -388,9 +411,22 @@ __global__ void __launch_bounds__(STHREADS, StridedTune<OP>::kMinBlocks) conv_st
           q0[off_k] = accG0;
           q1[off_k] = accD0 + accG1;
         } else {
-          q0[off_k] = a.scale * (accD0 + accG1);
+          const float v = a.scale * (accD0 + accG1);
+          q0[off_k] = v;
+          if (emit) {
+            cmask |= (unsigned)(vm1 > a.cand_thr && vm1 >= vm2 && vm1 >= v) << u;
+            vm2 = vm1;
+            vm1 = v;
+          }
         }
         off_k += (unsigned)st;
+      }
+    }
+    if (emit) {
+      while (cmask) {  // rare: a few candidates per thousand voxels
+        const int u = __ffs(cmask) - 1;
+        cmask &= cmask - 1;
+        emit_cand(off_first + (unsigned)((u - 1) * st), 0.f);
       }
     }
   };
@@ -404,6 +440,8 @@ __global__ void __launch_bounds__(STHREADS, StridedTune<OP>::kMinBlocks) conv_st
       sweep(std::false_type{}, k0, off_k);
     off_k += (unsigned)(RS * st);
   }
+  // the last output of the chunk: its successor belongs to another thread block (or does not exist)
+  if (emit && vm1 > a.cand_thr && vm1 >= vm2) emit_cand(i0 + (unsigned)((ke - 1) * st), vm1);
 }
 
 struct SGenArgs {
@@ -707,6 +745,10 @@ struct PassDesc {
   cudaStream_t st;
   int out_begin = 0;  // z axis only: produce outputs for [out_begin, out_end); out_end < 0 = whole line
   int out_end = -1;
+  float cand_thr = 0.f;  // LAST only: candidate emission (see SArgs)
+  uint32_t* cand = nullptr;
+  uint32_t* cand_count = nullptr;
+  uint32_t cand_cap = 0;
 };
 
 static int upload_taps(const PassDesc& p, float** dg, float** dd) {
@@ -772,6 +814,10 @@ static int launch_strided(const PassDesc& p) {
   a.scale = p.scale;
   a.out_begin = p.out_begin;
   a.out_end = p.out_end < 0 ? a.L : p.out_end;
+  a.cand_thr = p.cand_thr;
+  a.cand = p.op == MFISH_CONV_LAST ? p.cand : nullptr;
+  a.cand_count = p.cand_count;
+  a.cand_cap = p.cand_cap;
   const int nout = a.out_end - a.out_begin;
   fill_taps<R>(a.t, p.g, p.d, p.radius);
   // split long lines into chunks until the grid holds >= ~4 waves of threads
@@ -790,7 +836,12 @@ static int launch_strided(const PassDesc& p) {
     case MFISH_CONV_G: conv_strided_kernel<R, MFISH_CONV_G><<<grid, STHREADS, 0, p.st>>>(a); break;
     case MFISH_CONV_GD: conv_strided_kernel<R, MFISH_CONV_GD><<<grid, STHREADS, 0, p.st>>>(a); break;
     case MFISH_CONV_MID: conv_strided_kernel<R, MFISH_CONV_MID><<<grid, STHREADS, 0, p.st>>>(a); break;
-    default: conv_strided_kernel<R, MFISH_CONV_LAST><<<grid, STHREADS, 0, p.st>>>(a); break;
+    default:
+      if (a.cand != nullptr)
+        conv_strided_kernel<R, MFISH_CONV_LAST, true><<<grid, STHREADS, 0, p.st>>>(a);
+      else
+        conv_strided_kernel<R, MFISH_CONV_LAST><<<grid, STHREADS, 0, p.st>>>(a);
+      break;
   }
   count_launch(1);
   return check_launch("conv_strided");
@@ -869,7 +920,13 @@ static int launch_R(const PassDesc& p) {
   // the ring walker folds indices once, so the line must be at least R long and the plane
   // stride must fit 32 bits; anything else goes through the gather fallback
   const int64_t L = p.axis == MFISH_AXIS_Z ? p.nz : p.nx;
-  if (L < R || p.nz * p.nx * p.ny >= (1ll << 32)) return launch_generic(p);
+  if (L < R || p.nz * p.nx * p.ny >= (1ll << 32)) {
+    if (p.cand != nullptr) {
+      set_error("sepconv: candidate emission needs the register-ring kernel");
+      return MFISH_ERR_UNSUPPORTED;
+    }
+    return launch_generic(p);
+  }
   return launch_strided<R>(p);
 }
 
@@ -1013,9 +1070,10 @@ extern "C" int mfish_gaussian3d_f32(const float* in_dev, float* out_dev, float* 
 
 // LoG of the planes [out_z0, out_z1) of a z-extended slab: the y pass runs on every plane, the z pass
 // produces only the requested planes (its inputs reach `radius` planes further), the x pass runs on those.
-extern "C" int mfish_log3d_range_f32(const float* in_dev, float* out_dev, float* tmp1_dev, float* tmp2_dev,
-                                     float* tmp3_dev, int64_t nz, int64_t nx, int64_t ny, double sigma,
-                                     const float* norm_minmax_dev, int64_t out_z0, int64_t out_z1, void* stream) {
+static int log3d_impl(const float* in_dev, float* out_dev, float* tmp1_dev, float* tmp2_dev, float* tmp3_dev,
+                      int64_t nz, int64_t nx, int64_t ny, double sigma, const float* norm_minmax_dev, int64_t out_z0,
+                      int64_t out_z1, float cand_thr, uint32_t* cand, uint32_t* cand_count, uint32_t cand_cap,
+                      void* stream) {
   MFISH_REQUIRE(in_dev && out_dev && tmp1_dev && tmp2_dev && tmp3_dev, "log3d: null pointer");
   MFISH_REQUIRE(sigma > 0.0, "log3d: sigma must be positive");
   MFISH_REQUIRE(out_z0 >= 0 && out_z0 < out_z1 && out_z1 <= nz, "log3d: bad plane range");
@@ -1055,7 +1113,54 @@ extern "C" int mfish_log3d_range_f32(const float* in_dev, float* out_dev, float*
   const int64_t off = out_z0 * nx * ny;
   PassDesc px{tmp2_dev + off, tmp3_dev + off, out_dev + off, nullptr, out_z1 - out_z0, nx, ny, MFISH_AXIS_X, g.data(),
               d.data(), radius, MFISH_BOUNDARY_REFLECT, MFISH_CONV_LAST, (float)(-(sigma * sigma)), nullptr, st};
+  if (cand != nullptr) {
+    if (radius > 16 || !whole) {
+      set_error("log3d: fused candidate emission supports radius <= 16 on whole volumes");
+      return MFISH_ERR_UNSUPPORTED;
+    }
+    px.cand_thr = cand_thr;
+    px.cand = cand;
+    px.cand_count = cand_count;
+    px.cand_cap = cand_cap;
+  }
   return run_pass(px);
+}
+
+extern "C" int mfish_log3d_range_f32(const float* in_dev, float* out_dev, float* tmp1_dev, float* tmp2_dev,
+                                     float* tmp3_dev, int64_t nz, int64_t nx, int64_t ny, double sigma,
+                                     const float* norm_minmax_dev, int64_t out_z0, int64_t out_z1, void* stream) {
+  return log3d_impl(in_dev, out_dev, tmp1_dev, tmp2_dev, tmp3_dev, nz, nx, ny, sigma, norm_minmax_dev, out_z0, out_z1,
+                    0.f, nullptr, nullptr, 0, stream);
+}
+
+namespace mfish {
+int nms_verify_candidates(const float* cube, int64_t nz, int64_t nx, int64_t ny, float thr, const uint32_t* cand,
+                          const uint32_t* cand_count, uint32_t cand_cap, int64_t* out_idx, float* out_val,
+                          uint32_t* count, int64_t capacity, cudaStream_t st);
+}
+
+// LoG + thresholded 26-neighbour non-max suppression + compaction in one call (single scale): the x pass
+// emits, next to the LoG volume, the voxels above the threshold that are 1-D maxima along x (warp-ballot
+// append); a second, tiny kernel checks the full 3x3x3 neighbourhood of those candidates only.  Saves the
+// stand-alone NMS pass over the volume.  cand_ws_dev: (cand_cap + 1) uint32 of scratch.  *count_dev =
+// 0xFFFFFFFF reports a candidate overflow: run mfish_nms_compact_f32 on out_dev instead.
+extern "C" int mfish_log3d_peaks_f32(const float* in_dev, float* out_dev, float* tmp1_dev, float* tmp2_dev,
+                                     float* tmp3_dev, int64_t nz, int64_t nx, int64_t ny, double sigma,
+                                     const float* norm_minmax_dev, float threshold, void* cand_ws_dev,
+                                     int64_t cand_cap, int64_t* out_idx_dev, float* out_val_dev, uint32_t* count_dev,
+                                     int64_t capacity, void* stream) {
+  MFISH_REQUIRE(cand_ws_dev && out_idx_dev && out_val_dev && count_dev, "log3d_peaks: null pointer");
+  MFISH_REQUIRE(cand_cap > 0 && cand_cap < (1ll << 31) && capacity > 0, "log3d_peaks: bad capacity");
+  MFISH_REQUIRE(threshold >= 0.f, "log3d_peaks: threshold must be >= 0");
+  cudaStream_t st = as_stream(stream);
+  uint32_t* cand_count = reinterpret_cast<uint32_t*>(cand_ws_dev);
+  uint32_t* cand = cand_count + 1;
+  MFISH_CUDA(cudaMemsetAsync(cand_count, 0, sizeof(uint32_t), st));
+  int rc = log3d_impl(in_dev, out_dev, tmp1_dev, tmp2_dev, tmp3_dev, nz, nx, ny, sigma, norm_minmax_dev, 0, nz,
+                      threshold, cand, cand_count, (uint32_t)cand_cap, stream);
+  if (rc != MFISH_OK) return rc;
+  return nms_verify_candidates(out_dev, nz, nx, ny, threshold, cand, cand_count, (uint32_t)cand_cap, out_idx_dev,
+                               out_val_dev, count_dev, capacity, st);
 }
 
 extern "C" int mfish_log3d_f32(const float* in_dev, float* out_dev, float* tmp1_dev, float* tmp2_dev,

@@ -316,6 +316,46 @@ def detect_peaks(cube: torch.Tensor, threshold: float, capacity: int | None = No
     return detect_peaks_async(cube, threshold, capacity)()
 
 
+def log_peaks_async(vol: Volume, sigma: float, threshold: float, out: torch.Tensor | None = None,
+                    capacity: int | None = None):
+    """One scale of blob_log in a single library call: LoG volume + thresholded 26-neighbour NMS +
+    compaction, the candidate test fused into the last LoG pass.  Returns ``(log_volume, finish)``;
+    ``finish()`` waits for the count and returns (raster_idx, value) like ``detect_peaks``."""
+    if float(threshold) < 0:
+        raise ValueError("negative thresholds are not supported (reference zero-pads the scale axis)")
+    d = vol.data
+    shp, dev = d.shape, d.device
+    nz, nx, ny = shp
+    if d.numel() >= (1 << 32):  # candidate offsets are 32-bit: fall back to the two-call form
+        log = log_volume(vol, sigma, out)
+        return log, detect_peaks_async(log, threshold, capacity)
+    if out is None:
+        out = torch.empty(shp, dtype=torch.float32, device=dev)
+    t1 = WS.get("log1", shp, torch.float32, dev)
+    t2 = WS.get("log2", shp, torch.float32, dev)
+    t3 = WS.get("log3", shp, torch.float32, dev)
+    thr = max(float(threshold), 0.0)
+    cap = int(capacity or max(_DEFAULT_CAPACITY, d.numel() // 512))
+    cand_cap = max(1 << 22, d.numel() // 64)
+    cand_ws = WS.get("pk_cand", (cand_cap + 1,), torch.int32, dev)
+    count = torch.zeros(1, dtype=torch.int32, device=dev)
+    idx = WS.get("pk_idx", (cap,), torch.int64, dev)
+    val = WS.get("pk_val", (cap,), torch.float32, dev)
+    L.check(L.lib().mfish_log3d_peaks_f32(d.data_ptr(), out.data_ptr(), t1.data_ptr(), t2.data_ptr(), t3.data_ptr(),
+                                          nz, nx, ny, float(sigma),
+                                          vol.minmax.data_ptr() if vol.minmax is not None else None, thr,
+                                          cand_ws.data_ptr(), cand_cap, idx.data_ptr(), val.data_ptr(),
+                                          count.data_ptr(), cap, _stream()))
+
+    def finish():
+        n = int(count.item()) & 0xFFFFFFFF
+        if n == 0xFFFFFFFF or n > cap:  # candidate overflow / result overflow: stand-alone kernel
+            return detect_peaks(out, threshold, None if n == 0xFFFFFFFF else int(n * 1.25) + 1024)
+        return idx[:n], val[:n]
+
+    return out, finish
+
+
 def rank_prune_equal(idx, val, dims_sxyz, cutoff_sq: int):
     """Order peaks (descending value, ties by raster index) and apply the equal-sigma prune.
     Returns (idx_ranked, val_ranked, alive uint8), all on the device."""
@@ -389,12 +429,15 @@ def blob_log(vol: Volume, min_sigma, max_sigma, num_sigma, threshold, overlap=0.
     callable) is run after the filters and the peak detection have been queued and before the host
     waits for the peak count -- callers queue independent device work there."""
     sigmas = T.sigma_list(min_sigma, max_sigma, num_sigma)
-    if cube is None:
-        cube = log_cube(vol, sigmas)
     ns = len(sigmas)
     nz, nx, ny = vol.data.shape
     dims = (ns, nx, ny, nz)
-    peaks = detect_peaks_async(cube, threshold)
+    if cube is None and ns == 1 and T.gaussian_radius(float(sigmas[0])) <= 16 and min(nz, nx) > 16:
+        _, peaks = log_peaks_async(vol, float(sigmas[0]), threshold)  # fused LoG + NMS
+    else:
+        if cube is None:
+            cube = log_cube(vol, sigmas)
+        peaks = detect_peaks_async(cube, threshold)
     if before_sync is not None:
         before_sync()
     idx, val = peaks()
@@ -650,8 +693,7 @@ def analyze_stack(img_zxy: torch.Tensor, fiber_zxy: torch.Tensor, notnuc_zxy: to
     mm = t.run("minmax", minmax, img_zxy)
     vol = Volume(img_zxy, mm)
     log = WS.get("log_out", img_zxy.shape, torch.float32, img_zxy.device)
-    t.run("log3d", log_volume, vol, sigma, log)
-    peaks = t.run("nms", detect_peaks_async, log, t_spot)
+    _, peaks = t.run("log3d_nms", log_peaks_async, vol, sigma, t_spot, log)
     baseline_f = t.run("quantile", masked_percentile_async, vol, fiber_zxy, 25)
     # the distance transform runs on a side stream, after the streaming kernels above, so that the
     # small kernels and host round trips of the spot-list handling proceed while it runs

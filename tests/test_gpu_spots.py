@@ -332,3 +332,28 @@ def test_golden_spots(golden):
     assert match_fraction(got, golden["spots_s2"]) >= MIN_MATCH
     got_f, _ = mf.find_spots_snrfilter(golden["img"], sigma=2.0, t_spot=0.025, mask=golden["fiber_mask"])
     assert match_fraction(got_f, golden["spots_snr_s2"]) >= MIN_MATCH
+
+
+@pytest.mark.parametrize("sigma,shape", [(2.0, (96, 80, 24)), (1.0, (61, 77, 19)), (3.0, (64, 64, 40))])
+def test_fused_log_peaks_equals_two_call_form(sigma, shape):
+    """mfish_log3d_peaks_f32 (candidates emitted by the last LoG pass) == LoG volume + stand-alone NMS"""
+    import torch
+    from muscle_fish_b200 import device as D, synth
+    st = synth.make_stack(shape=shape, n_spots=80, n_nuclei=1, seed=23, nuc_semi=(8.0, 6.0, 3.0))
+    vol = D.ingest(st["img"])
+    log_a = D.log_volume(vol, sigma).clone()
+    idx_a, val_a = D.detect_peaks(log_a, 0.02)
+    log_b, fin = D.log_peaks_async(vol, sigma, 0.02)
+    idx_b, val_b = fin()
+    assert torch.equal(log_a, log_b)
+    oa, ob = torch.argsort(idx_a), torch.argsort(idx_b)
+    assert idx_a.numel() > 20
+    assert torch.equal(idx_a[oa], idx_b[ob]) and torch.equal(val_a[oa], val_b[ob])
+    # plateau / tie handling is identical too: a quantised image produces many ties
+    q = np.round(st["img"] / 40.0) * 40.0
+    volq = D.ingest(q.astype(np.float32))
+    la = D.log_volume(volq, sigma).clone()
+    ia, _ = D.detect_peaks(la, 0.0)
+    _, finq = D.log_peaks_async(volq, sigma, 0.0)
+    ib, _ = finq()
+    assert torch.equal(torch.sort(ia).values, torch.sort(ib).values)
