@@ -79,6 +79,32 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
                : "memory");
 }
 
+// packed fp32 pairs (SASS: FFMA2 / FMUL2 / FADD2; the scalar operand is broadcast)
+__device__ __forceinline__ float2 fma2(float a, float2 b, float2 c) {
+  float2 aa = make_float2(a, a);
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&aa);
+  unsigned long long rb = *reinterpret_cast<unsigned long long*>(&b);
+  unsigned long long rc = *reinterpret_cast<unsigned long long*>(&c);
+  unsigned long long rd;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 mul2(float a, float2 b) {
+  float2 aa = make_float2(a, a);
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&aa);
+  unsigned long long rb = *reinterpret_cast<unsigned long long*>(&b);
+  unsigned long long rd;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a);
+  unsigned long long rb = *reinterpret_cast<unsigned long long*>(&b);
+  unsigned long long rd;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2*>(&rd);
+}
+
 // --------------------------------------------------------------------------------------------
 // contiguous (y) axis
 // --------------------------------------------------------------------------------------------
@@ -104,7 +130,6 @@ template <int R, int OP>
 __global__ void __launch_bounds__(YTHREADS) conv_y_kernel(const YArgs<R> a) {
   constexpr int RP = (R + 3) & ~3;  // halo rounded up to a float4
   constexpr int NW = 4 + 2 * RP;    // register window per thread
-  constexpr unsigned BYTES = (YSEG + 2 * RP) * sizeof(float);
   __shared__ __align__(128) float buf[2][YSEG + 2 * RP];
   __shared__ __align__(8) unsigned long long bar[2];
 
@@ -119,33 +144,62 @@ __global__ void __launch_bounds__(YTHREADS) conv_y_kernel(const YArgs<R> a) {
   bool degen;
   load_norm(a.mm, mn, sc, degen);
 
-  const bool vec = ((ny & 3) == 0) && aligned16_dev(a.in);
-  // interior segments: the row segment + halo (raw voxels) is fetched by the TMA unit, one bulk copy
-  // per row, the copy of row i+1 in flight while row i is convolved
-  const bool interior = vec && (seg0 - RP >= 0) && (seg0 + YSEG + RP <= ny);
-  const float* __restrict__ seg_src = a.in + row_begin * ny + (seg0 - RP);
-  if (interior) {
+  // Rows whose length is a multiple of 4: the in-range part of the segment + halo (raw voxels) is
+  // fetched by the TMA unit, one bulk copy per row, the copy of row i+1 in flight while row i is
+  // convolved; the at most R out-of-range positions on either side of an edge segment are filled
+  // through the boundary map by the first R threads.
+  const bool tma = ((ny & 3) == 0) && aligned16_dev(a.in);
+  const int lo = max(seg0 - RP, 0), hi = min(seg0 + YSEG + RP, ny);
+  const unsigned bytes = (unsigned)(hi - lo) * (unsigned)sizeof(float);
+  const int dst_off = lo - (seg0 - RP);
+  const bool edge_lo = seg0 - RP < 0, edge_hi = seg0 + YSEG + RP > ny;
+  const float* __restrict__ row0 = a.in + row_begin * ny;
+  auto fill_halo = [&](float* stage, const float* __restrict__ src) {
+    if (t < R) {
+      if (edge_lo) {
+        const int y = -1 - t;
+        const int yy = a.bmode == MFISH_BOUNDARY_NEAREST ? bmap<MFISH_BOUNDARY_NEAREST>(y, ny)
+                                                         : bmap<MFISH_BOUNDARY_REFLECT>(y, ny);
+        stage[y - (seg0 - RP)] = __ldg(&src[yy]);
+      }
+      if (edge_hi) {
+        const int y = ny + t;
+        const int j = y - (seg0 - RP);
+        if (j < YSEG + 2 * RP) {
+          const int yy = a.bmode == MFISH_BOUNDARY_NEAREST ? bmap<MFISH_BOUNDARY_NEAREST>(y, ny)
+                                                           : bmap<MFISH_BOUNDARY_REFLECT>(y, ny);
+          stage[j] = __ldg(&src[yy]);
+        }
+      }
+    }
+  };
+  if (tma) {
     if (t == 0) {
       mbar_init(&bar[0], 1);
       mbar_init(&bar[1], 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    fill_halo(buf[0], row0);
     __syncthreads();
     if (t == 0) {
-      mbar_expect_tx(&bar[0], BYTES);
-      tma_load_1d(buf[0], seg_src, BYTES, &bar[0]);
+      mbar_expect_tx(&bar[0], bytes);
+      tma_load_1d(buf[0] + dst_off, row0 + lo, bytes, &bar[0]);
     }
   }
   const int y0 = seg0 + 4 * t;
-  const bool vst = vec && aligned16_dev(a.out0) && (OP != MFISH_CONV_GD || aligned16_dev(a.out1));
+  const bool vst = ((ny & 3) == 0) && aligned16_dev(a.out0) && (OP != MFISH_CONV_GD || aligned16_dev(a.out1));
 
   for (int i = 0; i < nrow; ++i) {
     const int64_t row = row_begin + i;
     float* cur = buf[i & 1];
-    if (interior) {
-      if (t == 0 && i + 1 < nrow) {  // the other stage was released by the barrier that ended row i-1
-        mbar_expect_tx(&bar[(i + 1) & 1], BYTES);
-        tma_load_1d(buf[(i + 1) & 1], seg_src + (int64_t)(i + 1) * ny, BYTES, &bar[(i + 1) & 1]);
+    if (tma) {
+      if (i + 1 < nrow) {  // the other stage was released by the barrier that ended row i-1
+        const float* __restrict__ nsrc = row0 + (int64_t)(i + 1) * ny;
+        if (t == 0) {
+          mbar_expect_tx(&bar[(i + 1) & 1], bytes);
+          tma_load_1d(buf[(i + 1) & 1] + dst_off, nsrc + lo, bytes, &bar[(i + 1) & 1]);
+        }
+        fill_halo(buf[(i + 1) & 1], nsrc);
       }
       mbar_wait(&bar[i & 1], (unsigned)((i >> 1) & 1));
     } else {
@@ -164,47 +218,52 @@ __global__ void __launch_bounds__(YTHREADS) conv_y_kernel(const YArgs<R> a) {
       __syncthreads();
     }
     if (y0 < ny) {
-      // register window; su.normalize_image is applied here, on load
-      float w[NW];
+      // register window as aligned pairs e[j] = (w[2j], w[2j+1]) and the shifted pairs
+      // o[j] = (w[2j+1], w[2j+2]); su.normalize_image is applied here, on load
+      float2 e[NW / 2], o[NW / 2 - 1];
       const float4* b4 = reinterpret_cast<const float4*>(cur + 4 * t);
+      const float2 nmn = make_float2(-mn, -mn);
 #pragma unroll
       for (int j = 0; j < NW / 4; ++j) {
         float4 v = b4[j];
-        w[4 * j + 0] = (v.x - mn) * sc;
-        w[4 * j + 1] = (v.y - mn) * sc;
-        w[4 * j + 2] = (v.z - mn) * sc;
-        w[4 * j + 3] = (v.w - mn) * sc;
+        e[2 * j + 0] = mul2(sc, add2(make_float2(v.x, v.y), nmn));
+        e[2 * j + 1] = mul2(sc, add2(make_float2(v.z, v.w), nmn));
       }
       if (degen) {
 #pragma unroll
-        for (int j = 0; j < NW; ++j) w[j] = 1.0f;
+        for (int j = 0; j < NW / 2; ++j) e[j] = make_float2(1.0f, 1.0f);
       }
-      float o0[4], o1[4];
 #pragma unroll
-      for (int k4 = 0; k4 < 4; ++k4) {
-        const int c = k4 + RP;
-        float acc0 = a.t.g[0] * w[c];
-        float acc1 = (OP == MFISH_CONV_GD) ? a.t.d[0] * w[c] : 0.f;
+      for (int j = 0; j < NW / 2 - 1; ++j) o[j] = make_float2(e[j].y, e[j + 1].x);
+      auto pair_at = [&](int idx) -> float2 { return (idx & 1) ? o[idx >> 1] : e[idx >> 1]; };
+      float2 o0[2], o1[2];
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        const int c = 2 * p + RP;
+        float2 acc0 = mul2(a.t.g[0], pair_at(c));
+        float2 acc1 = (OP == MFISH_CONV_GD) ? mul2(a.t.d[0], pair_at(c)) : make_float2(0.f, 0.f);
 #pragma unroll
         for (int k = 1; k <= R; ++k) {
-          float sN = w[c - k] + w[c + k];
-          acc0 = fmaf(a.t.g[k], sN, acc0);
-          if (OP == MFISH_CONV_GD) acc1 = fmaf(a.t.d[k], sN, acc1);
+          const float2 sN = add2(pair_at(c - k), pair_at(c + k));
+          acc0 = fma2(a.t.g[k], sN, acc0);
+          if (OP == MFISH_CONV_GD) acc1 = fma2(a.t.d[k], sN, acc1);
         }
-        o0[k4] = acc0;
-        o1[k4] = acc1;
+        o0[p] = acc0;
+        o1[p] = acc1;
       }
       float* __restrict__ d0 = a.out0 + row * ny + y0;
       if (vst && y0 + 3 < ny) {
-        *reinterpret_cast<float4*>(d0) = make_float4(o0[0], o0[1], o0[2], o0[3]);
+        *reinterpret_cast<float4*>(d0) = make_float4(o0[0].x, o0[0].y, o0[1].x, o0[1].y);
         if (OP == MFISH_CONV_GD)
-          *reinterpret_cast<float4*>(a.out1 + row * ny + y0) = make_float4(o1[0], o1[1], o1[2], o1[3]);
+          *reinterpret_cast<float4*>(a.out1 + row * ny + y0) = make_float4(o1[0].x, o1[0].y, o1[1].x, o1[1].y);
       } else {
+        const float r0[4] = {o0[0].x, o0[0].y, o0[1].x, o0[1].y};
+        const float r1[4] = {o1[0].x, o1[0].y, o1[1].x, o1[1].y};
 #pragma unroll
         for (int k4 = 0; k4 < 4; ++k4) {
           if (y0 + k4 < ny) {
-            d0[k4] = o0[k4];
-            if (OP == MFISH_CONV_GD) a.out1[row * ny + y0 + k4] = o1[k4];
+            d0[k4] = r0[k4];
+            if (OP == MFISH_CONV_GD) a.out1[row * ny + y0 + k4] = r1[k4];
           }
         }
       }
@@ -507,31 +566,6 @@ __global__ void __launch_bounds__(STHREADS) conv_strided_generic_kernel(const SG
 constexpr int YZ_THREADS = 256;
 constexpr int YZ_SEG = 2 * YZ_THREADS;
 constexpr int YZ_STAGES = 8;
-
-__device__ __forceinline__ float2 fma2(float a, float2 b, float2 c) {
-  float2 aa = make_float2(a, a);
-  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&aa);
-  unsigned long long rb = *reinterpret_cast<unsigned long long*>(&b);
-  unsigned long long rc = *reinterpret_cast<unsigned long long*>(&c);
-  unsigned long long rd;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
-  return *reinterpret_cast<float2*>(&rd);
-}
-__device__ __forceinline__ float2 mul2(float a, float2 b) {
-  float2 aa = make_float2(a, a);
-  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&aa);
-  unsigned long long rb = *reinterpret_cast<unsigned long long*>(&b);
-  unsigned long long rd;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
-  return *reinterpret_cast<float2*>(&rd);
-}
-__device__ __forceinline__ float2 add2(float2 a, float2 b) {
-  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a);
-  unsigned long long rb = *reinterpret_cast<unsigned long long*>(&b);
-  unsigned long long rd;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
-  return *reinterpret_cast<float2*>(&rd);
-}
 
 template <int R>
 struct YZArgs {

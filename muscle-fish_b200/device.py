@@ -9,6 +9,7 @@ never materialised -- the filters map ``(v - min) / (max - min)`` on load.
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -62,6 +63,7 @@ def host_to_device(arr) -> torch.Tensor:
 
 _COPY_STREAMS = {}
 _SIDE_STREAMS = {}
+_LIST_STREAMS = {}
 
 
 def _side_stream():
@@ -69,6 +71,17 @@ def _side_stream():
     st = _SIDE_STREAMS.get(dev)
     if st is None:
         st = _SIDE_STREAMS[dev] = torch.cuda.Stream()
+    return st
+
+
+def _list_stream():
+    """High-priority stream for the spot-list handling (tens of tiny kernels and a few host round
+    trips): its CTAs are dispatched ahead of the remaining CTAs of the distance transform running
+    on the side stream, instead of queueing behind each full-grid kernel."""
+    dev = torch.cuda.current_device()
+    st = _LIST_STREAMS.get(dev)
+    if st is None:
+        st = _LIST_STREAMS[dev] = torch.cuda.Stream(priority=-1)
     return st
 
 
@@ -704,16 +717,20 @@ def analyze_stack(img_zxy: torch.Tensor, fiber_zxy: torch.Tensor, notnuc_zxy: to
         dist = t.run("edt", edt, notnuc_zxy, sampling_xyz)
     idx, val = peaks()
     spots = np.empty((0, 4))
-    if idx.numel():
-        cutoff = max(T.prune_cutoff_sq(float(sigma), None, 0.5), 0)
-        idx_r, _, alive = t.run("rank_prune", rank_prune_equal, idx, val, dims, cutoff)
-        idx_h = idx_r[alive.bool()].cpu().numpy()
-        x, y, z, _ = decode_raster(idx_h, dims)
-        spots = np.stack([x, y, z, np.full(len(x), float(sigma))], axis=1).astype(np.float64)
-    if len(spots):
-        spots = spots[gather(fiber_zxy, spots) != 0]
-    inten = t.run("blur_pts", blur_at_points, vol, spots, (3, 3, 0.3), "nearest")
-    baseline = baseline_f()
+    hp = _list_stream() if os.environ.get("MFISH_LIST_PRIO", "1") != "0" else main
+    hp.wait_stream(main)
+    with torch.cuda.stream(hp):
+        if idx.numel():
+            cutoff = max(T.prune_cutoff_sq(float(sigma), None, 0.5), 0)
+            idx_r, _, alive = t.run("rank_prune", rank_prune_equal, idx, val, dims, cutoff)
+            idx_h = idx_r[alive.bool()].cpu().numpy()
+            x, y, z, _ = decode_raster(idx_h, dims)
+            spots = np.stack([x, y, z, np.full(len(x), float(sigma))], axis=1).astype(np.float64)
+        if len(spots):
+            spots = spots[gather(fiber_zxy, spots) != 0]
+        inten = t.run("blur_pts", blur_at_points, vol, spots, (3, 3, 0.3), "nearest")
+        baseline = baseline_f()
+    main.wait_stream(hp)
     if snr is None and len(spots):
         thresh = np.percentile(inten, 90) / (baseline * np.sqrt(10))
         snr = max(thresh, np.sqrt(10))
