@@ -70,6 +70,9 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
       "r"(parity)
       : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 // TMA bulk copy global -> shared, completion signalled on the mbarrier (16-byte aligned, size % 16 == 0)
 __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, unsigned bytes,
                                             unsigned long long* bar) {
@@ -567,6 +570,223 @@ constexpr int YZ_THREADS = 256;
 constexpr int YZ_SEG = 2 * YZ_THREADS;
 constexpr int YZ_STAGES = 8;
 
+// --------------------------------------------------------------------------------------------
+// strided (z or x) axis, TMA-staged walker (R <= 8, rows a multiple of 4 floats)
+// --------------------------------------------------------------------------------------------
+// A block owns a 256-float row segment and walks it along the axis.  One elected thread keeps
+// NST-2 rows in flight with bulk copies into a shared-memory stage ring (full/empty mbarriers per
+// stage; boundary handling is nothing but the source row of the copy), so the depth of the
+// prefetch costs shared memory instead of registers: each thread keeps only the 2R+1 window, as
+// float2 column pairs, and all tap arithmetic is packed (FADD2/FFMA2).  Same summation order as
+// conv_strided_kernel, hence bit-identical results.
+constexpr int TSEG = 256;
+constexpr int TTHREADS = 128;
+constexpr int TWARPS = TTHREADS / 32;
+constexpr int TMA_MAX_R = 8;
+constexpr int TSLACK = 3;  // a stage is refilled TSLACK steps after it was consumed
+template <int R, int OP>
+struct TmaTune {
+  static constexpr bool kTwoIn = (OP == MFISH_CONV_MID || OP == MFISH_CONV_LAST);
+  static constexpr int kW = 2 * R + 1;
+  // a multiple of the window length, so that one unrolled sweep of kStages steps sees every ring
+  // slot AND every stage at a compile-time index
+  static constexpr int kStages = kW >= 12 ? kW : kW * ((12 + kW - 1) / kW);
+  static constexpr int kMinBlocks = 5;
+  static constexpr size_t kSmem = (size_t)kStages * (kTwoIn ? 2 : 1) * TSEG * sizeof(float) + 2 * kStages * 8;
+};
+
+__device__ __forceinline__ bool elect_one() {
+  unsigned pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+__device__ __noinline__ void tma_issue_row(const float* in0, const float* in1, unsigned base, int k, int L, int bmode,
+                                           int st, unsigned dst_smem, unsigned bar_smem, unsigned bytes) {
+  if ((unsigned)k >= (unsigned)L) k = bmap1_rt(k, L, bmode);
+  const size_t off = (size_t)base + (size_t)k * (size_t)st;
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_smem),
+               "r"(in1 != nullptr ? 2u * bytes : bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(in0 + off), "r"(bytes), "r"(bar_smem)
+               : "memory");
+  if (in1 != nullptr)
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     dst_smem + (unsigned)(TSEG * sizeof(float))),
+                 "l"(in1 + off), "r"(bytes), "r"(bar_smem)
+                 : "memory");
+}
+
+// Rare path of the fused candidate emission (a few voxels per thousand are above the threshold), kept
+// out of line so that it costs the walker no registers: 1-D non-max test against the two neighbours
+// along the walked axis, re-read from the calling thread's own earlier stores.  A neighbour that is
+// not written yet (next sweep / another block) counts as passed: the verify kernel applies the full
+// 26-neighbour rule to every candidate anyway.
+__device__ __noinline__ void emit_sweep_candidates(const float* out0, unsigned off_first, unsigned st, unsigned cm,
+                                                   int o0, int nout, int nst, float thr, uint32_t* cand,
+                                                   uint32_t* cand_count, uint32_t cand_cap) {
+  auto emit_cand = [&](unsigned off) {
+    const unsigned active = __activemask();
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(active) - 1;
+    uint32_t b = 0;
+    if (lane == leader) b = atomicAdd(cand_count, (uint32_t)__popc(active));
+    b = __shfl_sync(active, b, leader);
+    const uint32_t pos = b + __popc(active & ((1u << lane) - 1));
+    if (pos < cand_cap) cand[pos] = off;
+  };
+  while (cm) {
+    const int u = __ffs(cm) - 1;
+    cm &= cm - 1;
+    const unsigned off = off_first + (unsigned)u * st;
+    const float2 v = *reinterpret_cast<const float2*>(out0 + off);
+    float2 pv = make_float2(-INFINITY, -INFINITY), nx = pv;
+    if (o0 + u > 0) pv = *reinterpret_cast<const float2*>(out0 + (off - st));
+    if (u + 1 < nst && o0 + u + 1 < nout) nx = *reinterpret_cast<const float2*>(out0 + (off + st));
+    if (v.x > thr && v.x >= pv.x && v.x >= nx.x) emit_cand(off);
+    if (v.y > thr && v.y >= pv.y && v.y >= nx.y) emit_cand(off + 1u);
+  }
+}
+
+template <int R, int OP, bool EMIT = false>
+__global__ void __launch_bounds__(TTHREADS, TmaTune<R, OP>::kMinBlocks) conv_strided_tma_kernel(const SArgs<R> a) {
+  constexpr int W = 2 * R + 1;
+  constexpr bool TWO_IN = TmaTune<R, OP>::kTwoIn;
+  constexpr int NIN = TWO_IN ? 2 : 1;
+  constexpr int NST = TmaTune<R, OP>::kStages;
+  constexpr int LEAD = NST - TSLACK;  // rows in flight ahead of the consumers
+  constexpr unsigned STAGE_BYTES = NIN * TSEG * sizeof(float);
+  static_assert(NST % W == 0 && 2 * R < NST && LEAD >= 4, "stage ring geometry");
+  extern __shared__ __align__(128) unsigned char tsm[];
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(tsm + (size_t)NST * STAGE_BYTES);
+  unsigned long long* empty = full + NST;
+
+  const int t = threadIdx.x;
+  const int wid = __shfl_sync(0xffffffffu, t >> 5, 0);  // warp-uniform by construction
+  const int64_t seg0 = (int64_t)blockIdx.x * TSEG;
+  const int nvalid = (int)min((int64_t)TSEG, a.inner - seg0);  // a multiple of 4 (launch precondition)
+  const unsigned base = (unsigned)((int64_t)blockIdx.y * a.outer_stride + seg0);
+  const int kb = a.out_begin + blockIdx.z * a.chunk_len;
+  const int ke = min(a.out_end, kb + a.chunk_len);
+  if (kb >= ke) return;
+  const int nout = ke - kb;
+  const int nrows = nout + 2 * R;  // line positions kb-R .. ke-1+R, boundary-mapped
+  const unsigned bytes = (unsigned)nvalid * (unsigned)sizeof(float);
+  const int st = a.stride;
+  const bool live = 2 * t < nvalid;
+
+  if (t == 0) {
+#pragma unroll 1
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], TWARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // one thread: fetch row m of the chunk into stage `sidx` (out of line: one copy of the address
+  // arithmetic instead of one per unrolled step keeps the sweep inside the instruction cache)
+  auto issue = [&](int m, int sidx) {
+    tma_issue_row(a.in0, TWO_IN ? a.in1 : nullptr, base, kb - R + m, a.L, a.bmode, st,
+                  smem_u32(tsm) + (unsigned)sidx * STAGE_BYTES, smem_u32(&full[sidx]), bytes);
+  };
+  if (wid == 0) {
+    if (elect_one()) {
+#pragma unroll 1
+      for (int m = 0; m < LEAD && m < nrows; ++m) issue(m, m);
+    }
+  }
+
+  // Consume row m (stage m % NST); the warp on duty refills the stage consumed TSLACK steps ago with
+  // row m + LEAD.  `mc` is m modulo 2*NST at compile time (stage and barrier parity), `m` the row.
+  auto fetch = [&](int m, int mc, unsigned phase, int duty, float2& v0, float2& v1) {
+    const int sidx = mc % NST;
+    const unsigned par = ((unsigned)(mc / NST) & 1u) ^ phase;
+    if (wid == duty) {
+      const int mn = m + LEAD;
+      if (mn < nrows) {
+        const int pc = mc + 2 * NST - TSLACK;  // (m - TSLACK) mod 2*NST
+        if (m >= TSLACK) mbar_wait(&empty[pc % NST], ((unsigned)(pc / NST) & 1u) ^ phase);
+        if (elect_one()) issue(mn, pc % NST);
+      }
+    }
+    mbar_wait(&full[sidx], par);
+    const float2* sp = reinterpret_cast<const float2*>(tsm + (size_t)sidx * STAGE_BYTES) + t;
+    v0 = sp[0];
+    if (TWO_IN) v1 = sp[TSEG / 2];
+    __syncwarp();
+    if ((t & 31) == 0) mbar_arrive(&empty[sidx]);
+  };
+
+  // candidate emission (fused threshold + 1-D non-max test of the LoG response, see SArgs)
+  constexpr bool emit = EMIT && (OP == MFISH_CONV_LAST);
+
+  float2 r0[W];
+  float2 r1[TWO_IN ? W : 1];
+  float2 dummy;
+#pragma unroll
+  for (int j = 0; j < 2 * R; ++j) fetch(j, j, 0u, j % TWARPS, r0[j], TWO_IN ? r1[j] : dummy);
+
+  unsigned off_k = base + (unsigned)(kb * st) + 2u * (unsigned)t;
+  unsigned phase = 0;  // (o0 / NST) & 1
+#pragma unroll 1
+  for (int o0 = 0; o0 < nout; o0 += NST, phase ^= 1) {
+    const unsigned off_first = off_k;
+    unsigned cm = 0;  // bit u: output u of this sweep exceeds the threshold in one of the two columns
+#pragma unroll
+    for (int u = 0; u < NST; ++u) {
+      if (o0 + u < nout) {
+        const int mc = u + 2 * R;  // row index modulo 2*NST when phase == 0
+        fetch(o0 + mc, mc, phase, u % TWARPS, r0[mc % W], TWO_IN ? r1[mc % W] : dummy);
+        const float2 c0 = r0[(u + R) % W];
+        float2 accG0 = mul2(a.t.g[0], c0);  // G * in0
+        float2 accD0 = mul2(a.t.d[0], c0);  // D * in0
+        float2 accG1 = make_float2(0.f, 0.f);  // G * in1
+        if (TWO_IN) accG1 = mul2(a.t.g[0], r1[(u + R) % W]);
+#pragma unroll
+        for (int j = 1; j <= R; ++j) {
+          const float2 s0 = add2(r0[(u + R - j + W) % W], r0[(u + R + j) % W]);
+          if (OP != MFISH_CONV_LAST) accG0 = fma2(a.t.g[j], s0, accG0);
+          if (OP != MFISH_CONV_G) accD0 = fma2(a.t.d[j], s0, accD0);
+          if (TWO_IN) {
+            const float2 s1 = add2(r1[(u + R - j + W) % W], r1[(u + R + j) % W]);
+            accG1 = fma2(a.t.g[j], s1, accG1);
+          }
+        }
+        if (OP == MFISH_CONV_G) {
+          if (live) *reinterpret_cast<float2*>(a.out0 + off_k) = accG0;
+        } else if (OP == MFISH_CONV_GD) {
+          if (live) {
+            *reinterpret_cast<float2*>(a.out0 + off_k) = accG0;
+            *reinterpret_cast<float2*>(a.out1 + off_k) = accD0;
+          }
+        } else if (OP == MFISH_CONV_MID) {
+          if (live) {
+            *reinterpret_cast<float2*>(a.out0 + off_k) = accG0;
+            *reinterpret_cast<float2*>(a.out1 + off_k) = add2(accD0, accG1);
+          }
+        } else {
+          const float2 v = mul2(a.scale, add2(accD0, accG1));
+          if (live) *reinterpret_cast<float2*>(a.out0 + off_k) = v;
+          if (emit) cm |= (unsigned)(v.x > a.cand_thr || v.y > a.cand_thr) << u;
+        }
+        off_k += (unsigned)st;
+      }
+    }
+    if (emit && live && cm != 0)
+      emit_sweep_candidates(a.out0, off_first, (unsigned)st, cm, o0, nout, NST, a.cand_thr, a.cand, a.cand_count,
+                            a.cand_cap);
+  }
+}
+
 template <int R>
 struct YZArgs {
   const float* in;
@@ -577,9 +797,6 @@ struct YZArgs {
   Taps<R> t;
 };
 
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 
 // Stages cycle through full (TMA bytes landed) / empty (all warps have copied their window to
 // registers) mbarriers; there is no block-wide barrier in the plane loop.  Thread 0 doubles as the
@@ -823,6 +1040,14 @@ static int launch_y(const PassDesc& p) {
   return check_launch("conv_y");
 }
 
+static bool strided_tma_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("MFISH_STRIDED_TMA");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
 template <int R>
 static int launch_strided(const PassDesc& p) {
   SArgs<R> a;
@@ -854,17 +1079,61 @@ static int launch_strided(const PassDesc& p) {
   a.cand_cap = p.cand_cap;
   const int nout = a.out_end - a.out_begin;
   fill_taps<R>(a.t, p.g, p.d, p.radius);
+  static const char* const names[2][4] = {{"conv_z_g", "conv_z_gd", "conv_z_mid", "conv_z_last"},
+                                          {"conv_x_g", "conv_x_gd", "conv_x_mid", "conv_x_last"}};
+  const int min_chunk = std::max(64, 8 * R);
+  const int64_t want = (int64_t)num_sms() * 16 * 2;  // blocks
+  // TMA-staged walker: rows must be 16-byte addressable pieces
+  const bool two_in = p.op == MFISH_CONV_MID || p.op == MFISH_CONV_LAST;
+  const bool two_out = p.op == MFISH_CONV_GD || p.op == MFISH_CONV_MID;
+  const bool tma_ok = R <= TMA_MAX_R && strided_tma_enabled() && (a.inner % 4 == 0) && (a.stride % 4 == 0) &&
+                      (a.outer_stride % 4 == 0) && aligned16(a.in0) && (!two_in || aligned16(a.in1)) &&
+                      aligned16(a.out0) && (!two_out || aligned16(a.out1));
+  if (tma_ok) {
+    if constexpr (R <= TMA_MAX_R) {
+      int64_t bx = (a.inner + TSEG - 1) / TSEG;
+      int chunks = 1;
+      static const int64_t want_tma = [] {
+        const char* e = getenv("MFISH_TMA_WANT");
+        return e ? (int64_t)atoll(e) : (int64_t)0;
+      }();
+      const int64_t wt = want_tma > 0 ? want_tma : want / 2;
+      while (bx * nouter * chunks < wt && nout / (chunks * 2) >= min_chunk) chunks *= 2;
+      a.chunk_len = (nout + chunks - 1) / chunks;
+      MFISH_REQUIRE(bx < (1ll << 31) && nouter < 65536, "sepconv(strided): grid too large");
+      dim3 grid((unsigned)bx, (unsigned)nouter, (unsigned)chunks);
+      ProfScope prof(names[p.axis == MFISH_AXIS_Z ? 0 : 1][p.op], p.st);
+      auto go = [&](auto kern, size_t smem) {
+        static bool configured = false;  // per instantiation (the lambda is instantiated per kernel type)
+        if (!configured) {
+          cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+          if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          configured = true;
+        }
+        kern<<<grid, TTHREADS, smem, p.st>>>(a);
+      };
+      switch (p.op) {
+        case MFISH_CONV_G: go(conv_strided_tma_kernel<R, MFISH_CONV_G>, TmaTune<R, MFISH_CONV_G>::kSmem); break;
+        case MFISH_CONV_GD: go(conv_strided_tma_kernel<R, MFISH_CONV_GD>, TmaTune<R, MFISH_CONV_GD>::kSmem); break;
+        case MFISH_CONV_MID: go(conv_strided_tma_kernel<R, MFISH_CONV_MID>, TmaTune<R, MFISH_CONV_MID>::kSmem); break;
+        default:
+          if (a.cand != nullptr)
+            go(conv_strided_tma_kernel<R, MFISH_CONV_LAST, true>, TmaTune<R, MFISH_CONV_LAST>::kSmem);
+          else
+            go(conv_strided_tma_kernel<R, MFISH_CONV_LAST>, TmaTune<R, MFISH_CONV_LAST>::kSmem);
+          break;
+      }
+      count_launch(1);
+      return check_launch("conv_strided_tma");
+    }
+  }
   // split long lines into chunks until the grid holds >= ~4 waves of threads
   int64_t bx = (a.inner + STHREADS - 1) / STHREADS;
-  int64_t want = (int64_t)num_sms() * 16 * 2;  // blocks
   int chunks = 1;
-  const int min_chunk = std::max(64, 8 * R);
   while (bx * nouter * chunks < want && nout / (chunks * 2) >= min_chunk) chunks *= 2;
   a.chunk_len = (nout + chunks - 1) / chunks;
   MFISH_REQUIRE(bx < (1ll << 31) && nouter < 65536, "sepconv(strided): grid too large");
   dim3 grid((unsigned)bx, (unsigned)nouter, (unsigned)chunks);
-  static const char* const names[2][4] = {{"conv_z_g", "conv_z_gd", "conv_z_mid", "conv_z_last"},
-                                          {"conv_x_g", "conv_x_gd", "conv_x_mid", "conv_x_last"}};
   ProfScope prof(names[p.axis == MFISH_AXIS_Z ? 0 : 1][p.op], p.st);
   switch (p.op) {
     case MFISH_CONV_G: conv_strided_kernel<R, MFISH_CONV_G><<<grid, STHREADS, 0, p.st>>>(a); break;
