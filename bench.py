@@ -48,7 +48,7 @@ WORKLOADS = {
 # algorithmic bytes per voxel of each kernel (fp32 volumes, u8 masks)
 ALGO_BYTES = {
     "minmax": 4, "conv_y_gd": 12, "conv_z_mid": 16, "conv_x_last": 12, "nms_compact": 4,
-    "masked_quantile_3pass": 15, "masked_quantile_bracketed": 5, "edt_scan_y": 3, "edt_envelope_x": 8, "edt_envelope_z": 10,
+    "masked_quantile_3pass": 15, "masked_quantile_bracketed": 5, "masked_quantile_minmax": 5, "edt_scan_y": 3, "edt_envelope_x": 8, "edt_envelope_z": 10,
     "ingest_xyz": 8, "ingest_flat": 8,
 }
 

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MFISH_ABI_VERSION 2
+#define MFISH_ABI_VERSION 3
 
 #define MFISH_OK 0
 #define MFISH_ERR_INVALID (-1)
@@ -190,6 +190,14 @@ int mfish_masked_quantile_f32(const float* vol_dev, const uint8_t* mask_dev, int
  * on the device) and the caller must fall back to mfish_masked_quantile_f32; status 0 is exact.          */
 int mfish_masked_quantile_fast_f32(const float* vol_dev, const uint8_t* mask_dev, int64_t n, double q,
                                    void* ws_dev, float* out_dev, double* info_dev, void* stream);
+
+/* mfish_masked_quantile_fast_f32 whose one full pass also reduces {min, max} over ALL voxels into
+ * minmax_dev (float[2]): su.normalize_image's bounds (modules/scope_utils3.py:381-386) and the fibre
+ * baseline percentile (modules/muscle_fish.py:355-356) from a single read of the volume.  minmax_dev is
+ * valid whatever the bracket status says.                                                              */
+int mfish_masked_quantile_minmax_f32(const float* vol_dev, const uint8_t* mask_dev, int64_t n, double q,
+                                     void* ws_dev, float* out_dev, double* info_dev, float* minmax_dev,
+                                     void* stream);
 
 /* the same select in its three steps, for a z-slab decomposed volume: after every
  * mfish_qsel_hist the caller all-reduces (sum) the first 2*2048 uint32 of ws_dev

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmfish_sm100.so")
 
 # constants mirrored from include/mfish.h
-ABI_VERSION = 2
+ABI_VERSION = 3
 OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 U8, U16, I16, I32, I64, F32, F64 = range(7)
 LAYOUT_XYZ, LAYOUT_ZXY = 0, 1
@@ -52,6 +52,7 @@ SIGNATURES = {
     "mfish_overlap_pairs": (_i, [_p, _i64, _i64, _i64, _i64, _i64, _p, _p, _p, _i64, _p]),
     "mfish_masked_quantile_f32": (_i, [_p, _p, _i64, _d, _p, _p, _p, _p]),
     "mfish_masked_quantile_fast_f32": (_i, [_p, _p, _i64, _d, _p, _p, _p, _p]),
+    "mfish_masked_quantile_minmax_f32": (_i, [_p, _p, _i64, _d, _p, _p, _p, _p, _p]),
     "mfish_qsel_begin": (_i, [_p, _d, _p]),
     "mfish_qsel_hist": (_i, [_p, _p, _i64, _i, _p, _p]),
     "mfish_qsel_scan": (_i, [_i, _p, _p, _p, _p]),

@@ -19,30 +19,6 @@ __global__ void minmax_finalize_kernel(uint32_t* mm) {
   reinterpret_cast<float*>(mm)[1] = hi;
 }
 
-// Block reduction of (lo, hi) followed by one atomic pair per block.
-__device__ __forceinline__ void block_minmax_commit(float lo, float hi, uint32_t* mm) {
-  __shared__ float s_lo[32], s_hi[32];
-  lo = warp_min(lo);
-  hi = warp_max(hi);
-  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  int nw = (blockDim.x + 31) >> 5;
-  if (lane == 0) {
-    s_lo[w] = lo;
-    s_hi[w] = hi;
-  }
-  __syncthreads();
-  if (w == 0) {
-    lo = lane < nw ? s_lo[lane] : INFINITY;
-    hi = lane < nw ? s_hi[lane] : -INFINITY;
-    lo = warp_min(lo);
-    hi = warp_max(hi);
-    if (lane == 0) {
-      atomicMin(&mm[0], f32_to_key(lo));
-      atomicMax(&mm[1], f32_to_key(hi));
-    }
-  }
-}
-
 template <typename S>
 __device__ __forceinline__ float cvt_value(S v) {
   return static_cast<float>(v);

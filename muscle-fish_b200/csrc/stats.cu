@@ -24,9 +24,9 @@ struct QState {
   int mode;  // how qsel_scan_kernel<0> chooses the two ranks
 };
 // bracketed select (mfish_masked_quantile_f32): control block shared by its kernels
-constexpr int QSEG = 64;  // the candidate buffer is filled through QSEG independent cursors
+constexpr int QSEG = 64;  // (layout constant of the control block)
 struct QCtl {
-  unsigned int seg_count[QSEG * 32];  // one cursor per 128-byte line (entry i * 32)
+  unsigned int seg_count[QSEG * 32];  // [0]: overflow flag of the candidate buffer (rest: reserved)
   unsigned long long n_masked, n_below, n_cand;
   float v_lo, v_hi;    // candidates are the masked values in [v_lo, v_hi]
   int lo_open, hi_open;
@@ -304,77 +304,112 @@ __global__ void qsel_bracket_kernel(QWs* ws, const float* pair) {
 }
 
 // one full pass: count the masked voxels, those below the bracket, and collect those inside it.
-// The candidate buffer (pre-filled with a huge value) is written through QSEG cursors, each owning
-// cap / QSEG slots, so the appends do not serialise on one counter; unused slots sort to the top.
+// The candidate buffer (pre-filled with a huge value; unused slots sort to the top) is split into one
+// private region per warp of the grid, so an append is a register increment: no atomic, and no round
+// trip to wait for, on the path of the streaming loads.  A warp that outgrows its region raises the
+// overflow flag (seg_count[0]) and the caller falls back to the exact three-pass select.
+template <bool MM>
 __global__ void __launch_bounds__(256) qsel_range_kernel(const float* __restrict__ v, const uint8_t* __restrict__ m,
-                                                         int64_t n, QWs* ws, float* __restrict__ cand) {
+                                                         int64_t n, QWs* ws, float* __restrict__ cand, uint32_t* mm) {
   const float lo = ws->ctl.v_lo, hi = ws->ctl.v_hi;
-  const unsigned seg_cap = (unsigned)(ws->ctl.cap / QSEG);
-  const int seg = blockIdx.x % QSEG;
-  unsigned int* cursor = &ws->ctl.seg_count[seg * 32];
-  float* seg_buf = cand + (size_t)seg * seg_cap;
+  const unsigned nwarps = gridDim.x * (256 / 32);
+  const unsigned seg_cap = (unsigned)(ws->ctl.cap / nwarps);
+  float* seg_buf = cand + (size_t)(blockIdx.x * (256 / 32) + (threadIdx.x >> 5)) * seg_cap;
+  unsigned wcount = 0;  // candidates this warp has appended (same value in every lane)
   unsigned nm = 0, nb = 0;
+  float vmin = INFINITY, vmax = -INFINITY;  // MM: min / max over ALL voxels (su.normalize_image)
   const int lane = threadIdx.x & 31;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const bool vec = aligned16_dev(v) && ((reinterpret_cast<uintptr_t>(m) & 3u) == 0);
   const int64_t n4 = vec ? n / 4 : 0;
-  // uniform control flow: every lane classifies its 4 voxels, the warp reserves room for all of its
-  // candidates with ONE atomic (exclusive scan of the per-lane counts), then each lane stores its own
-  const int64_t n4_warp = (n4 + 31) / 32 * 32;  // keep whole warps in the loop for the shuffles
-  for (int64_t i = tid; i < n4_warp; i += stride) {
-    float val[4];
+  // uniform control flow: every lane classifies its 4 voxels, then one ballot per voxel slot ranks the
+  // warp's candidates behind the warp's running count
+  const unsigned lt_mask = (1u << lane) - 1u;
+  auto classify = [&](const uchar4 mk, const float4 a, bool have) {
+    float val[4] = {a.x, a.y, a.z, a.w};
     unsigned is_c = 0;
-    if (i < n4) {
-      const uchar4 mk = __ldg(reinterpret_cast<const uchar4*>(m) + i);
-      if (mk.x | mk.y | mk.z | mk.w) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(v) + i);
-        val[0] = a.x; val[1] = a.y; val[2] = a.z; val[3] = a.w;
-        const unsigned char mb[4] = {mk.x, mk.y, mk.z, mk.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (mb[k]) {
-            ++nm;
-            if (val[k] < lo) ++nb;
-            else if (val[k] <= hi) is_c |= 1u << k;
-          }
-        }
+    if (have) {
+      if (MM) {
+        vmin = fminf(fminf(vmin, a.x), fminf(a.y, fminf(a.z, a.w)));
+        vmax = fmaxf(fmaxf(vmax, a.x), fmaxf(a.y, fmaxf(a.z, a.w)));
       }
-    }
-    const unsigned any = __ballot_sync(0xffffffffu, is_c != 0);
-    if (any) {
-      const unsigned cnt = __popc(is_c);
-      unsigned incl = cnt;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-      }
-      const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
-      unsigned base = 0;
-      if (lane == 0) base = atomicAdd(cursor, total);
-      base = __shfl_sync(0xffffffffu, base, 0);
-      unsigned pos = base + incl - cnt;
+      const unsigned char mb[4] = {mk.x, mk.y, mk.z, mk.w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        if (is_c & (1u << k)) {
-          if (pos < seg_cap) seg_buf[pos] = val[k];
-          ++pos;
+        if (mb[k]) {
+          ++nm;
+          if (val[k] < lo) ++nb;
+          else if (val[k] <= hi) is_c |= 1u << k;
         }
       }
     }
-  }
-  for (int64_t i = n4 * 4 + tid; i < n; i += stride) {  // scalar tail (unaligned volumes)
-    if (m[i]) {
-      const float x = v[i];
-      ++nm;
-      if (x < lo) {
-        ++nb;
-      } else if (x <= hi) {
-        const unsigned pos = atomicAdd(cursor, 1u);
-        if (pos < seg_cap) seg_buf[pos] = x;
+    if (__any_sync(0xffffffffu, is_c != 0)) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const unsigned bk = __ballot_sync(0xffffffffu, (is_c >> k) & 1u);
+        if ((is_c >> k) & 1u) {
+          const unsigned pos = wcount + __popc(bk & lt_mask);
+          if (pos < seg_cap) seg_buf[pos] = val[k];
+        }
+        wcount += __popc(bk);
       }
     }
+  };
+  // QGROUPS independent groups of 4 voxels per iteration: every load is in flight before the first is
+  // used.  Without MM the voxels of an unmasked group are never fetched.
+  constexpr int QGROUPS = 2;
+  const int64_t n4_warp = (n4 + 31) / 32 * 32;  // keep whole warps in the loop for the shuffles
+  for (int64_t i = tid; i < n4_warp; i += QGROUPS * stride) {
+    uchar4 mk[QGROUPS];
+    float4 a[QGROUPS];
+    bool f[QGROUPS];
+#pragma unroll
+    for (int g = 0; g < QGROUPS; ++g) {
+      const int64_t j = i + g * stride;
+      mk[g] = make_uchar4(0, 0, 0, 0);
+      if (j < n4) mk[g] = __ldg(reinterpret_cast<const uchar4*>(m) + j);
+    }
+#pragma unroll
+    for (int g = 0; g < QGROUPS; ++g) {
+      const int64_t j = i + g * stride;
+      f[g] = j < n4 && (MM || (mk[g].x | mk[g].y | mk[g].z | mk[g].w));
+      a[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (f[g]) a[g] = __ldg(reinterpret_cast<const float4*>(v) + j);
+    }
+#pragma unroll
+    for (int g = 0; g < QGROUPS; ++g)
+      if (i + g * stride < n4_warp) classify(mk[g], a[g], f[g]);
+  }
+  // scalar tail (up to 3 voxels, or the whole of an unaligned volume), whole warps again
+  const int64_t tail0 = n4 * 4;
+  const int64_t ntail = n - tail0;
+  const int64_t ntail_warp = (ntail + 31) / 32 * 32;
+  for (int64_t r = tid; r < ntail_warp; r += stride) {
+    bool c = false;
+    float x = 0.f;
+    if (r < ntail) {
+      x = v[tail0 + r];
+      if (MM) {
+        vmin = fminf(vmin, x);
+        vmax = fmaxf(vmax, x);
+      }
+      if (m[tail0 + r]) {
+        ++nm;
+        if (x < lo) ++nb;
+        else if (x <= hi) c = true;
+      }
+    }
+    const unsigned bk = __ballot_sync(0xffffffffu, c);
+    if (c) {
+      const unsigned pos = wcount + __popc(bk & lt_mask);
+      if (pos < seg_cap) seg_buf[pos] = x;
+    }
+    wcount += __popc(bk);
+  }
+  if (lane == 0 && wcount != 0) {
+    atomicAdd(&ws->ctl.n_cand, (unsigned long long)min(wcount, seg_cap));
+    if (wcount > seg_cap) atomicOr(&ws->ctl.seg_count[0], 1u);
   }
   // block reduction of the two counters, one atomic pair per block
 #pragma unroll
@@ -397,6 +432,21 @@ __global__ void __launch_bounds__(256) qsel_range_kernel(const float* __restrict
     atomicAdd(&ws->ctl.n_masked, tm);
     atomicAdd(&ws->ctl.n_below, tb);
   }
+  if (MM) {
+    __syncthreads();
+    block_minmax_commit(vmin, vmax, mm);
+  }
+}
+
+__global__ void qsel_mm_init_kernel(uint32_t* mm) {
+  mm[0] = 0xFFFFFFFFu;
+  mm[1] = 0u;
+}
+__global__ void qsel_mm_finalize_kernel(uint32_t* mm) {
+  const float lo = key_to_f32(mm[0]);
+  const float hi = key_to_f32(mm[1]);
+  reinterpret_cast<float*>(mm)[0] = lo;
+  reinterpret_cast<float*>(mm)[1] = hi;
 }
 
 // exact ranks of the population quantile, relative to the candidate buffer; verifies the bracket
@@ -406,12 +456,7 @@ __global__ void qsel_ranks_kernel(QWs* ws, float* out, double* info) {
   QState& s = ws->st;
   const unsigned long long n = c.n_masked;
   info[1] = (double)n;
-  bool overflow = false;
-  c.n_cand = 0;
-  for (int i = 0; i < QSEG; ++i) {
-    c.n_cand += c.seg_count[i * 32];
-    overflow |= c.seg_count[i * 32] > (unsigned)(c.cap / QSEG);
-  }
+  const bool overflow = c.seg_count[0] != 0;  // a warp outgrew its region of the candidate buffer
   if (n == 0) {
     out[0] = out[1] = nanf("");
     info[0] = 0.0;
@@ -620,12 +665,13 @@ extern "C" int mfish_masked_quantile_f32(const float* vol_dev, const uint8_t* ma
 //   3. the exact ranks, shifted by the count below, are selected inside the (small) candidate buffer.
 // The bracket is verified on the device; info_dev[2] = 1 means it missed (or the buffer overflowed) and
 // the caller must run mfish_masked_quantile_f32.  info_dev = {gamma, n_masked, status}.
-extern "C" int mfish_masked_quantile_fast_f32(const float* vol_dev, const uint8_t* mask_dev, int64_t n, double q,
-                                              void* ws_dev, float* out_dev, double* info_dev, void* stream) {
+static int quantile_fast_impl(const float* vol_dev, const uint8_t* mask_dev, int64_t n, double q, void* ws_dev,
+                              float* out_dev, double* info_dev, float* minmax_dev, void* stream) {
   MFISH_REQUIRE(vol_dev && mask_dev && ws_dev && out_dev && info_dev, "masked_quantile: null pointer");
   MFISH_REQUIRE(n > 0 && q >= 0.0 && q <= 1.0, "masked_quantile: bad arguments");
   cudaStream_t st = as_stream(stream);
-  ProfScope prof("masked_quantile_bracketed", st);
+  ProfScope prof(minmax_dev ? "masked_quantile_minmax" : "masked_quantile_bracketed", st);
+  uint32_t* mm = reinterpret_cast<uint32_t*>(minmax_dev);
   QWs* ws = reinterpret_cast<QWs*>(ws_dev);
   const int64_t cap = (std::max<int64_t>(1 << 20, n / 64) + QSEG - 1) / QSEG * QSEG;
   float* cand = nullptr;
@@ -648,7 +694,14 @@ extern "C" int mfish_masked_quantile_fast_f32(const float* vol_dev, const uint8_
   // 2. the one full pass
   MFISH_CUDA(cudaMemsetAsync(cand, 0x7f, (size_t)cap * sizeof(float), st));  // 3.39e38: sorts above any voxel
   MFISH_CUDA(cudaMemcpyAsync(&ws->ctl.cap, &cap, sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
-  qsel_range_kernel<<<blocks, 256, 0, st>>>(vol_dev, mask_dev, n, ws, cand);
+  if (mm) {
+    qsel_mm_init_kernel<<<1, 1, 0, st>>>(mm);
+    qsel_range_kernel<true><<<blocks, 256, 0, st>>>(vol_dev, mask_dev, n, ws, cand, mm);
+    qsel_mm_finalize_kernel<<<1, 1, 0, st>>>(mm);
+    count_launch(2);
+  } else {
+    qsel_range_kernel<false><<<blocks, 256, 0, st>>>(vol_dev, mask_dev, n, ws, cand, nullptr);
+  }
   // 3. exact ranks inside the candidates
   qsel_init_kernel<<<1, 256, 0, st>>>(ws, q, QMODE_RANKS);
   qsel_ranks_kernel<<<1, 32, 0, st>>>(ws, out_dev, info_dev);
@@ -664,6 +717,21 @@ extern "C" int mfish_masked_quantile_fast_f32(const float* vol_dev, const uint8_
   cudaFreeAsync(cand, st);
   cudaFreeAsync(pair, st);
   return rc;
+}
+
+extern "C" int mfish_masked_quantile_fast_f32(const float* vol_dev, const uint8_t* mask_dev, int64_t n, double q,
+                                              void* ws_dev, float* out_dev, double* info_dev, void* stream) {
+  return quantile_fast_impl(vol_dev, mask_dev, n, q, ws_dev, out_dev, info_dev, nullptr, stream);
+}
+
+// Same selection; the one full pass over the voxels also reduces the global {min, max} of ALL voxels
+// (su.normalize_image's bounds) into minmax_dev, saving the separate pass of mfish_minmax_f32.  The
+// pair is valid whatever the bracket status says.
+extern "C" int mfish_masked_quantile_minmax_f32(const float* vol_dev, const uint8_t* mask_dev, int64_t n, double q,
+                                                void* ws_dev, float* out_dev, double* info_dev, float* minmax_dev,
+                                                void* stream) {
+  MFISH_REQUIRE(minmax_dev != nullptr, "masked_quantile_minmax: null minmax");
+  return quantile_fast_impl(vol_dev, mask_dev, n, q, ws_dev, out_dev, info_dev, minmax_dev, stream);
 }
 
 extern "C" int mfish_blur_at_points(const float* vol_dev, int64_t nz, int64_t nx, int64_t ny,

@@ -543,16 +543,22 @@ def blur_at_points(vol: Volume, spots_xyz, sigma_xyz=(3, 3, 0.3), mode="nearest"
     return out.cpu().numpy()
 
 
-def masked_percentile_async(vol: Volume, mask: torch.Tensor, q_percent: float):
+def masked_percentile_async(vol: Volume, mask: torch.Tensor, q_percent: float, minmax_out: torch.Tensor = None):
     """Launch the masked radix select; the returned ``finish()`` reads the two order statistics and
-    completes np.percentile(normalize(img)[mask], q) in float64 on the host."""
+    completes np.percentile(normalize(img)[mask], q) in float64 on the host.  With ``minmax_out``
+    (float32[2], = ``vol.minmax``) the select's one full pass also reduces the global min/max."""
     dev = vol.data.device
     ws = WS.get("qws", (L.QUANTILE_WS_BYTES,), torch.uint8, dev)
     out = torch.empty(2, dtype=torch.float32, device=dev)
     info = torch.empty(3, dtype=torch.float64, device=dev)
     q = float(q_percent) / 100.0
-    L.check(L.lib().mfish_masked_quantile_fast_f32(vol.data.data_ptr(), mask.data_ptr(), vol.data.numel(), q,
-                                                   ws.data_ptr(), out.data_ptr(), info.data_ptr(), _stream()))
+    if minmax_out is not None:
+        L.check(L.lib().mfish_masked_quantile_minmax_f32(vol.data.data_ptr(), mask.data_ptr(), vol.data.numel(), q,
+                                                         ws.data_ptr(), out.data_ptr(), info.data_ptr(),
+                                                         minmax_out.data_ptr(), _stream()))
+    else:
+        L.check(L.lib().mfish_masked_quantile_fast_f32(vol.data.data_ptr(), mask.data_ptr(), vol.data.numel(), q,
+                                                       ws.data_ptr(), out.data_ptr(), info.data_ptr(), _stream()))
 
     def finish():
         gamma, n, status = info.tolist()
@@ -571,6 +577,14 @@ def masked_percentile_async(vol: Volume, mask: torch.Tensor, q_percent: float):
         return T.lerp(float(a), float(b), float(gamma))
 
     return finish
+
+
+def masked_percentile_minmax_async(img_zxy: torch.Tensor, mask: torch.Tensor, q_percent: float):
+    """``(Volume(img, minmax), finish)``: su.normalize_image's bounds and the masked percentile from a
+    single read of the voxels (the percentile is selected on raw values and mapped afterwards)."""
+    mm = torch.empty(2, dtype=torch.float32, device=img_zxy.device)
+    vol = Volume(img_zxy, mm)
+    return vol, masked_percentile_async(vol, mask, q_percent, minmax_out=mm)
 
 
 def masked_percentile(vol: Volume, mask: torch.Tensor, q_percent: float) -> float:
@@ -703,11 +717,10 @@ def analyze_stack(img_zxy: torch.Tensor, fiber_zxy: torch.Tensor, notnuc_zxy: to
     dims = (1, nx, ny, nz)
     # everything that does not depend on the spot list is queued first, so the host round trips of
     # the list handling (count, D2H, decode) overlap the remaining device work
-    mm = t.run("minmax", minmax, img_zxy)
-    vol = Volume(img_zxy, mm)
+    # normalize_image's bounds come out of the baseline percentile's pass over the voxels
+    vol, baseline_f = t.run("quantile_minmax", masked_percentile_minmax_async, img_zxy, fiber_zxy, 25)
     log = WS.get("log_out", img_zxy.shape, torch.float32, img_zxy.device)
     _, peaks = t.run("log3d_nms", log_peaks_async, vol, sigma, t_spot, log)
-    baseline_f = t.run("quantile", masked_percentile_async, vol, fiber_zxy, 25)
     # the distance transform runs on a side stream, after the streaming kernels above, so that the
     # small kernels and host round trips of the spot-list handling proceed while it runs
     main = torch.cuda.current_stream()

@@ -100,6 +100,39 @@ def test_sepconv_one_axis(sigma, axis, mode):
     assert _rel_err(g2, ref_g) < REL_TOL
 
 
+@pytest.mark.parametrize("sigma", [0.5, 1.0, 1.5, 2.0])
+@pytest.mark.parametrize("shape", [(48, 72, 37), (40, 256, 20), (33, 520, 9), (300, 8, 19)])
+@pytest.mark.parametrize("mode", ["reflect", "nearest"])
+def test_sepconv_tma_staged_walker(sigma, shape, mode):
+    """rows that are a multiple of 4 floats take the TMA-staged z/x walker (radius <= 8): full and
+    partial 256-float segments, lines shorter than one unrolled sweep, both boundary rules"""
+    from muscle_fish_b200 import _lib as L
+    rng = np.random.default_rng(int(sigma * 10) + shape[0])
+    a = rng.random(shape).astype(np.float32)
+    for axis in (0, 2):
+        g, d = _sepconv(a, axis, sigma, L.CONV_GD, mode)
+        ref_g = ndi.gaussian_filter1d(a.astype(np.float64), sigma, axis=axis, order=0, mode=mode)
+        ref_d = ndi.gaussian_filter1d(a.astype(np.float64), sigma, axis=axis, order=2, mode=mode)
+        assert _rel_err(g, ref_g) < REL_TOL, (axis,)
+        assert _rel_err(d, ref_d) < REL_TOL, (axis,)
+        g2, _ = _sepconv(a, axis, sigma, L.CONV_G, mode)
+        assert _rel_err(g2, ref_g) < REL_TOL, (axis,)
+
+
+@pytest.mark.parametrize("shape", [(48, 72, 37), (64, 256, 21), (20, 8, 150)])
+@pytest.mark.parametrize("sigma", [1.0, 2.0])
+def test_log_volume_tma_staged_shapes(shape, sigma):
+    """LoG through the TMA-staged z and x walkers on small aligned volumes (partial segments, lines
+    shorter than the stage ring)"""
+    from muscle_fish_b200 import device as D
+    rng = np.random.default_rng(11)
+    a = rng.random(shape).astype(np.float32)
+    vol = D.ingest(a)
+    got = _zxy_to_xyz(D.log_volume(vol, sigma))
+    ref = oracle.log_cube(oracle.normalize_image(a), [sigma])[..., 0]
+    assert _rel_err(got, ref) < REL_TOL
+
+
 @pytest.mark.parametrize("shape", [(3, 5, 2), (9, 4, 5), (130, 516, 20), (17, 1030, 3)])
 def test_sepconv_short_and_ragged_lines(shape):
     """lines shorter than the kernel radius (reflect wraps with period 2N) and ragged rows"""

@@ -248,6 +248,26 @@ def test_masked_percentile_exact(q):
         D.masked_percentile(vol, D.ingest(np.zeros(a.shape, np.uint8), as_mask=True), q)
 
 
+@pytest.mark.parametrize("shape", [(200, 192, 40), (61, 47, 13), (64, 64, 9)])
+@pytest.mark.parametrize("q", [25, 50, 99.9])
+def test_masked_percentile_fused_minmax(shape, q):
+    """one pass over the voxels: normalize_image's bounds (bit exact, over ALL voxels, masked or not)
+    and the masked percentile"""
+    import torch
+    from muscle_fish_b200 import device as D
+    rng = np.random.default_rng(19)
+    a = (rng.standard_normal(shape) * 30 + 500).astype(np.float32)
+    mask = rng.random(shape) < 0.3
+    a[~mask] *= 3.0  # the extremes lie outside the mask
+    vol = D.ingest(a)
+    m = D.ingest(mask, as_mask=True)
+    vol2, finish = D.masked_percentile_minmax_async(vol.data, m, q)
+    got = finish()
+    assert torch.equal(vol2.minmax, vol.minmax)
+    assert vol2.minmax_host() == (float(a.min()), float(a.max()))
+    assert got == np.percentile(oracle.normalize_image(a)[mask], q)
+
+
 @pytest.mark.parametrize("kind", ["float", "uint8_ties", "two_values", "sparse_mask"])
 @pytest.mark.parametrize("q", [25, 90, 0.01, 99.99])
 def test_masked_percentile_bracketed_path_exact(kind, q):
