@@ -3,16 +3,23 @@
 // skimage.filters.gaussian drive them (modules/muscle_fish.py:333,357,661).
 //
 // Device layout [z][x][y], y contiguous.
-//  * conv_y_kernel      : contiguous axis.  A 512-voxel row segment + halo is staged in shared
-//                         memory by the TMA unit (cp.async.bulk + mbarrier, double-buffered over 4
-//                         rows per block; row-end segments fall back to mapped loads); each thread
-//                         produces 4 consecutive outputs from a register window filled with 128-bit
-//                         shared loads.                      R4 + W4 (G) or R4 + W8 (G,D) B/voxel.
-//  * conv_strided_kernel: z or x axis.  One thread per contiguous-axis position walks the strided
-//                         axis with a (2R+1+D)-deep register ring (D planes of load lookahead), so
-//                         every voxel is read once and written once.  8 / 12 / 16 / 12 B/voxel for
-//                         ops G / GD / MID / LAST.
-// Taps live in the kernel parameter block (constant bank) so every FFMA has two register sources.
+//  * conv_y_kernel          : contiguous axis.  A 512-voxel row segment + halo is staged in shared
+//                             memory by the TMA unit (cp.async.bulk + mbarrier, double-buffered over
+//                             4 rows per block; row-end segments copy their in-range part and patch
+//                             the <= R boundary-mapped voxels); each thread produces 4 consecutive
+//                             outputs from a register window of aligned and one-shifted float2 pairs,
+//                             every tap a packed FFMA2 / FADD2.   R4 + W4 (G) or R4 + W8 (G,D) B/voxel.
+//  * conv_strided_tma_kernel: z or x axis, R <= 8, rows a multiple of 4 floats.  A block owns a
+//                             256-float row segment and walks the axis; rows arrive through a
+//                             shared-memory stage ring filled by TMA bulk copies (full / empty
+//                             mbarriers), each thread keeps the 2R+1 window as float2 column pairs.
+//                             Every voxel is read once and written once: 8 / 12 / 16 / 12 B/voxel
+//                             for ops G / GD / MID / LAST.  LAST can also flag outputs above a
+//                             threshold (fused NMS candidates).
+//  * conv_strided_kernel    : the same passes with a (2R+1+D)-deep register ring per thread (D planes
+//                             of load look-ahead): any radius <= 16, any row length.
+//  * *_generic kernels      : gather fallbacks (radius > 16, lines shorter than the radius).
+// Taps live in the kernel parameter block (constant bank / uniform registers).
 #include <stdlib.h>
 
 #include <algorithm>
