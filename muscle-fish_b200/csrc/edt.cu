@@ -164,7 +164,7 @@ __device__ __forceinline__ double u2d(uint32_t v) {
 // MUFU.SQRT: relative error <= 2^-23, one instruction instead of the ~8 of the correctly rounded sqrtf
 __device__ __forceinline__ float sqrt_approx(float x) {
   float r;
-  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
 // non-negative double < 2^31 holding an integer -> int32, without F2I
@@ -174,26 +174,31 @@ __device__ __forceinline__ int32_t d2i_exact(double v) { return __double2loint(v
 // u16 rows hold |dy| (squared here: at most 65534^2 < 0xFFFFFFFF).
 template <typename TIn>
 struct EdtRaw;
+// fetch() only issues the load (the software-pipelined batches must not touch the value before it is
+// consumed, or the thread waits for it on the spot); decode() turns the fetched bits into the payload.
 template <>
 struct EdtRaw<uint16_t> {
   static constexpr uint32_t kNone = 0xFFFFFFFFu;
-  static __device__ __forceinline__ uint32_t load(const uint16_t* p) {
-    const uint32_t d = __ldg(p);
-    return d == EDT_INF_U16 ? kNone : d * d;
-  }
+  static constexpr uint32_t kFetchNone = EDT_INF_U16;
+  static __device__ __forceinline__ uint32_t fetch(const uint16_t* p) { return __ldg(p); }
+  static __device__ __forceinline__ uint32_t decode(uint32_t d) { return d == EDT_INF_U16 ? kNone : d * d; }
+  static __device__ __forceinline__ uint32_t load(const uint16_t* p) { return decode(fetch(p)); }
 };
 template <>
 struct EdtRaw<int32_t> {
   static constexpr uint32_t kNone = (uint32_t)EDT_INF_I32;
-  static __device__ __forceinline__ uint32_t load(const int32_t* p) { return (uint32_t)__ldg(p); }
+  static constexpr uint32_t kFetchNone = kNone;
+  static __device__ __forceinline__ uint32_t fetch(const int32_t* p) { return (uint32_t)__ldg(p); }
+  static __device__ __forceinline__ uint32_t decode(uint32_t v) { return v; }
+  static __device__ __forceinline__ uint32_t load(const int32_t* p) { return fetch(p); }
 };
 template <>
 struct EdtRaw<float> {
   static constexpr uint32_t kNone = 0x7F800000u;  // +inf
-  static __device__ __forceinline__ uint32_t load(const float* p) {
-    const float f = __ldg(p);
-    return f < INFINITY ? __float_as_uint(f) : kNone;
-  }
+  static constexpr uint32_t kFetchNone = kNone;
+  static __device__ __forceinline__ uint32_t fetch(const float* p) { return __float_as_uint(__ldg(p)); }
+  static __device__ __forceinline__ uint32_t decode(uint32_t v) { return __uint_as_float(v) < INFINITY ? v : kNone; }
+  static __device__ __forceinline__ uint32_t load(const float* p) { return decode(fetch(p)); }
 };
 template <typename TIn>
 __device__ __forceinline__ double edt_value(uint32_t v) {
@@ -291,7 +296,7 @@ __global__ void __launch_bounds__(ENV_THREADS) edt_envelope_kernel(const EnvArgs
   {
     uint32_t nb[ENV_BATCH];
 #pragma unroll
-    for (int u = 0; u < ENV_BATCH; ++u) nb[u] = u < L ? R::load(in + (IdxT)u * st) : R::kNone;
+    for (int u = 0; u < ENV_BATCH; ++u) nb[u] = u < L ? R::fetch(in + (IdxT)u * st) : R::kFetchNone;
     LinkT* __restrict__ plink = link;
     const TIn* __restrict__ pnext = in + (IdxT)ENV_BATCH * st;
     double qd = 0.0;
@@ -331,10 +336,10 @@ __global__ void __launch_bounds__(ENV_THREADS) edt_envelope_kernel(const EnvArgs
 #pragma unroll
       for (int u = 0; u < ENV_BATCH; ++u) s_raw[u][threadIdx.x] = nb[u];
 #pragma unroll
-      for (int u = 0; u < ENV_BATCH; ++u) nb[u] = R::load(pnext + (IdxT)u * st);
+      for (int u = 0; u < ENV_BATCH; ++u) nb[u] = R::fetch(pnext + (IdxT)u * st);
       pnext += (IdxT)ENV_BATCH * st;
 #pragma unroll 4
-      for (int u = 0; u < ENV_BATCH; ++u) step(s_raw[u][threadIdx.x], q0 + u);
+      for (int u = 0; u < ENV_BATCH; ++u) step(R::decode(s_raw[u][threadIdx.x]), q0 + u);
     }
 #pragma unroll 1
     for (; q0 < L; q0 += ENV_BATCH) {  // the last one or two batches, bounds-checked
@@ -342,11 +347,11 @@ __global__ void __launch_bounds__(ENV_THREADS) edt_envelope_kernel(const EnvArgs
       for (int u = 0; u < ENV_BATCH; ++u) s_raw[u][threadIdx.x] = nb[u];
 #pragma unroll
       for (int u = 0; u < ENV_BATCH; ++u)
-        nb[u] = (q0 + ENV_BATCH + u < L) ? R::load(pnext + (IdxT)u * st) : R::kNone;
+        nb[u] = (q0 + ENV_BATCH + u < L) ? R::fetch(pnext + (IdxT)u * st) : R::kFetchNone;
       pnext += (IdxT)ENV_BATCH * st;
       const int qe = min(L, q0 + ENV_BATCH);
 #pragma unroll 1
-      for (int q = q0; q < qe; ++q) step(s_raw[q - q0][threadIdx.x], q);
+      for (int q = q0; q < qe; ++q) step(R::decode(s_raw[q - q0][threadIdx.x]), q);
     }
   }
 
