@@ -120,6 +120,25 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) edt_scan_y_kernel(const ScanA
       const int y0 = w * 32;
       const int cl = carryL[w], cr = carryR[w];
       const bool full = vout && y0 + 32 <= ny;
+      if (b == 0u && full) {
+        // no site inside the word (the common case: nuclei fill a few percent of the volume): the
+        // distance is a ramp from the carried neighbours, no bit scans
+        int dl = min(y0 - cl, (int)EDT_INF_U16);      // y - l at j = 0, grows by 1 per voxel
+        int dr = min(cr - y0, 2 * (int)EDT_INF_U16);  // r - y at j = 0, shrinks by 1 per voxel
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint32_t packed[4];
+#pragma unroll
+          for (int jj = 0; jj < 8; jj += 2) {
+            const int j = 8 * k + jj;
+            const int d0 = min(min(dl + j, dr - j), (int)EDT_INF_U16);
+            const int d1 = min(min(dl + j + 1, dr - j - 1), (int)EDT_INF_U16);
+            packed[jj >> 1] = (uint32_t)d0 | ((uint32_t)d1 << 16);
+          }
+          reinterpret_cast<uint4*>(dst + y0)[k] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        }
+        continue;
+      }
 #pragma unroll 1
       for (int k = 0; k < 4; ++k) {  // 8 voxels -> one 128-bit store (keeps the register count low)
         uint32_t packed[4];
