@@ -598,7 +598,7 @@ struct TmaTune {
   // a multiple of the window length, so that one unrolled sweep of kStages steps sees every ring
   // slot AND every stage at a compile-time index
   static constexpr int kStages = kW >= 12 ? kW : kW * ((12 + kW - 1) / kW);
-  static constexpr int kMinBlocks = 5;
+  static constexpr int kMinBlocks = (OP == MFISH_CONV_LAST) ? 4 : 5;
   static constexpr size_t kSmem = (size_t)kStages * (kTwoIn ? 2 : 1) * TSEG * sizeof(float) + 2 * kStages * 8;
 };
 
