@@ -407,3 +407,32 @@ def slab_spot_distances(dist_xslab: torch.Tensor, spots_xyz: np.ndarray, lay: Sl
             out[own] = ops.gather_f32(dist_xslab, loc).to(torch.float64)
     dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
     return out.cpu().numpy()
+
+
+def slab_analyze(img_slab: torch.Tensor, mask_slab: torch.Tensor, notnuc_slab: torch.Tensor, lay: SlabLayout,
+                 sigma=2.0, t_spot=0.025, sampling_xyz=(1.0, 1.0, 1.0), snr=None, ops=None, group=None,
+                 edt_group=None, full_table=True):
+    """The whole path on a z-slab decomposed mosaic: ``slab_find_spots_snrfilter`` + ``slab_edt`` +
+    ``slab_spot_distances``.  The distance transform does not depend on the spots and its chain has no
+    host round trip: given ``edt_group`` (a second communicator over the same ranks, ``dist.new_group()``)
+    on CUDA tensors it is queued first on a side stream, so its all-to-all and kernels run beside the
+    spot chain's halo exchange, small collectives and host round trips.  Returns the spot dict plus
+    ``spot_dist`` (float64 per kept spot) and ``dist_xslab`` (the x-slab partitioned distance map)."""
+    if edt_group is not None and img_slab.is_cuda:
+        from . import device as D
+        cur = torch.cuda.current_stream()
+        side = D._side_stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            dmap = slab_edt(notnuc_slab, lay, sampling_xyz, ops=ops, group=edt_group)
+        res = slab_find_spots_snrfilter(img_slab, mask_slab, lay, sigma=sigma, t_spot=t_spot, snr=snr, ops=ops,
+                                        group=group, full_table=full_table)
+        cur.wait_stream(side)
+        dmap.record_stream(cur)
+    else:
+        res = slab_find_spots_snrfilter(img_slab, mask_slab, lay, sigma=sigma, t_spot=t_spot, snr=snr, ops=ops,
+                                        group=group, full_table=full_table)
+        dmap = slab_edt(notnuc_slab, lay, sampling_xyz, ops=ops, group=group)
+    res["spot_dist"] = slab_spot_distances(dmap, res["spots"], lay, ops=ops, group=group)
+    res["dist_xslab"] = dmap
+    return res

@@ -42,6 +42,11 @@ def _job(rank, world, port, outdir):
         dmap = P.slab_edt(notnuc, lay, ANISO)
         sd = P.slab_spot_distances(dmap, res["spots"], lay)
         dz = P.slab_edt(notnuc, lay, ANISO, back_to_z=True).cpu().numpy()
+        # combined driver, EDT chain on a side stream with its own communicator: same results
+        both = P.slab_analyze(img, fib, notnuc, lay, sigma=2.0, t_spot=0.025, sampling_xyz=ANISO,
+                              edt_group=dist.new_group())
+        torch.cuda.synchronize()
+        assert np.array_equal(both["spots"], res["spots"]) and np.array_equal(both["spot_dist"], sd)
         np.save(os.path.join(outdir, f"r{rank}.npy"),
                 np.array([res["spots"], res["intensity"], res["baseline"], sd, dz, (lay.z0, lay.z1)], dtype=object),
                 allow_pickle=True)

@@ -195,6 +195,11 @@ def _spots_job(rank, world, seed):
     dmap = P.slab_edt(notnuc[lay.z0:lay.z1].clone(), lay, ANISO, ops=ops)
     sd = P.slab_spot_distances(dmap, res["spots"], lay, ops=ops)
     dz = P.slab_edt(notnuc[lay.z0:lay.z1].clone(), lay, ANISO, ops=ops, back_to_z=True)
+    # the combined driver (CPU tensors: no side stream) returns the same thing
+    both = P.slab_analyze(img[lay.z0:lay.z1].clone(), fib[lay.z0:lay.z1].clone(), notnuc[lay.z0:lay.z1].clone(), lay,
+                          sigma=2.0, t_spot=0.025, sampling_xyz=ANISO, ops=ops, edt_group=dist.new_group())
+    assert np.array_equal(both["spots"], res["spots"]) and np.array_equal(both["spot_dist"], sd)
+    assert torch.equal(both["dist_xslab"], dmap)
     return [res["spots"], res["spots_masked"], res["intensity"], res["baseline"], res["snr"], sd, dz.numpy(),
             (lay.z0, lay.z1)]
 

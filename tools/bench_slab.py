@@ -22,7 +22,6 @@ rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_S
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 edt_group = dist.new_group()  # second communicator: the EDT's all-to-all runs beside the spot chain's collectives
-side = torch.cuda.Stream()
 X, Y, Z = args.shape
 lay = P.SlabLayout(Z, X, Y)
 st = synth.make_stack_device((X, Y, Z), args.spots, args.nuclei, 4, z_range=(lay.z0, lay.z1))
@@ -47,16 +46,10 @@ def step_overlap():
     side stream / second communicator first, then run the spot chain; join before the gather"""
     t = {}
     torch.cuda.synchronize(); t0 = time.perf_counter()
-    cur = torch.cuda.current_stream()
-    side.wait_stream(cur)
-    with torch.cuda.stream(side):
-        dmap = P.slab_edt(notnuc, lay, SAMPLING, group=edt_group)
-    res = P.slab_find_spots_snrfilter(img, fib, lay, sigma=2.0, t_spot=0.025, full_table=False)
-    cur.wait_stream(side)
-    torch.cuda.synchronize(); t["spots+edt"] = time.perf_counter() - t0; t0 = time.perf_counter()
-    sd = P.slab_spot_distances(dmap, res["spots"], lay)
-    torch.cuda.synchronize(); t["gather"] = time.perf_counter() - t0
-    return res, sd, t
+    res = P.slab_analyze(img, fib, notnuc, lay, sigma=2.0, t_spot=0.025, sampling_xyz=SAMPLING, edt_group=edt_group,
+                         full_table=False)
+    torch.cuda.synchronize(); t["all"] = time.perf_counter() - t0
+    return res, res["spot_dist"], t
 
 for _ in range(args.warmup):
     step()
