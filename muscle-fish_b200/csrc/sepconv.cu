@@ -1105,7 +1105,7 @@ static int launch_strided(const PassDesc& p) {
         return e ? (int64_t)atoll(e) : (int64_t)0;
       }();
       const int64_t wt = want_tma > 0 ? want_tma : want / 2;
-      while (bx * nouter * chunks < wt && nout / (chunks * 2) >= min_chunk) chunks *= 2;
+      while (chunks < 16384 && bx * nouter * chunks < wt && nout / (chunks * 2) >= min_chunk) chunks *= 2;
       a.chunk_len = (nout + chunks - 1) / chunks;
       MFISH_REQUIRE(bx < (1ll << 31) && nouter < 65536, "sepconv(strided): grid too large");
       dim3 grid((unsigned)bx, (unsigned)nouter, (unsigned)chunks);
@@ -1137,7 +1137,7 @@ static int launch_strided(const PassDesc& p) {
   // split long lines into chunks until the grid holds >= ~4 waves of threads
   int64_t bx = (a.inner + STHREADS - 1) / STHREADS;
   int chunks = 1;
-  while (bx * nouter * chunks < want && nout / (chunks * 2) >= min_chunk) chunks *= 2;
+  while (chunks < 16384 && bx * nouter * chunks < want && nout / (chunks * 2) >= min_chunk) chunks *= 2;
   a.chunk_len = (nout + chunks - 1) / chunks;
   MFISH_REQUIRE(bx < (1ll << 31) && nouter < 65536, "sepconv(strided): grid too large");
   dim3 grid((unsigned)bx, (unsigned)nouter, (unsigned)chunks);
