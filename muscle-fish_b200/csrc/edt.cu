@@ -299,7 +299,9 @@ __global__ void __launch_bounds__(ENV_THREADS) edt_envelope_kernel(const EnvArgs
   if (i >= a.inner) return;
   const int64_t base = (int64_t)blockIdx.y * a.outer_stride + i;
   const TIn* __restrict__ in = a.in + base;
-  LinkT* __restrict__ link = a.link + base;
+  // hull links and payloads are addressed as parameter base + one IdxT element index (a single
+  // IMAD.WIDE per access when the volume has < 2^32 elements), not through 64-bit pointer arithmetic
+  const IdxT bi = (IdxT)base;
   const IdxT st = (IdxT)a.stride;
   const int L = a.L;
   const double sG = a.sG;
@@ -316,7 +318,7 @@ __global__ void __launch_bounds__(ENV_THREADS) edt_envelope_kernel(const EnvArgs
     uint32_t nb[ENV_BATCH];
 #pragma unroll
     for (int u = 0; u < ENV_BATCH; ++u) nb[u] = u < L ? R::fetch(in + (IdxT)u * st) : R::kFetchNone;
-    LinkT* __restrict__ plink = link;
+    IdxT lidx = bi;
     const TIn* __restrict__ pnext = in + (IdxT)ENV_BATCH * st;
     double qd = 0.0;
     // one hull step for site q with payload rq (skipped for "no site")
@@ -330,23 +332,23 @@ __global__ void __launch_bounds__(ENV_THREADS) edt_envelope_kernel(const EnvArgs
           do {
             t0 = t1;
             G0 = G0 - A;  // = G1
-            t1 = (int)link[(IdxT)t0 * st];
+            t1 = (int)a.link[bi + (IdxT)t0 * st];
             dG = Gq - G0;
             dq = H::idiff(q, t0);
             if (t1 == EDT_NO_SITE) break;
-            const GT G1 = H::template make<TIn>(R::load(in + (IdxT)t1 * st), t1, u2d((uint32_t)t1), sG);
+            const GT G1 = H::template make<TIn>(R::load(a.in + (bi + (IdxT)t1 * st)), t1, u2d((uint32_t)t1), sG);
             A = G0 - G1;
             Bb = H::idiff(t0, t1);
           } while (H::hidden(A, Bb, dG, dq));
         }
-        *plink = (LinkT)t0;
+        a.link[lidx] = (LinkT)t0;
         t1 = t0;
         t0 = q;
         G0 = Gq;
         A = dG;
         Bb = dq;
       }
-      plink += st;
+      lidx += st;
       qd += 1.0;
     };
     int q0 = 0;
@@ -396,10 +398,10 @@ __global__ void __launch_bounds__(ENV_THREADS) edt_envelope_kernel(const EnvArgs
   // entered and consumed only at the next hull move
   int nxt = EDT_NO_SITE, nxt_link = EDT_NO_SITE;
   uint32_t nxt_raw = 0;
-  if (prev != EDT_NO_SITE) nxt = (int)link[(IdxT)prev * st];
+  if (prev != EDT_NO_SITE) nxt = (int)a.link[bi + (IdxT)prev * st];
   if (nxt != EDT_NO_SITE) {
-    nxt_raw = R::load(in + (IdxT)nxt * st);
-    nxt_link = (int)link[(IdxT)nxt * st];
+    nxt_raw = R::load(a.in + (bi + (IdxT)nxt * st));
+    nxt_link = (int)a.link[bi + (IdxT)nxt * st];
   }
   const double w2s = a.w2 * a.out_scale;  // F64 + EDT_OUT_DIST: the output scale is folded in
   const double w2 = (OUT == EDT_OUT_DIST) ? w2s : a.w2;
@@ -456,8 +458,8 @@ __global__ void __launch_bounds__(ENV_THREADS) edt_envelope_kernel(const EnvArgs
           Bb = H::idiff(cur, prev);
           nxt = nxt_link;
           if (nxt != EDT_NO_SITE) {
-            nxt_raw = R::load(in + (IdxT)nxt * st);
-            nxt_link = (int)link[(IdxT)nxt * st];
+            nxt_raw = R::load(a.in + (bi + (IdxT)nxt * st));
+            nxt_link = (int)a.link[bi + (IdxT)nxt * st];
           }
         }
         enter(p, A, Bb);

@@ -336,12 +336,13 @@ __global__ void __launch_bounds__(256) qsel_range_kernel(const float* __restrict
       }
       const unsigned char mb[4] = {mk.x, mk.y, mk.z, mk.w};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (mb[k]) {
-          ++nm;
-          if (val[k] < lo) ++nb;
-          else if (val[k] <= hi) is_c |= 1u << k;
-        }
+      for (int k = 0; k < 4; ++k) {  // branch-free: predicates and selects only
+        const unsigned in_mask = mb[k] != 0;
+        const unsigned below = in_mask & (unsigned)(val[k] < lo);
+        const unsigned inside = in_mask & (unsigned)(val[k] >= lo) & (unsigned)(val[k] <= hi);
+        nm += in_mask;
+        nb += below;
+        is_c |= inside << k;
       }
     }
     if (__any_sync(0xffffffffu, is_c != 0)) {
