@@ -23,6 +23,8 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <mutex>
+#include <vector>
 #include <type_traits>
 
 #include "common.cuh"
@@ -1111,11 +1113,16 @@ static int launch_strided(const PassDesc& p) {
       dim3 grid((unsigned)bx, (unsigned)nouter, (unsigned)chunks);
       ProfScope prof(names[p.axis == MFISH_AXIS_Z ? 0 : 1][p.op], p.st);
       auto go = [&](auto kern, size_t smem) {
-        static bool configured = false;  // per instantiation (the lambda is instantiated per kernel type)
-        if (!configured) {
+        // every op of one radius shares a function-pointer type, so remember the configured kernels by
+        // address: the walker wants the large shared-memory carve-out (5 blocks x 35 KB per SM)
+        static std::vector<const void*> configured;
+        static std::mutex configured_lock;
+        std::lock_guard<std::mutex> guard(configured_lock);
+        const void* key = reinterpret_cast<const void*>(kern);
+        if (std::find(configured.begin(), configured.end(), key) == configured.end()) {
           cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
           if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-          configured = true;
+          configured.push_back(key);
         }
         kern<<<grid, TTHREADS, smem, p.st>>>(a);
       };
