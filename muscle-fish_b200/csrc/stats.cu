@@ -6,6 +6,8 @@
 //    (muscle_fish.py:362-365,385-388), so it is evaluated sparsely, one warp per spot, in float64.
 #include <algorithm>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mfish {
@@ -680,7 +682,12 @@ static int quantile_fast_impl(const float* vol_dev, const uint8_t* mask_dev, int
   MFISH_CUDA(cudaMallocAsync((void**)&cand, (size_t)cap * sizeof(float), st));
   MFISH_CUDA(cudaMallocAsync((void**)&pair, 2 * sizeof(float) + 3 * sizeof(double), st));
   double* dummy = reinterpret_cast<double*>(pair + 2);
-  const int blocks = (int)std::min<int64_t>((n / 4 + 255) / 256 + 1, (int64_t)num_sms() * 8);
+  static const int range_bps = [] {  // blocks per SM of the one full pass (diagnostic switch)
+    const char* e = getenv("MFISH_QSEL_BPS");
+    const int v = e ? atoi(e) : 0;
+    return v > 0 && v <= 64 ? v : 8;
+  }();
+  const int blocks = (int)std::min<int64_t>((n / 4 + 255) / 256 + 1, (int64_t)num_sms() * range_bps);
   const int sblocks = (int)std::min<int64_t>((n / 4 / 64 + 255) / 256 + 1, (int64_t)num_sms() * 8);
   constexpr int SAMPLE = 64;
   // 1. bracket from the sample
