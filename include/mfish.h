@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MFISH_ABI_VERSION 3
+#define MFISH_ABI_VERSION 4
 
 #define MFISH_OK 0
 #define MFISH_ERR_INVALID (-1)
@@ -255,9 +255,11 @@ int mfish_edt3d_u8(const uint8_t* mask_dev, int64_t nz, int64_t nx, int64_t ny,
 int mfish_edt_inplane_u8(const uint8_t* mask_dev, int64_t nz, int64_t nx, int64_t ny,
                          const double* spacing_zxy_host, void* f2_out_dev, int* f2_kind_host,
                          void* workspace_dev, void* stream);
+/* f2_bound: upper bound on the finite values of f2 (integer kind), or 0 to derive it from nx, ny --
+ * an x-slab of a wider mosaic holds in-plane distances measured over the GLOBAL plane.          */
 int mfish_edt_zpass(const void* f2_dev, int f2_kind, int64_t nz, int64_t nx, int64_t ny,
-                    const double* spacing_zxy_host, float* out_dist_dev, int32_t* out_sq_dev,
-                    void* link_ws_dev, void* stream);
+                    const double* spacing_zxy_host, int64_t f2_bound, float* out_dist_dev,
+                    int32_t* out_sq_dev, void* link_ws_dev, void* stream);
 
 #ifdef __cplusplus
 }

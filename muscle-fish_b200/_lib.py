@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmfish_sm100.so")
 
 # constants mirrored from include/mfish.h
-ABI_VERSION = 3
+ABI_VERSION = 4
 OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 U8, U16, I16, I32, I64, F32, F64 = range(7)
 LAYOUT_XYZ, LAYOUT_ZXY = 0, 1
@@ -64,7 +64,7 @@ SIGNATURES = {
     "mfish_edt_workspace_bytes": (_i64, [_i64, _i64, _i64]),
     "mfish_edt3d_u8": (_i, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p]),
     "mfish_edt_inplane_u8": (_i, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p]),
-    "mfish_edt_zpass": (_i, [_p, _i, _i64, _i64, _i64, _p, _p, _p, _p, _p]),
+    "mfish_edt_zpass": (_i, [_p, _i, _i64, _i64, _i64, _p, _i64, _p, _p, _p, _p]),
     "mfish_export_f64": (_i, [_p, _i64, _i64, _i64, _i, _p, _p]),
 }
 

@@ -613,8 +613,8 @@ extern "C" int mfish_edt_inplane_u8(const uint8_t* mask_dev, int64_t nz, int64_t
 
 // pass 3 along z.  link_ws_dev: nz*nx*ny*4 bytes of scratch.
 extern "C" int mfish_edt_zpass(const void* f2_dev, int f2_kind, int64_t nz, int64_t nx, int64_t ny,
-                               const double* spacing_zxy_host, float* out_dist_dev, int32_t* out_sq_dev,
-                               void* link_ws_dev, void* stream) {
+                               const double* spacing_zxy_host, int64_t f2_bound, float* out_dist_dev,
+                               int32_t* out_sq_dev, void* link_ws_dev, void* stream) {
   MFISH_REQUIRE(f2_dev && link_ws_dev, "edt: null pointer");
   MFISH_REQUIRE(out_dist_dev || out_sq_dev, "edt: no output requested");
   MFISH_REQUIRE(nz > 0 && nx > 0 && ny > 0 && nz < (1 << 24), "edt: bad dimensions");
@@ -634,10 +634,13 @@ extern "C" int mfish_edt_zpass(const void* f2_dev, int f2_kind, int64_t nz, int6
   }
   cudaStream_t st = as_stream(stream);
   const bool link16 = nz <= 32767;
+  // largest finite in-plane value: the caller's bound (x-slabs of a wider mosaic), else this volume's
+  const double plane_max =
+      f2_bound > 0 ? (double)f2_bound : (double)(nx - 1) * (nx - 1) + (double)(ny - 1) * (ny - 1);
   if (f2_kind == MFISH_EDT_F2_I32) {
     const int32_t* f2 = reinterpret_cast<const int32_t*>(f2_dev);
     if (iso) {  // keep integers, scale once at the end: dist = sqrt(sq) * w
-      const double gmax = (double)(nx - 1) * (nx - 1) + (double)(ny - 1) * (ny - 1) + (double)nz * nz;
+      const double gmax = plane_max + (double)nz * nz;
       const double sc = wz * wz;
       if (gmax < 2147483000.0) {
         if (out_dist_dev && out_sq_dev)
@@ -674,5 +677,5 @@ extern "C" int mfish_edt3d_u8(const uint8_t* mask_dev, int64_t nz, int64_t nx, i
   int kind = 0;
   int rc = mfish_edt_inplane_u8(mask_dev, nz, nx, ny, spacing_zxy_host, f2, &kind, workspace_dev, stream);
   if (rc != MFISH_OK) return rc;
-  return mfish_edt_zpass(f2, kind, nz, nx, ny, spacing_zxy_host, out_dist_dev, out_sq_dev, link, stream);
+  return mfish_edt_zpass(f2, kind, nz, nx, ny, spacing_zxy_host, 0, out_dist_dev, out_sq_dev, link, stream);
 }

@@ -663,8 +663,10 @@ def edt_inplane(mask_zxy: torch.Tensor, sampling_xyz=None, out: torch.Tensor | N
     return f2, kind.value
 
 
-def edt_zpass(f2: torch.Tensor, kind: int, sampling_xyz=None, out: torch.Tensor | None = None):
-    """z pass on (possibly re-partitioned) in-plane squared distances -> float32 distances."""
+def edt_zpass(f2: torch.Tensor, kind: int, sampling_xyz=None, out: torch.Tensor | None = None, plane_xy=None):
+    """z pass on (possibly re-partitioned) in-plane squared distances -> float32 distances.
+    ``plane_xy=(nx, ny)``: extents of the plane the in-plane pass ran over when ``f2`` is an x-slab of
+    a wider mosaic (bounds the integer payloads)."""
     nz, nx, ny = f2.shape
     dev = f2.device
     sx, sy, sz = [float(s) for s in (sampling_xyz or (1.0, 1.0, 1.0))]
@@ -672,8 +674,9 @@ def edt_zpass(f2: torch.Tensor, kind: int, sampling_xyz=None, out: torch.Tensor 
     if out is None:
         out = torch.empty((nz, nx, ny), dtype=torch.float32, device=dev)
     f2 = f2.contiguous()
-    L.check(L.lib().mfish_edt_zpass(f2.data_ptr(), int(kind), nz, nx, ny, L.darray([sz, sx, sy]), out.data_ptr(), None,
-                                    link.data_ptr(), _stream()))
+    bound = 0 if plane_xy is None else (int(plane_xy[0]) - 1) ** 2 + (int(plane_xy[1]) - 1) ** 2
+    L.check(L.lib().mfish_edt_zpass(f2.data_ptr(), int(kind), nz, nx, ny, L.darray([sz, sx, sy]), bound,
+                                    out.data_ptr(), None, link.data_ptr(), _stream()))
     return out
 
 

@@ -1,11 +1,27 @@
-"""``import muscle_fish as mf`` drop-in: put this directory first on PYTHONPATH and the
-reference's scripts (general_pipeline/fish_analysis.py:21-22 and friends) pick up the
-B200 spot path unchanged."""
+"""``import muscle_fish as mf`` drop-in: put this directory first on PYTHONPATH (the reference's
+``modules/`` directory after it) and the reference's scripts (general_pipeline/fish_analysis.py:21-22
+and friends) run unchanged: ``find_spots``, ``find_spots_snrfilter`` and ``fix_bleaching`` are the
+B200 implementations, every other name (``open_image``, ``threshold_fiber``, ``threshold_nuclei`` ...)
+falls through to the original module (see ``_passthrough.py``)."""
 import os as _os
 import sys as _sys
 
-_root = _os.path.dirname(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
+_here = _os.path.dirname(_os.path.abspath(__file__))
+_root = _os.path.dirname(_os.path.dirname(_here))
 if _root not in _sys.path:
     _sys.path.insert(0, _root)
 
 from muscle_fish_b200.muscle_fish import find_spots, find_spots_snrfilter, fix_bleaching  # noqa: E402,F401
+from muscle_fish_b200.dropin import _passthrough  # noqa: E402
+
+HOT_PATH = ("find_spots", "find_spots_snrfilter", "fix_bleaching")
+
+
+def __getattr__(name):
+    if name.startswith("__"):
+        raise AttributeError(name)
+    return _passthrough.fallthrough("muscle_fish", _here, name)
+
+
+def __dir__():
+    return sorted(set(globals()) | set(_passthrough.names("muscle_fish", _here)))

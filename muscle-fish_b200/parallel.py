@@ -243,8 +243,9 @@ class DeviceOps:
     def edt_inplane(self, mask, sampling_xyz):
         return self.D.edt_inplane(mask, sampling_xyz, out=_buf("edt_f2", mask.shape, torch.int32, mask.device))
 
-    def edt_zpass(self, f2, kind, sampling_xyz):
-        return self.D.edt_zpass(f2, kind, sampling_xyz, out=_buf("edt_dist", f2.shape, torch.float32, f2.device))
+    def edt_zpass(self, f2, kind, sampling_xyz, plane_xy=None):
+        return self.D.edt_zpass(f2, kind, sampling_xyz, out=_buf("edt_dist", f2.shape, torch.float32, f2.device),
+                                plane_xy=plane_xy)
 
 
 # ------------------------------------------------------------------------ slab-mode pipeline
@@ -387,7 +388,7 @@ def slab_edt(notnuc_slab: torch.Tensor, lay: SlabLayout, sampling_xyz=(1.0, 1.0,
     with _phase("edt_all_to_all"):
         f2x = repartition_z_to_x(f2, lay, group)
     with _phase("edt_zpass"):
-        dx = ops.edt_zpass(f2x, kind, sampling_xyz)
+        dx = ops.edt_zpass(f2x, kind, sampling_xyz, plane_xy=(lay.nx, lay.ny))
     return repartition_x_to_z(dx, lay, group) if back_to_z else dx
 
 

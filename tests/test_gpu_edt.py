@@ -133,7 +133,7 @@ def test_edt_split_inplane_then_zpass_equals_fused():
                                              ws.data_ptr(), D._stream()))
         out = torch.empty((nz, nx, ny), dtype=torch.float32, device="cuda")
         link = torch.empty(nz * nx * ny, dtype=torch.int32, device="cuda")
-        L.check(L.lib().mfish_edt_zpass(f2.data_ptr(), kind.value, nz, nx, ny, sp, out.data_ptr(), None,
+        L.check(L.lib().mfish_edt_zpass(f2.data_ptr(), kind.value, nz, nx, ny, sp, 0, out.data_ptr(), None,
                                         link.data_ptr(), D._stream()))
         assert torch.equal(out, ref)
 

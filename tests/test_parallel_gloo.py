@@ -115,7 +115,7 @@ class OracleOps:
                 f2[z] = ndi.distance_transform_edt(m[z], sampling=(sx, sy)) ** 2
         return torch.from_numpy(f2), 1
 
-    def edt_zpass(self, f2, kind, sampling_xyz):
+    def edt_zpass(self, f2, kind, sampling_xyz, plane_xy=None):
         sz = sampling_xyz[2]
         f = f2.numpy().astype(np.float64)
         nz = f.shape[0]
