@@ -67,7 +67,7 @@ extern "C" {
 #define MFISH_CONV_MID 2  /* out0 = G*in0, out1 = D*in0 + G*in1         */
 #define MFISH_CONV_LAST 3 /* out0 = out_scale * (D*in0 + G*in1)         */
 
-#define MFISH_MAX_RADIUS 128
+#define MFISH_MAX_RADIUS 512
 
 int mfish_abi_version(void);
 const char* mfish_last_error(void);
@@ -160,14 +160,18 @@ int mfish_nms_compact_f32(const float* cube_dev, int64_t ns, int64_t nz, int64_t
                           float threshold, int64_t* out_idx_dev, float* out_val_dev,
                           uint32_t* count_dev, int64_t capacity, void* stream);
 
-/* order peaks like peak_local_max (descending value, ties by ascending
- * raster index) and apply blob_log's _prune_blobs for equal sigma: with
- * integer coordinates, peak r is dropped iff some peak of lower rank-order
- * priority (index > r) lies within squared voxel distance cutoff_sq.
+/* order peaks like peak_local_max and apply blob_log's _prune_blobs for equal sigma.
+ * order = MFISH_ORDER_RESPONSE: descending value, ties by ascending raster index (skimage >= 0.18);
+ * order = MFISH_ORDER_REVERSE_RASTER: descending raster index (skimage 0.14-0.17, the reference's era:
+ * _get_high_intensity_peaks returns np.column_stack(np.nonzero(mask))[::-1]).  With integer
+ * coordinates, the peak of rank r is dropped iff some peak of HIGHER rank index lies within squared
+ * voxel distance cutoff_sq (the lower index of every overlapping pair is zeroed).
  * n is the number of valid entries.  alive_dev[r] in {0,1}.                */
+#define MFISH_ORDER_RESPONSE 0
+#define MFISH_ORDER_REVERSE_RASTER 1
 int mfish_rank_prune(const int64_t* idx_dev, const float* val_dev, int64_t n, int64_t ns,
-                     int64_t nz, int64_t nx, int64_t ny, int64_t cutoff_sq, int64_t* idx_out_dev,
-                     float* val_out_dev, uint8_t* alive_out_dev, void* stream);
+                     int64_t nz, int64_t nx, int64_t ny, int64_t cutoff_sq, int order,
+                     int64_t* idx_out_dev, float* val_out_dev, uint8_t* alive_out_dev, void* stream);
 
 /* candidate pairs for the unequal-sigma prune (multi-scale blob_log,
  * modules/scope_utils3.py:403): all i<j (rank order) whose squared voxel

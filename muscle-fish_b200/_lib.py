@@ -22,6 +22,7 @@ AXIS_Z, AXIS_X, AXIS_Y = 0, 1, 2
 CONV_G, CONV_GD, CONV_MID, CONV_LAST = 0, 1, 2, 3
 QUANTILE_WS_BYTES = 64 * 1024
 EDT_F2_I32, EDT_F2_F32 = 0, 1
+ORDER_RESPONSE, ORDER_REVERSE_RASTER = 0, 1
 
 
 class MfishError(RuntimeError):
@@ -48,7 +49,7 @@ SIGNATURES = {
     "mfish_log3d_range_f32": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _d, _p, _i64, _i64, _p]),
     "mfish_log3d_peaks_f32": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _d, _p, _f, _p, _i64, _p, _p, _p, _i64, _p]),
     "mfish_nms_compact_f32": (_i, [_p, _i64, _i64, _i64, _i64, _f, _p, _p, _p, _i64, _p]),
-    "mfish_rank_prune": (_i, [_p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p, _p, _p]),
+    "mfish_rank_prune": (_i, [_p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i, _p, _p, _p, _p]),
     "mfish_overlap_pairs": (_i, [_p, _i64, _i64, _i64, _i64, _i64, _p, _p, _p, _i64, _p]),
     "mfish_masked_quantile_f32": (_i, [_p, _p, _i64, _d, _p, _p, _p, _p]),
     "mfish_masked_quantile_fast_f32": (_i, [_p, _p, _i64, _d, _p, _p, _p, _p]),

@@ -195,6 +195,11 @@ __global__ void iota_kernel(int32_t* p, int64_t n) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = (int32_t)i;
 }
+// rank r <- position n-1-r of the ascending raster order (reverse raster order)
+__global__ void reverse_iota_kernel(int32_t* p, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = (int32_t)(n - 1 - i);
+}
 
 // descending value  <=>  ascending ~key
 __global__ void desc_key_kernel(const float* val, uint32_t* key, int64_t n) {
@@ -342,7 +347,7 @@ struct RankBuffers {
 };
 
 static int rank_spots(const int64_t* idx, const float* val, int64_t n, int64_t* idx_out, float* val_out,
-                      RankBuffers& b, cudaStream_t st) {
+                      RankBuffers& b, int order, cudaStream_t st) {
   MFISH_REQUIRE(n < (1ll << 31), "rank: too many peaks");
   const int ni = (int)n;
   MFISH_CUDA(cudaMallocAsync((void**)&b.idxA, n * sizeof(int64_t), st));
@@ -359,10 +364,14 @@ static int rank_spots(const int64_t* idx, const float* val, int64_t n, int64_t* 
   MFISH_CUDA(cudaMallocAsync(&b.cub_tmp, tb, st));
   MFISH_CUDA(cub::DeviceRadixSort::SortPairs(b.cub_tmp, tb, idx, b.idxA, val, b.valA, ni, 0, 64, st));
   int blocks = (int)((n + 255) / 256);
-  iota_kernel<<<blocks, 256, 0, st>>>(b.posA, n);
-  desc_key_kernel<<<blocks, 256, 0, st>>>(b.valA, b.key, n);
-  MFISH_CUDA(cub::DeviceRadixSort::SortPairs(b.cub_tmp, tb, b.key, b.key_sorted, b.posA, b.pos_of_rank, ni,
-                                             0, 32, st));
+  if (order == MFISH_ORDER_REVERSE_RASTER) {
+    reverse_iota_kernel<<<blocks, 256, 0, st>>>(b.pos_of_rank, n);
+  } else {
+    iota_kernel<<<blocks, 256, 0, st>>>(b.posA, n);
+    desc_key_kernel<<<blocks, 256, 0, st>>>(b.valA, b.key, n);
+    MFISH_CUDA(cub::DeviceRadixSort::SortPairs(b.cub_tmp, tb, b.key, b.key_sorted, b.posA, b.pos_of_rank, ni,
+                                               0, 32, st));
+  }
   apply_rank_kernel<<<blocks, 256, 0, st>>>(b.pos_of_rank, b.idxA, b.valA, idx_out, val_out, b.rank_of_pos, n);
   count_launch(5);
   return check_launch("rank_spots");
@@ -397,16 +406,17 @@ extern "C" int mfish_nms_compact_f32(const float* cube_dev, int64_t ns, int64_t 
 }
 
 extern "C" int mfish_rank_prune(const int64_t* idx_dev, const float* val_dev, int64_t n, int64_t ns,
-                                int64_t nz, int64_t nx, int64_t ny, int64_t cutoff_sq, int64_t* idx_out_dev,
-                                float* val_out_dev, uint8_t* alive_out_dev, void* stream) {
+                                int64_t nz, int64_t nx, int64_t ny, int64_t cutoff_sq, int order,
+                                int64_t* idx_out_dev, float* val_out_dev, uint8_t* alive_out_dev, void* stream) {
   MFISH_REQUIRE(n >= 0, "rank_prune: negative n");
+  MFISH_REQUIRE(order == MFISH_ORDER_RESPONSE || order == MFISH_ORDER_REVERSE_RASTER, "rank_prune: bad order");
   if (n == 0) return MFISH_OK;
   MFISH_REQUIRE(idx_dev && val_dev && idx_out_dev && val_out_dev && alive_out_dev, "rank_prune: null pointer");
   MFISH_REQUIRE(cutoff_sq < (1 << 20), "rank_prune: cutoff too large");
   cudaStream_t st = as_stream(stream);
   ProfScope prof("rank_prune", st);
   RankBuffers b;
-  int rc = rank_spots(idx_dev, val_dev, n, idx_out_dev, val_out_dev, b, st);
+  int rc = rank_spots(idx_dev, val_dev, n, idx_out_dev, val_out_dev, b, order, st);
   if (rc == MFISH_OK) {
     if (cutoff_sq < 1) {
       MFISH_CUDA(cudaMemsetAsync(alive_out_dev, 1, n, st));

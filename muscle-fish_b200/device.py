@@ -190,6 +190,20 @@ def ingest(src, z_first=False, as_mask=False, want_minmax=True, negate=False, re
     return Volume(out, mm)
 
 
+def ingest_as_float(src):
+    """``skimage.util.img_as_float`` semantics for the inputs of blob_log / filters.gaussian: floating
+    images as they are, unsigned integers divided by the type's maximum, bool as 0/1.  The scale is
+    applied on load by the first filter pass (``Volume.minmax`` = {0, type max})."""
+    a = src if isinstance(src, torch.Tensor) else np.asarray(src)
+    dt = np.dtype(str(a.dtype).replace("torch.", "")) if isinstance(a, torch.Tensor) else a.dtype
+    vol = ingest(a, want_minmax=False)
+    if dt.kind == "u":
+        vol.minmax = torch.tensor([0.0, float(np.iinfo(dt).max)], dtype=torch.float32, device=vol.data.device)
+    elif dt.kind == "i":
+        raise NotImplementedError("signed integer images: convert with skimage.util.img_as_float first")
+    return vol
+
+
 def minmax(vol: torch.Tensor) -> torch.Tensor:
     mm = torch.empty(2, dtype=torch.float32, device=vol.device)
     L.check(L.lib().mfish_minmax_f32(vol.data_ptr(), vol.numel(), mm.data_ptr(), _stream()))
@@ -369,8 +383,23 @@ def log_peaks_async(vol: Volume, sigma: float, threshold: float, out: torch.Tens
     return out, finish
 
 
-def rank_prune_equal(idx, val, dims_sxyz, cutoff_sq: int):
-    """Order peaks (descending value, ties by raster index) and apply the equal-sigma prune.
+# Order in which peak_local_max hands the peaks to _prune_blobs (it decides which blob of an overlapping
+# equal-sigma pair survives, ~0.1 % of the peaks at the dense-stress density and none at C1/C2 density --
+# tools/measure_peak_order.py): "response" = skimage >= 0.18 (descending intensity, the frozen default),
+# "reverse_raster" = skimage 0.14-0.17, the reference's era.  MFISH_PEAK_ORDER overrides the default.
+PEAK_ORDERS = {"response": L.ORDER_RESPONSE, "reverse_raster": L.ORDER_REVERSE_RASTER}
+DEFAULT_PEAK_ORDER = os.environ.get("MFISH_PEAK_ORDER", "response")
+
+
+def _order_code(peak_order):
+    po = DEFAULT_PEAK_ORDER if peak_order is None else peak_order
+    if po not in PEAK_ORDERS:
+        raise ValueError(f"peak_order must be one of {sorted(PEAK_ORDERS)}, got {po!r}")
+    return PEAK_ORDERS[po]
+
+
+def rank_prune_equal(idx, val, dims_sxyz, cutoff_sq: int, peak_order=None):
+    """Order peaks (``peak_order``) and apply the equal-sigma prune.
     Returns (idx_ranked, val_ranked, alive uint8), all on the device."""
     ns, nx, ny, nz = dims_sxyz
     n = idx.numel()
@@ -380,7 +409,8 @@ def rank_prune_equal(idx, val, dims_sxyz, cutoff_sq: int):
     alive = torch.ones(n, dtype=torch.uint8, device=dev)
     if n:
         L.check(L.lib().mfish_rank_prune(idx.data_ptr(), val.data_ptr(), n, ns, nz, nx, ny, int(cutoff_sq),
-                                         idx_o.data_ptr(), val_o.data_ptr(), alive.data_ptr(), _stream()))
+                                         _order_code(peak_order), idx_o.data_ptr(), val_o.data_ptr(),
+                                         alive.data_ptr(), _stream()))
     return idx_o, val_o, alive
 
 
@@ -436,7 +466,8 @@ def prune_unequal_host(n, s_idx, sigmas, pairs):
     return sig
 
 
-def blob_log(vol: Volume, min_sigma, max_sigma, num_sigma, threshold, overlap=0.5, cube=None, before_sync=None):
+def blob_log(vol: Volume, min_sigma, max_sigma, num_sigma, threshold, overlap=0.5, cube=None, before_sync=None,
+             peak_order=None):
     """skimage.feature.blob_log on the device.  Returns host float64 array (N, 4) rows
     [x, y, z, sigma] in peak_local_max order (descending response).  ``before_sync`` (optional
     callable) is run after the filters and the peak detection have been queued and before the host
@@ -458,13 +489,13 @@ def blob_log(vol: Volume, min_sigma, max_sigma, num_sigma, threshold, overlap=0.
         return np.empty((0, 3))
     if ns == 1:
         cutoff = T.prune_cutoff_sq(float(sigmas[0]), None, overlap)
-        idx_r, _, alive = rank_prune_equal(idx, val, dims, max(cutoff, 0))
+        idx_r, _, alive = rank_prune_equal(idx, val, dims, max(cutoff, 0), peak_order)
         keep = alive.bool()
         idx_h = idx_r[keep].cpu().numpy()
         x, y, z, s = decode_raster(idx_h, dims)
         return np.stack([x, y, z, sigmas[s]], axis=1).astype(np.float64)
     # multi-scale: rank, candidate pairs on the device, sequential sigma rule on the host
-    idx_r, _, _ = rank_prune_equal(idx, val, dims, 0)
+    idx_r, _, _ = rank_prune_equal(idx, val, dims, 0, peak_order)
     cut = np.array([[T.prune_cutoff_sq(float(a), float(b), overlap) for b in sigmas] for a in sigmas], dtype=np.int64)
     pairs = overlap_pairs(idx_r, dims, cut)
     idx_h = idx_r.cpu().numpy()

@@ -72,6 +72,5 @@ def gaussian_laplace(image, sigma):
 
 def blob_log(image, min_sigma=1, max_sigma=50, num_sigma=10, threshold=.2, overlap=.5):
     """skimage.feature.blob_log for a 3-D float image (linear sigma ladder, scalar sigmas)."""
-    a = np.asarray(image)
-    vol = D.ingest(a, want_minmax=False)
+    vol = D.ingest_as_float(np.asarray(image))
     return D.blob_log(vol, min_sigma, max_sigma, num_sigma, threshold, overlap)

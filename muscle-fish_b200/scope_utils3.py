@@ -29,8 +29,16 @@ def optimize_threshold_blob_log(image, min_sigma=1., max_sigma=50., num_sigma=10
     from scipy.signal import argrelextrema
     from . import taps as T
 
-    vol = D.ingest(np.asarray(image), want_minmax=False)  # blob_log is applied to the image as given
+    vol = D.ingest_as_float(np.asarray(image))  # blob_log applies img_as_float, nothing else
     sigmas = T.sigma_list(min_sigma, max_sigma, num_sigma)
+    # the whole scale cube is resident (num_sigma float32 volumes + 3 scratch volumes): C2 with the default
+    # 10 scales is 22 GB of the 180 GB; refuse loudly rather than thrash when it cannot fit
+    import torch
+    need = (len(sigmas) + 4) * vol.data.numel() * 4
+    free, _ = torch.cuda.mem_get_info(vol.data.device)
+    if need > free:
+        raise MemoryError(f"optimize_threshold_blob_log: the {len(sigmas)}-scale cube needs {need / 2**30:.1f} GiB "
+                          f"of device memory, {free / 2**30:.1f} GiB are free; lower num_sigma or crop the image")
     cube = D.log_cube(vol, sigmas)
     t_range = np.linspace(tmin, tmax, num=num)
     num_spots = [len(D.blob_log(vol, min_sigma, max_sigma, num_sigma, t, cube=cube)) for t in t_range]

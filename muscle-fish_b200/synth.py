@@ -108,12 +108,34 @@ def make_config(name, **over):
     return make_stack(**kw)
 
 
+def make_threshold_stack(shape=(72, 72, 24)):
+    """Noise-free float64 stack whose blob count first falls, then rises, then falls with the blob_log
+    threshold -- the shape ``su.optimize_threshold_blob_log`` (modules/scope_utils3.py:388-422) looks
+    for.  Three broad dim blobs (sigma 5), each with six bright small spots 4-6.5 voxels from its centre
+    (inside its blob sphere: pruned for as long as the broad blob is detected), plus five isolated weak
+    spots that drop out one after the other.  With sigmas (1, 3, 5) and thresholds 0, 0.01 ... 0.2 the
+    counts are 8 8 6 4 4 3 3 3 3 3 3 8 13 18 18 ... and the chosen threshold is 0.02."""
+    X, Y, Z = np.meshgrid(*[np.arange(n, dtype=np.float64) for n in shape], indexing="ij")
+    img = np.zeros(shape)
+
+    def g(cx, cy, cz, a, s):
+        return a * np.exp(-((X - cx) ** 2 + (Y - cy) ** 2 + (Z - cz) ** 2) / (2 * s * s))
+
+    for (cx, cy, amp) in [(18, 18, 9.0), (52, 20, 8.0), (20, 52, 7.0)]:
+        img += g(cx, cy, 12, amp, 5.0)
+        for k, (dx, dy, dz) in enumerate([(5, 0, 0), (-5, 1, 0), (0, 5, 1), (1, -5, -1), (3, 3, 2), (-3, -4, -2)]):
+            img += g(cx + dx, cy + dy, 12 + dz, 40.0 + 3 * k, 1.0)
+    for k, a in enumerate([1.2, 1.8, 2.3, 2.8, 5.5]):
+        img += g(44 + 6 * (k % 3), 44 + 8 * (k // 3), 6 + 3 * k, a, 1.0)
+    return img
+
+
 def make_stack_device(shape, n_spots, n_nuclei, seed, device="cuda", z_first=True, z_range=None):
     """Same distribution drawn on the GPU with torch (bench inputs only).
 
     ``z_range=(z0, z1)`` draws only those planes of the stack (one z-slab of a mosaic): spots,
-    fibre and nuclei are the global ones, so neighbouring slabs are consistent; only the noise
-    stream is per-slab.
+    fibre and nuclei are the global ones and the noise is seeded per global plane, so the slabs of any
+    decomposition are exactly the planes of the whole stack.
 
     Returns float32 image and uint8 masks as torch tensors on ``device`` in
     (z, x, y) order when ``z_first`` else (x, y, z).  Spot/nucleus centres
@@ -127,9 +149,10 @@ def make_stack_device(shape, n_spots, n_nuclei, seed, device="cuda", z_first=Tru
     ZL = zb - za
     rng = np.random.default_rng(seed)
     g = torch.Generator(device=device)
-    g.manual_seed(int(seed) + 7919 * za)
     img = torch.empty((ZL, X, Y), dtype=torch.float32, device=device)
-    img.normal_(100.0, 10.0, generator=g)
+    for z in range(za, zb):  # one noise stream per GLOBAL plane: a slab of any decomposition draws the same voxels
+        g.manual_seed((int(seed) * 1000003 + z * 7919) & 0x7FFFFFFFFFFFFFFF)
+        img[z - za].normal_(100.0, 10.0, generator=g)
     y0, y1, z0, z1 = _fiber_bounds(shape)
     fiber = torch.zeros((ZL, X, Y), dtype=torch.uint8, device=device)
     fz0, fz1 = max(z0, za) - za, min(z1, zb) - za

@@ -62,7 +62,12 @@ def log_cube(image, sigmas):
 # p=inf) in new releases rejects only points at distance < 1, i.e. nothing on
 # integer coordinates, so plateau ties are all kept.
 # --------------------------------------------------------------------------- #
-def peak_local_max(cube, threshold_abs, threshold_rel=0.0):
+def peak_local_max(cube, threshold_abs, threshold_rel=0.0, peak_order="response"):
+    """``peak_order='response'``: skimage >= 0.18 (stable descending intensity over raster order).
+    ``peak_order='reverse_raster'``: skimage 0.14-0.17, the reference's era -- with ``num_peaks=inf``
+    ``_get_high_intensity_peaks`` returns ``np.column_stack(np.nonzero(mask))[::-1]``.  Same SET of peaks;
+    the order decides which blob of an overlapping equal-sigma pair ``_prune_blobs`` zeroes (the lower
+    index: the brighter one under 'response', the raster-later one under 'reverse_raster')."""
     cube = np.asarray(cube)
     fp = np.ones((3,) * cube.ndim, dtype=bool)
     mx = ndi.maximum_filter(cube, footprint=fp, mode="constant")
@@ -74,6 +79,10 @@ def peak_local_max(cube, threshold_abs, threshold_rel=0.0):
         thr = max(thr, threshold_rel * cube.max())
     mask &= cube > thr
     coord = np.nonzero(mask)
+    if peak_order == "reverse_raster":
+        return np.transpose(coord)[::-1]
+    if peak_order != "response":
+        raise ValueError(peak_order)
     intens = cube[coord]
     order = np.argsort(-intens, kind="stable")
     return np.transpose(coord)[order]
@@ -179,11 +188,11 @@ def prune_cutoff_sq(sigma, ndim=3, overlap=0.5):
 # skimage.feature.blob_log(image, min_sigma, max_sigma, num_sigma, threshold)
 # --------------------------------------------------------------------------- #
 def blob_log(image, min_sigma=1, max_sigma=50, num_sigma=10, threshold=0.2,
-             overlap=0.5, pair_order="set", return_raw=False):
+             overlap=0.5, pair_order="set", return_raw=False, peak_order="response"):
     image = np.asarray(image, dtype=np.float64)
     sigmas = sigma_list(min_sigma, max_sigma, num_sigma)
     cube = log_cube(image, sigmas)
-    peaks = peak_local_max(cube, threshold_abs=threshold, threshold_rel=0.0)
+    peaks = peak_local_max(cube, threshold_abs=threshold, threshold_rel=0.0, peak_order=peak_order)
     if peaks.size == 0:
         out = np.empty((0, 3))
         return (out, out) if return_raw else out
@@ -196,9 +205,9 @@ def blob_log(image, min_sigma=1, max_sigma=50, num_sigma=10, threshold=0.2,
 # --------------------------------------------------------------------------- #
 # modules/muscle_fish.py:631-672
 # --------------------------------------------------------------------------- #
-def find_spots(img_fish, sigma=1.0, t_spot=0.025, mask=None, pair_order="set"):
+def find_spots(img_fish, sigma=1.0, t_spot=0.025, mask=None, pair_order="set", peak_order="response"):
     spots = blob_log(normalize_image(img_fish), sigma, sigma, num_sigma=1,
-                     threshold=t_spot, pair_order=pair_order)
+                     threshold=t_spot, pair_order=pair_order, peak_order=peak_order)
     if mask is not None:
         keep = [s for s in spots if mask[tuple(s[0:3].astype(int))]]
         return np.vstack(keep)  # np.row_stack([]) -> ValueError, as upstream
@@ -209,7 +218,7 @@ def find_spots(img_fish, sigma=1.0, t_spot=0.025, mask=None, pair_order="set"):
 # modules/muscle_fish.py:281-402 (draw=False path)
 # --------------------------------------------------------------------------- #
 def find_spots_snrfilter(img_fish, snr=None, sigma=1.0, t_spot=0.025, mask=None,
-                         z_first=False, pair_order="set", verbose=False):
+                         z_first=False, pair_order="set", verbose=False, peak_order="response"):
     if z_first:
         img_fish = normalize_image(np.asarray(img_fish).transpose(1, 2, 0))
         if mask is not None:
@@ -218,7 +227,7 @@ def find_spots_snrfilter(img_fish, snr=None, sigma=1.0, t_spot=0.025, mask=None,
         img_fish = normalize_image(img_fish)
 
     spots = blob_log(normalize_image(img_fish), sigma, sigma, num_sigma=1,
-                     threshold=t_spot, pair_order=pair_order)
+                     threshold=t_spot, pair_order=pair_order, peak_order=peak_order)
     if mask is not None:
         spots_masked = [s for s in spots if mask[tuple(s[0:3].astype(int))]]
         spots_masked = np.vstack(spots_masked)

@@ -53,3 +53,42 @@ def match_fraction(a, b):
     if not sa and not sb:
         return 1.0
     return len(sa & sb) / max(len(sa), len(sb))
+
+
+def boundary_safe_peaks(raw_blobs, crop_xy, edge_unsafe, overlap=0.5):
+    """Which raw peaks of a CROP have a blob_log outcome that provably does not depend on the crop's
+    artificial x/y faces: a peak is unsafe if it lies within ``edge_unsafe`` voxels of such a face
+    (filter radius + NMS: its response or its very existence may differ from the whole volume), and so
+    is every peak connected to an unsafe one through a chain of blob pairs overlapping by more than
+    ``overlap`` -- only such pairs make ``_prune_blobs`` zero anything, so only they carry a change
+    along.  ``raw_blobs`` rows [x, y, z, sigma]; ``crop_xy`` = ((nx, ny), ((x_lo_cut, x_hi_cut),
+    (y_lo_cut, y_hi_cut))): is that face a cut (True) or a real volume face (False).
+    Returns a set of integer (x, y, z) tuples."""
+    import math
+    import oracle
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    from scipy.spatial import cKDTree
+    b = np.asarray(raw_blobs, dtype=np.float64)
+    n = len(b)
+    if n == 0:
+        return set()
+    (nx, ny), ((xl, xh), (yl, yh)) = crop_xy[0], crop_xy[1]
+    unsafe = np.zeros(n, bool)
+    if xl:
+        unsafe |= b[:, 0] < edge_unsafe
+    if xh:
+        unsafe |= b[:, 0] >= nx - edge_unsafe
+    if yl:
+        unsafe |= b[:, 1] < edge_unsafe
+    if yh:
+        unsafe |= b[:, 1] >= ny - edge_unsafe
+    cand = cKDTree(b[:, :3]).query_pairs(2 * b[:, 3].max() * math.sqrt(3.0), output_type="ndarray")
+    edges = [(i, j) for i, j in cand if oracle.blob_overlap(b[i], b[j]) > overlap]
+    if edges:
+        e = np.asarray(edges)
+        g = coo_matrix((np.ones(len(e)), (e[:, 0], e[:, 1])), shape=(n, n))
+        _, lab = connected_components(g, directed=False)
+        unsafe = np.isin(lab, np.unique(lab[unsafe]))
+    pts = b[~unsafe, :3].astype(np.int64)
+    return set(map(tuple, pts.tolist()))

@@ -122,32 +122,49 @@ def test_c2_edt_properties_and_crops(c2):
 
 def test_c5_dense_multiscale_matches_oracle_on_crops():
     """configs[4]: 2048x2048x100, ~500k spots, sigma sweep 1..3 (5 scales): 80-neighbour NMS,
-    unequal-sigma prune on the compacted list"""
+    unequal-sigma prune on the compacted list.  The crop's own faces change the LoG within 13 voxels
+    (radius 12 at sigma 3 + NMS) and sequential pruning carries such a change along chains of
+    overlapping blobs, so peaks connected to the contaminated rim through overlapping pairs are left out
+    of the comparison on BOTH sides (conftest.boundary_safe_peaks); everything else must match to
+    99.9 %."""
     import torch
     import muscle_fish_b200  # noqa: F401
     from muscle_fish_b200 import device as D, synth
+    from conftest import boundary_safe_peaks
     st = synth.make_stack_device(SHAPE, 500000, 120, 5)
     img = st["img"]
     mm = D.minmax(img)
     lo, hi = [float(v) for v in mm.tolist()]
     spots = D.blob_log(D.Volume(img, mm), 1.0, 3.0, 5, 0.02)
     assert len(spots) > 200000
-    H = 40
-    n_ref = n_match = 0
-    for (x0, y0) in [(300, 500), (1500, 1100)]:
-        x1, y1 = x0 + 144, y0 + 144
+    C, H = 176, 32
+    n_ref = n_got = n_match = n_excluded = 0
+    for (x0, y0) in [(300, 500), (1500, 1100), (0, 1872)]:
+        x1, y1 = x0 + C, y0 + C
         crop = _crop_xyz(img, x0, x1, y0, y1).astype(np.float64)
         norm = (crop - lo) * (1.0 / (hi - lo))
-        ref = oracle.blob_log(norm, 1.0, 3.0, 5, 0.02, pair_order="sorted")
-        inside = lambda s: ((s[:, 0] >= H) & (s[:, 0] < 144 - H) & (s[:, 1] >= H) & (s[:, 1] < 144 - H))
-        ref_in = ref[inside(ref)]
+        ref, raw = oracle.blob_log(norm, 1.0, 3.0, 5, 0.02, pair_order="sorted", return_raw=True)
+        cuts = ((x0 > 0, x1 < SHAPE[0]), (y0 > 0, y1 < SHAPE[1]))
+        safe = boundary_safe_peaks(raw, ((C, C), cuts), edge_unsafe=14)
+        rawset = set(map(tuple, raw[:, :3].astype(np.int64).tolist()))
+        n_excluded += len(rawset) - len(safe)
+        xa, xb = (H if cuts[0][0] else 0), (C - H if cuts[0][1] else C)
+        ya, yb = (H if cuts[1][0] else 0), (C - H if cuts[1][1] else C)
+        inside = lambda s: ((s[:, 0] >= xa) & (s[:, 0] < xb) & (s[:, 1] >= ya) & (s[:, 1] < yb))
         g = spots[(spots[:, 0] >= x0) & (spots[:, 0] < x1) & (spots[:, 1] >= y0) & (spots[:, 1] < y1)].copy()
         g[:, 0] -= x0
         g[:, 1] -= y0
-        g_in = g[inside(g)]
+
+        def comparable(s):
+            s = s[inside(s)]
+            pts = list(map(tuple, s[:, :3].astype(np.int64).tolist()))
+            # a device spot that is not a raw peak of the oracle at all stays in (it counts as a miss)
+            return s[[p in safe or p not in rawset for p in pts]] if len(s) else s
+
+        ref_in, g_in = comparable(ref), comparable(g)
         n_ref += len(ref_in)
+        n_got += len(g_in)
         n_match += len(spot_set(g_in) & spot_set(ref_in))
-        assert abs(len(g_in) - len(ref_in)) <= max(2, 0.01 * len(ref_in))
-    assert n_ref > 300
-    # dense overlapping blobs: sequential prune chains can differ where a chain crosses the crop margin
-    assert n_match / n_ref >= 0.99
+    assert n_ref > 1500
+    assert n_excluded < 0.5 * n_ref  # the exclusion is a rim effect, not the bulk
+    assert n_match / max(n_ref, n_got) >= 0.999, (n_match, n_ref, n_got)

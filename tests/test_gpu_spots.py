@@ -160,7 +160,7 @@ def test_blob_log_multi_scale_vs_oracle():
     assert len(ref) > 300
     assert match_fraction(got, ref) >= MIN_MATCH
     ref_set = oracle.blob_log(img, 1.0, 3.0, 5, 0.02, pair_order="set")
-    assert match_fraction(got, ref_set) >= 0.995
+    assert match_fraction(got, ref_set) >= MIN_MATCH
 
 
 def test_blob_log_no_peaks_returns_empty_0x3():
@@ -344,6 +344,114 @@ def test_optimize_threshold_blob_log_counts():
         ref_counts.append(len(oracle.blob_log(img, 1.0, 2.0, 2, threshold=t, pair_order="sorted")))
         got = len(D.blob_log(vol, 1.0, 2.0, 2, t, cube=cube))
         assert abs(got - ref_counts[-1]) <= max(1, round(0.001 * ref_counts[-1]))
+
+
+def test_optimize_threshold_blob_log_itself_vs_oracle(capsys):
+    """modules/scope_utils3.py:388-422 called as the reference calls it: same chosen threshold, the
+    'Optimal threshold value' print, and IndexError when the counts have no plateau inflection (which is
+    what a monotonically falling count gives upstream)."""
+    from muscle_fish_b200 import scope_utils3 as su, synth
+    img = oracle.normalize_image(synth.make_threshold_stack())
+    t_ref, counts = oracle.optimize_threshold_blob_log(img, 1.0, 5.0, 3, 0.0, 0.2, 21, pair_order="sorted")
+    assert counts.tolist()[:13] == [8, 8, 6, 4, 4, 3, 3, 3, 3, 3, 3, 8, 13] and abs(t_ref - 0.02) < 1e-12
+    t_got = su.optimize_threshold_blob_log(img, min_sigma=1., max_sigma=5., num_sigma=3, tmin=0., tmax=0.2, num=21)
+    assert t_got == t_ref
+    assert "Optimal threshold value for blob_log: " + str(t_ref) in capsys.readouterr().out
+    # float32 input takes the same path
+    assert su.optimize_threshold_blob_log(img.astype(np.float32), 1., 5., 3, 0., 0.2, 21) == t_ref
+    # a natural stack: the count only falls with the threshold -> no inflection before the spike
+    st = synth.make_stack(shape=(96, 80, 20), n_spots=300, n_nuclei=1, seed=21)
+    nat = oracle.normalize_image(st["img"])
+    with pytest.raises(IndexError):
+        oracle.optimize_threshold_blob_log(nat, 1.0, 2.0, 2, 0.0, 0.1, 8, pair_order="sorted")
+    with pytest.raises(IndexError):
+        su.optimize_threshold_blob_log(nat, 1.0, 2.0, 2, 0.0, 0.1, 8)
+
+
+def test_optimize_threshold_blob_log_default_sigma_ladder():
+    """the signature defaults (max_sigma=50, num_sigma=10: radii up to 200 voxels, reflect folding many
+    times over a short z axis) run through the large-radius filter path: counts equal the oracle's"""
+    from muscle_fish_b200 import device as D, ndimage as nd, taps as T
+    rng = np.random.default_rng(31)
+    img = rng.random((40, 36, 12))
+    img[20, 18, 6] += 6.0
+    img[8, 30, 3] += 4.0
+    img = oracle.normalize_image(img)
+    ref = oracle.blob_log(img, 1.0, 50.0, 10, threshold=0.05, pair_order="sorted")
+    got = nd.blob_log(img, 1.0, 50.0, 10, threshold=0.05)
+    assert len(ref) >= 2
+    assert match_fraction(got, ref) >= MIN_MATCH
+    cube = D.log_cube(D.ingest(img, want_minmax=False), T.sigma_list(1.0, 50.0, 10))
+    ref_cube = oracle.log_cube(img, oracle.sigma_list(1.0, 50.0, 10))
+    got_cube = cube.permute(2, 3, 1, 0).cpu().numpy()
+    assert np.max(np.abs(got_cube - ref_cube)) / np.max(np.abs(ref_cube)) < 1e-5
+
+
+def test_blob_log_integer_images_are_scaled_like_img_as_float():
+    """skimage.feature.blob_log starts with img_as_float: uint8 / 255, uint16 / 65535"""
+    from muscle_fish_b200 import ndimage as nd, synth
+    st = synth.make_stack(shape=(64, 56, 16), n_spots=60, n_nuclei=1, seed=33)
+    u16 = np.clip(st["img"] * 20.0, 0, 65535).astype(np.uint16)
+    ref = oracle.blob_log(u16.astype(np.float64) / 65535.0, 2.0, 2.0, 1, 0.005, pair_order="sorted")
+    got = nd.blob_log(u16, 2.0, 2.0, 1, 0.005)
+    assert len(ref) > 20 and match_fraction(got, ref) >= MIN_MATCH
+    u8 = np.clip(st["img"] / 8.0, 0, 255).astype(np.uint8)
+    ref8 = oracle.blob_log(u8.astype(np.float64) / 255.0, 2.0, 2.0, 1, 0.01, pair_order="sorted")
+    got8 = nd.blob_log(u8, 2.0, 2.0, 1, 0.01)
+    assert len(ref8) > 10 and match_fraction(got8, ref8) >= MIN_MATCH
+
+
+@pytest.mark.parametrize("peak_order", ["response", "reverse_raster"])
+def test_peak_order_decides_the_survivor_like_the_oracle(peak_order):
+    """skimage >= 0.18 hands _prune_blobs the peaks in descending-response order, 0.14-0.17 (the
+    reference's era) in reverse raster order; the lower INDEX of an overlapping equal-sigma pair is
+    zeroed, so the order picks the survivor.  Both orders are implemented; each matches the oracle run
+    with the same order, on a list dense enough that a quarter of the peaks is pruned."""
+    import torch
+    from muscle_fish_b200 import device as D, taps as T
+    rng = np.random.default_rng(41)
+    shape = (40, 36, 12)
+    n = 1500
+    flat = np.sort(rng.choice(np.prod(shape), size=n, replace=False))
+    vals = rng.random(n).astype(np.float32)
+    dims = (1,) + shape
+    idx_r, val_r, alive = D.rank_prune_equal(torch.from_numpy(flat.astype(np.int64)).cuda(),
+                                             torch.from_numpy(vals).cuda(), dims, T.prune_cutoff_sq(2.0),
+                                             peak_order=peak_order)
+    x, y, z, _ = D.decode_raster(idx_r.cpu().numpy(), dims)
+    order = np.lexsort((flat, -vals.astype(np.float64))) if peak_order == "response" else np.arange(n)[::-1]
+    xr, yr, zr = np.unravel_index(flat[order], shape)
+    np.testing.assert_array_equal(np.stack([x, y, z], 1), np.stack([xr, yr, zr], 1))  # same ranking
+    np.testing.assert_array_equal(val_r.cpu().numpy(), vals[order])
+    blobs = np.stack([xr, yr, zr, np.full(n, 2.0)], axis=1).astype(np.float64)
+    ref = oracle.prune_blobs(blobs, 0.5, pair_order="sorted")
+    keep = alive.cpu().numpy().astype(bool)
+    got = blobs[keep]
+    assert len(ref) < 0.8 * n
+    np.testing.assert_array_equal(got, ref)
+
+
+def test_peak_orders_on_a_dense_stack_vs_oracle_and_each_other():
+    """config-5 density: each order matches its oracle to 99.9 %, and the two survivor sets differ by
+    less than 0.1 % of the spots (measured on the CPU in tools/measure_peak_order.py: 3 of 4057)"""
+    from muscle_fish_b200 import device as D, synth
+    full = np.prod((2048, 2048, 100))
+    shape = (224, 224, 64)
+    st = synth.make_stack(shape=shape, n_spots=int(500000 * np.prod(shape) / full), n_nuclei=1, seed=5)
+    img = oracle.normalize_image(st["img"])
+    vol = D.ingest(st["img"])
+    res = {}
+    for po in ("response", "reverse_raster"):
+        ref = oracle.blob_log(img, 2.0, 2.0, 1, 0.025, pair_order="sorted", peak_order=po)
+        got = D.blob_log(vol, 2.0, 2.0, 1, 0.025, peak_order=po)
+        assert len(ref) > 2000
+        assert match_fraction(got, ref) >= MIN_MATCH, po
+        res[po] = got
+    # reverse raster order of the rows themselves
+    r = res["reverse_raster"]
+    ras = (r[:, 0] * shape[1] + r[:, 1]) * shape[2] + r[:, 2]
+    assert np.all(np.diff(ras) < 0)
+    assert match_fraction(res["response"], res["reverse_raster"]) >= MIN_MATCH
 
 
 def test_golden_spots(golden):
