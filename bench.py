@@ -10,16 +10,27 @@ P25 baseline -> Gaussian blur at spots -> SNR filter, then the anisotropic EDT o
 NOT-nucleus mask and the per-spot distance gather.
 
 * ``value``  : voxels processed / device time with the stack already resident in HBM.
-* ``e2e``    : same step through the drop-in host API (muscle_fish.find_spots_snrfilter +
-               ndimage.spot_distances) with pinned HOST buffers in, host results out.
-* N > 1      : one process per GPU (torchrun), independent stacks per rank, no data-path
-               collective (the reference's batch_process.py model) -> "scaling": "weak".
+* ``e2e``    : the same step from HOST buffers through the drop-in host API
+               (muscle_fish.find_spots_snrfilter_with_distances: pinned float32 (x,y,z) image + uint8
+               masks in, host float64 spots / table / distances out), H2D and D2H inside the timed region.
+               ``e2e_variants`` holds the other ways a caller can hand the data over: the two
+               reference-signature calls one after the other, raw uint16 counts, and what
+               general_pipeline/fish_analysis.py:196-199 actually passes (pageable float64 + int64 masks).
+* ``batch``  : BASELINE configs[2] -- 64 stacks of config-1 geometry through parallel.run_batch, every
+               N-th stack per rank, double-buffered pinned staging (host buffers in, host results out).
+* ``slab``   : (N > 1) BASELINE configs[3] -- one mosaic 16384x2048x200 split into z-slabs
+               (parallel.slab_analyze: NCCL halo exchange, all-to-all before the EDT's z pass), strong
+               scaling, plus a check of a quarter mosaic against a single-GPU run of the same data.
+* N > 1      : one process per GPU (torchrun); ``value`` / ``e2e`` run independent stacks per rank, no
+               data-path collective (the reference's batch_process.py model) -> "scaling": "weak".
 * ``--impl reference``: the reference's CPU arithmetic (oracle: scipy.ndimage float64) on the
-               box's host cores, one stack per worker process.
+               box's host cores, one bounded sample stack per worker process.
 """
 from __future__ import annotations
 
 import argparse
+import contextlib
+import io
 import json
 import os
 import sys
@@ -44,13 +55,22 @@ WORKLOADS = {
     "C1": ((1024, 1024, 60), 5000, 30, 1234, "configs[0]: 1024x1024x60 stack, 5k spots, 30 nuclei"),
     "small": ((256, 192, 40), 300, 6, 11, "debug stack 256x192x40"),
 }
+MOSAIC = ((16384, 2048, 200), 640000, 4000, 4)  # configs[3]
 
 # algorithmic bytes per voxel of each kernel (fp32 volumes, u8 masks)
 ALGO_BYTES = {
     "minmax": 4, "conv_y_gd": 12, "conv_z_mid": 16, "conv_x_last": 12, "nms_compact": 4,
-    "masked_quantile_3pass": 15, "masked_quantile_bracketed": 5, "masked_quantile_minmax": 5, "edt_scan_y": 3, "edt_envelope_x": 8, "edt_envelope_z": 10,
-    "ingest_xyz": 8, "ingest_flat": 8,
+    "masked_quantile_3pass": 15, "masked_quantile_bracketed": 5, "masked_quantile_minmax": 5, "edt_scan_y": 3,
+    "edt_envelope_x": 8, "edt_envelope_z": 10, "ingest_xyz": 8, "ingest_flat": 8,
 }
+
+
+def workload_config(name):
+    """The ``config`` object of the JSON line -- identical for both arms."""
+    shape, n_spots, n_nuc, _, desc = WORKLOADS[name]
+    return {"workload": desc, "shape_xyz": list(shape), "spots": n_spots, "nuclei": n_nuc, "sigma": SIGMA,
+            "t_spot": T_SPOT, "sampling_um": list(SAMPLING), "stacks_per_gpu": 1,
+            "l2": "inputs (1.7 GB/stack at C2) larger than the 126 MB L2; no explicit flush"}
 
 
 _JSON_FD = None
@@ -168,19 +188,20 @@ def _sample_geometry(workload, sample_xy):
     return (sx, sy, shape[2]), max(8, int(round(n_spots * frac))), max(1, int(round(n_nuc * frac))), seed
 
 
-def cpu_baseline_single(workload, sample_xy=448):
-    """oracle, 1 process / 1 thread, on a crop-sized sample of the workload (same density)."""
+def cpu_baseline_single(workload="C1"):
+    """The oracle (scipy float64, what the reference's libraries compute), 1 process / 1 thread, on the whole
+    configs[0] stack -- the CPU-runnable case BASELINE.md section 4 plans the CPU arm on."""
     import muscle_fish_b200  # noqa: F401
     from muscle_fish_b200 import synth
-    shape, n_spots, n_nuc, seed = _sample_geometry(workload, sample_xy)
+    shape, n_spots, n_nuc, seed, desc = WORKLOADS[workload]
     st = synth.make_stack(shape=shape, n_spots=n_spots, n_nuclei=n_nuc, seed=seed)
     t0 = time.perf_counter()
-    _cpu_pipeline(st)
+    found, _ = _cpu_pipeline(st)
     dt = time.perf_counter() - t0
     nvox = float(np.prod(shape))
     return {"value": nvox / dt / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"{shape[0]}x{shape[1]}x{shape[2]} stack at the workload's spot/nucleus density, "
-                      f"{n_spots} spots, {n_nuc} nuclei, {dt:.1f} s of scipy float64 on one core"}
+            "sample": f"{desc}: the whole {shape[0]}x{shape[1]}x{shape[2]} stack once, {found} spots kept, "
+                      f"{dt:.1f} s of scipy.ndimage float64 on one core (spot path + EDT + gather)"}
 
 
 def run_reference(args):
@@ -202,14 +223,15 @@ def run_reference(args):
         dt = time.perf_counter() - t0
     nvox = float(np.prod(shape)) * workers * args.steps
     value = nvox / dt / 1e9
-    sample = (f"each step: {workers} worker processes x one {shape[0]}x{shape[1]}x{shape[2]} stack "
-              f"({n_spots} spots, {n_nuc} nuclei; the workload's density), oracle = scipy.ndimage float64")
+    sample = (f"each step: {workers} worker processes (the reference's only parallel mode is one image per "
+              f"process, general_pipeline/batch_process.py) x one {shape[0]}x{shape[1]}x{shape[2]} crop-sized stack "
+              f"at the workload's spot / nucleus density ({n_spots} spots, {n_nuc} nuclei); oracle = "
+              f"scipy.ndimage float64; throughput is per voxel")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload][4], "sigma": SIGMA, "t_spot": T_SPOT,
-                   "sampling_um": SAMPLING, "sample": sample},
+        "config": workload_config(args.workload),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -218,20 +240,266 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------- GPU side
-def run_ours(args):
+class _Ctx:
+    """rank / world / collectives of one bench process"""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, v):
+        t = self.torch.tensor([float(v)], dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(self, fn, steps, warmup):
+        """wall clock of `steps` calls, barrier + synchronize on both sides, max over ranks (seconds)"""
+        out = None
+        for _ in range(warmup):
+            out = fn()
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            out = fn()
+        self.barrier()
+        return self.max_over_ranks(time.perf_counter() - t0), out
+
+
+def _quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def bench_e2e(ctx, args, img, fiber, nuc, shape, nvox):
+    """host buffers in, host results out.  Returns (e2e object, variants)"""
+    import torch
+    from muscle_fish_b200 import muscle_fish as mf, ndimage as nd
+    h_img = torch.empty(shape, dtype=torch.float32).pin_memory()
+    h_fib = torch.empty(shape, dtype=torch.uint8).pin_memory()
+    h_nuc = torch.empty(shape, dtype=torch.uint8).pin_memory()
+    h_img.copy_(img.permute(1, 2, 0))
+    h_fib.copy_(fiber.permute(1, 2, 0))
+    h_nuc.copy_(nuc.permute(1, 2, 0))
+    torch.cuda.synchronize()
+    a_img, a_fib, a_nuc = h_img.numpy(), h_fib.numpy(), h_nuc.numpy()
+
+    def fused(ai=a_img, af=a_fib, an=a_nuc):
+        return _quiet(mf.find_spots_snrfilter_with_distances, ai, an, SAMPLING, sigma=SIGMA, t_spot=T_SPOT, mask=af)
+
+    def two_calls():
+        spots, data = _quiet(mf.find_spots_snrfilter, a_img, sigma=SIGMA, t_spot=T_SPOT, mask=a_fib)
+        return spots, data, nd.spot_distances(a_nuc, spots, SAMPLING)
+
+    def d2h_bytes(res):
+        spots, data, d = res
+        return int(spots.size * 8 + d.size * 8 + (len(data) - 1) * 6 * 8)
+
+    steps = max(1, min(args.steps, args.e2e_steps))
+    warm = max(1, min(args.warmup, 3))
+    dt, res = ctx.timed(fused, steps, warm)
+    h2d = int(h_img.numel() * 4 + h_fib.numel() + h_nuc.numel())
+    e2e = {"value": ctx.world * nvox * steps / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h_bytes(res), "steps": steps, "ms_per_step": dt / steps * 1e3,
+           "pcie_floor_ms": h2d / 55e9 * 1e3,
+           "api": "muscle_fish.find_spots_snrfilter_with_distances (= find_spots_snrfilter + the EDT/interpn pair of "
+                  "nocodazole/fish_analysis_noco.py:218-221,297-298 in one call): pinned host float32 (x,y,z) image "
+                  "+ uint8 masks in, host float64 spots / table / distances out"}
+    variants = {}
+    vsteps = max(1, min(steps, 3))
+    dt2, res2 = ctx.timed(two_calls, vsteps, 1)
+    variants["two_reference_calls_f32_pinned"] = {
+        "value": ctx.world * nvox * vsteps / dt2 / 1e9, "ms_per_step": dt2 / vsteps * 1e3, "h2d_bytes_per_step": h2d,
+        "api": "muscle_fish.find_spots_snrfilter, then ndimage.spot_distances (round-1 e2e)",
+        "same_spots_as_fused": bool(np.array_equal(res2[0], res[0]) and np.array_equal(res2[2], res[2]))}
+    if not args.quick:
+        # raw detector counts: uint16 over PCIe, no widening on the host
+        u_img = torch.empty(shape, dtype=torch.uint16).pin_memory()
+        u_img.copy_((img.permute(1, 2, 0) * 16.0).round().clamp(0, 65535).to(torch.uint16))
+        torch.cuda.synchronize()
+        au = u_img.numpy()
+        dt3, res3 = ctx.timed(lambda: fused(au), vsteps, 1)
+        hb = int(u_img.numel() * 2 + h_fib.numel() + h_nuc.numel())
+        variants["uint16_pinned"] = {"value": ctx.world * nvox * vsteps / dt3 / 1e9, "ms_per_step": dt3 / vsteps * 1e3,
+                                     "h2d_bytes_per_step": hb, "pcie_floor_ms": hb / 55e9 * 1e3,
+                                     "found_spots": int(len(res3[0])),
+                                     "api": "same call, the image as uint16 counts (x16 gain, rounded)"}
+        del u_img, au
+        # what general_pipeline/fish_analysis.py:196-199 hands over: pageable float64 (fix_bleaching's output)
+        # and int64 0/1 masks (np.where(..., 1, 0))
+        p_img = a_img.astype(np.float64)
+        p_fib = a_fib.astype(np.int64)
+        p_nuc = a_nuc.astype(np.int64)
+        dt4, res4 = ctx.timed(lambda: fused(p_img, p_fib, p_nuc), 2, 1)
+        hb = int(p_img.nbytes + p_fib.nbytes + p_nuc.nbytes)
+        variants["float64_int64_pageable"] = {
+            "value": ctx.world * nvox * 2 / dt4 / 1e9, "ms_per_step": dt4 / 2 * 1e3, "h2d_bytes_per_step": hb,
+            "same_spots_as_fused": bool(np.array_equal(res4[0], res[0])),
+            "api": "same call, pageable float64 image + int64 masks: the dtypes "
+                   "general_pipeline/fish_analysis.py:196-199 passes"}
+        del p_img, p_fib, p_nuc
+    return e2e, variants
+
+
+def bench_batch(ctx, args):
+    """configs[2]: 64 stacks of configs[0] geometry, one process per GPU taking every N-th stack"""
+    import torch
+    from muscle_fish_b200 import parallel as P, synth
+    shape, n_spots, n_nuc, seed, _ = WORKLOADS["C1" if not args.quick else "small"]
+    n_stacks = args.batch_stacks
+    pool = []
+    for k in range(4):  # four distinct stacks in pinned host memory stand for the image files
+        st = synth.make_stack_device(shape, n_spots, n_nuc, 1000 + k, z_first=False)
+        u = (st["img"] * 16.0).round().clamp(0, 65535).to(torch.uint16)
+        pool.append(tuple(t.cpu().pin_memory() for t in (u, st["fiber_mask"], st["nuc_mask"])))
+        del st, u
+    torch.cuda.synchronize()
+
+    def loader(i, img, fiber, nuc):  # "reading file i": the pinned pool buffer is handed over as it is
+        a, b, c = pool[i % len(pool)]
+        return a, b, c
+
+    found = []
+
+    def once():
+        found.clear()
+        res = P.run_batch(n_stacks, loader, shape, torch.uint16, SIGMA, T_SPOT, SAMPLING, rank=ctx.rank,
+                          world=ctx.world)
+        found.extend(len(r["spots"]) for _, r in res)
+        return res
+
+    dt, res = ctx.timed(once, 1, 1)
+    nvox = float(np.prod(shape))
+    per_stack = int(nvox) * 4
+    return {"workload": f"configs[2]: {n_stacks} stacks {shape[0]}x{shape[1]}x{shape[2]} (uint16 image + two uint8 masks "
+                        f"per stack in pinned host memory), every {ctx.world}-th stack per GPU, parallel.run_batch",
+            "n_stacks": n_stacks, "stacks_this_rank": len(res), "value": n_stacks * nvox / dt / 1e9, "unit": UNIT,
+            "ms_total": dt * 1e3, "ms_per_stack_per_gpu": dt * 1e3 / max(1, len(res)),
+            "h2d_bytes_per_stack": per_stack, "pcie_floor_ms_per_stack": per_stack / 55e9 * 1e3,
+            "spots_first_stack": found[0] if found else None, "scaling": "strong (fixed batch)"}
+
+
+def _mosaic_for(world, quick):
+    (X, Y, Z), ns, nn, seed = MOSAIC
+    if quick:
+        return (1024, 512, 64), 2500, 16, seed
+    # ~63 bytes of device memory per voxel per rank (extended slab, LoG scratch, EDT workspace, re-partition
+    # buffers): keep a rank below ~150 GB of the 180 GB
+    while X * Y * Z / world * 63 > 150e9 and X > 2048:
+        X //= 2
+        ns //= 2
+        nn //= 2
+    return (X, Y, Z), ns, nn, seed
+
+
+def bench_slab(ctx, args):
+    """configs[3]: z-slab decomposed mosaic through parallel.slab_analyze (strong scaling), its phases, and a
+    correctness check of the slab path against one GPU on a mosaic that fits one GPU"""
     import torch
     import torch.distributed as dist
+    from muscle_fish_b200 import device as D, parallel as P, synth
+    world, rank = ctx.world, ctx.rank
+    edt_group = dist.new_group()
+    out = {}
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    def slabs(shape, ns, nn, seed):
+        X, Y, Z = shape
+        lay = P.SlabLayout(Z, X, Y)
+        st = synth.make_stack_device(shape, ns, nn, seed, z_range=(lay.z0, lay.z1))
+        notnuc = (st["nuc_mask"] == 0).to(torch.uint8)
+        return lay, st["img"], st["fiber_mask"], notnuc
+
+    # -- 1. same result as one GPU (a quarter-length mosaic fits one B200)
+    cshape, cns, cnn, cseed = ((4096, 2048, 200), 160000, 1000, 4) if not args.quick else ((512, 256, 48), 600, 8, 4)
+    lay, img, fib, notnuc = slabs(cshape, cns, cnn, cseed)
+    res = P.slab_analyze(img, fib, notnuc, lay, sigma=SIGMA, t_spot=T_SPOT, sampling_xyz=SAMPLING,
+                         edt_group=edt_group)
+    del img, fib, notnuc
+    P.clear_buffers()
+    D.WS.clear()
+    torch.cuda.empty_cache()
+    verdict = torch.zeros(4, dtype=torch.float64, device="cuda")
+    if rank == 0:
+        st = synth.make_stack_device(cshape, cns, cnn, cseed)
+        nn1 = (st["nuc_mask"] == 0).to(torch.uint8)
+        one = D.analyze_stack(st["img"], st["fiber_mask"], nn1, SIGMA, T_SPOT, SAMPLING)
+        same_spots = np.array_equal(one["spots"], res["spots"])
+        same_dist = same_spots and np.array_equal(one["spot_dist"], res["spot_dist"])
+        verdict[:] = torch.tensor([float(same_spots), float(same_dist), len(one["spots"]), len(res["spots"])])
+        del st, nn1, one
+        D.WS.clear()
+        torch.cuda.empty_cache()
+    dist.broadcast(verdict, 0)
+    v = verdict.tolist()
+    out["matches_n1"] = {"mosaic": list(cshape), "spots_identical": bool(v[0]), "distances_identical": bool(v[1]),
+                         "spots_one_gpu": int(v[2]), "spots_slabs": int(v[3]),
+                         "how": "spot list (coordinates, order) and per-spot distances of parallel.slab_analyze on "
+                                f"{world} ranks == device.analyze_stack on rank 0 over the same voxels, bit for bit"}
+    ctx.barrier()
+
+    # -- 2. timing on the mosaic itself
+    shape, ns, nn, seed = _mosaic_for(world, args.quick)
+    X, Y, Z = shape
+    lay, img, fib, notnuc = slabs(shape, ns, nn, seed)
+    nvox = float(X) * Y * Z
+
+    def step():
+        return P.slab_analyze(img, fib, notnuc, lay, sigma=SIGMA, t_spot=T_SPOT, sampling_xyz=SAMPLING,
+                              edt_group=edt_group, full_table=False)
+
+    steps = max(1, min(args.steps, args.slab_steps))
+    dt, res = ctx.timed(step, steps, 2)
+    ms = dt / steps * 1e3
+    # one more step with per-phase wall clocks (synchronising: the chains run one after the other)
+    P.PHASES = {}
+    P.slab_analyze(img, fib, notnuc, lay, sigma=SIGMA, t_spot=T_SPOT, sampling_xyz=SAMPLING, full_table=False)
+    phases = {k: round(v * 1e3, 3) for k, v in P.PHASES.items()}
+    P.PHASES = None
+    radius = 8
+    halo_bytes = 2 * (radius + 1) * X * Y * 4  # received by an interior rank
+    a2a_bytes = (Z / world) * X * Y * 4 * (world - 1) / world  # sent by every rank
+    out.update({
+        "workload": f"configs[3]: mosaic {X}x{Y}x{Z} in {world} z-slabs, parallel.slab_analyze (spot path + EDT + "
+                    f"per-spot distances), device-resident slabs",
+        "mosaic": [X, Y, Z], "n_gpus": world, "ms_per_step": ms, "value": nvox / ms / 1e6, "unit": UNIT,
+        "steps": steps, "found_spots": int(len(res["spots"])), "scaling": "strong",
+        "phases_ms_serialised": phases,
+        "nvlink": {
+            "halo_bytes_in_per_rank": int(halo_bytes),
+            "halo_gbs": halo_bytes / max(phases.get("halo", 0.0), 1e-9) / 1e6 if "halo" in phases else None,
+            "all_to_all_bytes_out_per_rank": int(a2a_bytes),
+            "all_to_all_gbs": a2a_bytes / max(phases.get("edt_all_to_all", 0.0), 1e-9) / 1e6
+            if "edt_all_to_all" in phases else None,
+            "peer_copy_reference_gbs": 770.0},
+        "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9,
+    })
+    del img, fib, notnuc
+    P.clear_buffers()
+    D.WS.clear()
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_ours(args):
+    ctx = _Ctx()
+    torch, dist = ctx.torch, ctx.dist
+    rank, world, local = ctx.rank, ctx.world, ctx.local
 
     import muscle_fish_b200  # noqa: F401
-    from muscle_fish_b200 import _lib, device as D, synth
-    from muscle_fish_b200 import muscle_fish as mf, ndimage as nd
+    from muscle_fish_b200 import _lib, device as D, parallel as P, synth
+    P.bind_to_gpu_numa(local)
 
     shape, n_spots, n_nuc, seed, desc = WORKLOADS[args.workload]
     nvox = float(np.prod(shape))
@@ -240,11 +508,6 @@ def run_ours(args):
     notnuc = (nuc == 0).to(torch.uint8)  # bench input preparation (not timed)
     torch.cuda.synchronize()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     def step():
         return D.analyze_stack(img, fiber, notnuc, SIGMA, T_SPOT, SAMPLING)
 
@@ -252,7 +515,7 @@ def run_ours(args):
     res = None
     for _ in range(args.warmup):
         res = step()
-    barrier()
+    ctx.barrier()
     sampler = ClockSampler(local)
     sampler.start()
     _lib.profile_enable(True)
@@ -263,54 +526,27 @@ def run_ours(args):
     for _ in range(args.steps):
         res = step()
     e1.record()
-    barrier()
+    ctx.barrier()
     launches = _lib.launch_count() - n0
     kern = _lib.profile_collect()
     _lib.profile_enable(False)
     clocks = sampler.stop()
-    ms_total = e0.elapsed_time(e1)
-    tmax = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ms_step = float(tmax.item()) / args.steps
+    ms_step = ctx.max_over_ranks(e0.elapsed_time(e1)) / args.steps
     value = world * nvox / (ms_step * 1e-3) / 1e9
+    found = int(len(res["spots"]))
 
-    # ---- end to end through the drop-in host API, pinned host buffers
-    h_img = torch.empty(shape, dtype=torch.float32).pin_memory()
-    h_fib = torch.empty(shape, dtype=torch.uint8).pin_memory()
-    h_nuc = torch.empty(shape, dtype=torch.uint8).pin_memory()
-    h_img.copy_(img.permute(1, 2, 0))
-    h_fib.copy_(fiber.permute(1, 2, 0))
-    h_nuc.copy_(nuc.permute(1, 2, 0))
-    torch.cuda.synchronize()
-    a_img, a_fib, a_nuc = h_img.numpy(), h_fib.numpy(), h_nuc.numpy()
-    del st
+    # ---- end to end through the drop-in host API
+    D.WS.clear()
+    torch.cuda.empty_cache()
+    e2e, variants = bench_e2e(ctx, args, img, fiber, nuc, shape, nvox)
+    del st, img, fiber, nuc, notnuc
     D.WS.clear()
     torch.cuda.empty_cache()
 
-    def step_e2e():
-        import contextlib
-        import io
-        with contextlib.redirect_stdout(io.StringIO()):
-            spots, _ = mf.find_spots_snrfilter(a_img, sigma=SIGMA, t_spot=T_SPOT, mask=a_fib)
-        d = nd.spot_distances(a_nuc, spots, SAMPLING)
-        return spots, d
-
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    for _ in range(max(1, min(args.warmup, 3))):
-        spots_e, d_e = step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        spots_e, d_e = step_e2e()
-    barrier()
-    dt = time.perf_counter() - t0
-    tm = torch.tensor([dt], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    e2e_value = world * nvox * e2e_steps / float(tm.item()) / 1e9
-    h2d = int(h_img.numel() * 4 + h_fib.numel() + h_nuc.numel())
-    d2h = int(spots_e.size * 8 + d_e.size * 8 + len(spots_e) * 16)
+    batch = bench_batch(ctx, args) if not args.no_batch else None
+    D.WS.clear()
+    torch.cuda.empty_cache()
+    slab = bench_slab(ctx, args) if (world > 1 and not args.no_slab) else None
 
     if rank != 0:
         if world > 1:
@@ -337,23 +573,14 @@ def run_ours(args):
                 "frac": kernels[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": ALGO_BYTES[dom] * nvox,
                 "share_of_step": share[dom] / ms_step}
-    cpu = cpu_baseline_single(args.workload) if (world == 1 and not args.no_cpu_baseline) else None
+    cpu = cpu_baseline_single("C1" if not args.quick else "small") if (world == 1 and not args.no_cpu_baseline) else None
+    cfg = workload_config(args.workload)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
-        "config": {"workload": desc, "shape_xyz": list(shape), "spots": n_spots, "nuclei": n_nuc, "sigma": SIGMA,
-                   "t_spot": T_SPOT, "sampling_um": list(SAMPLING), "stacks_per_gpu": 1,
-                   "l2": "inputs (1.7 GB/stack at C2) larger than the 126 MB L2; no explicit flush",
-                   "found_spots": int(len(res["spots"]))},
-        "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "api": "muscle_fish.find_spots_snrfilter + ndimage.spot_distances, pinned host "
-                                           "numpy (x,y,z) in, host float64 out"},
-        "gpu_launches": int(launches),
-        "roofline": roofline,
-        "kernels": kernels,
-        "cpu_baseline": cpu,
+        "data": "synthetic", "config": cfg, "found_spots": found, "clocks": clocks, "e2e": e2e,
+        "e2e_variants": variants, "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels,
+        "cpu_baseline": cpu, "batch": batch, "slab": slab,
     }
     _emit(line)
     if world > 1:
@@ -368,7 +595,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--slab-steps", type=int, default=5)
+    ap.add_argument("--batch-stacks", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-batch", action="store_true")
+    ap.add_argument("--no-slab", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="small shapes for the batch / slab parts, no e2e variants "
+                                                         "(debugging the harness)")
     ap.add_argument("--ref-sample", type=int, default=320, help="x/y edge of the per-worker CPU sample stack")
     ap.add_argument("--ref-workers", type=int, default=0)
     args = ap.parse_args()

@@ -166,6 +166,7 @@ def ingest(src, z_first=False, as_mask=False, want_minmax=True, negate=False, re
     t = host_to_device(src)
     if ready is not None:
         torch.cuda.current_stream().wait_event(ready)
+        t.record_stream(torch.cuda.current_stream())  # allocated by the copy's caller, consumed here
     if t.dim() != 3:
         raise ValueError("expected a 3-D volume, got shape %r" % (tuple(t.shape),))
     if t.dtype == torch.bool:
@@ -202,6 +203,48 @@ def ingest_as_float(src):
     elif dt.kind == "i":
         raise NotImplementedError("signed integer images: convert with skimage.util.img_as_float first")
     return vol
+
+
+class Handoff:
+    """Device-resident hand-off between the reference's consecutive calls.
+
+    ``su.normalize_image`` -> ``mf.fix_bleaching`` -> ``mf.find_spots_snrfilter``
+    (general_pipeline/fish_analysis.py:132-142,196-199) pass the SAME float64 volume from one call to the
+    next through host memory: 8 bytes per voxel up and down PCIe at every step.  The functions here return
+    real host float64 arrays (the scripts index, clip and plot them), but remember, per returned array,
+    the device volume that holds exactly what ``ingest(array)`` would produce; when that very array object
+    comes back as an argument the upload is skipped.  To keep the pairing sound the returned arrays are
+    read-only (a script that wants to edit one takes a ``.copy()``, which is then uploaded like any other
+    array); the entry dies with the array.  ``MFISH_HANDOFF=0`` switches the mechanism off."""
+
+    def __init__(self):
+        self._entries = {}
+        self.enabled = os.environ.get("MFISH_HANDOFF", "1") != "0"
+        self.hits = 0
+
+    def register(self, arr: np.ndarray, vol: "Volume", z_first: bool):
+        if not self.enabled or not isinstance(arr, np.ndarray) or arr.ndim != 3:
+            return arr
+        import weakref
+        arr.flags.writeable = False
+        key = id(arr)
+        self._entries[key] = (weakref.ref(arr, lambda _r, k=key: self._entries.pop(k, None)), vol, bool(z_first))
+        return arr
+
+    def lookup(self, arr, z_first: bool):
+        if not self.enabled or not isinstance(arr, np.ndarray):
+            return None
+        e = self._entries.get(id(arr))
+        if e is None or e[0]() is not arr or arr.flags.writeable or e[2] != bool(z_first):
+            return None
+        self.hits += 1
+        return e[1]
+
+    def clear(self):
+        self._entries.clear()
+
+
+HANDOFF = Handoff()
 
 
 def minmax(vol: torch.Tensor) -> torch.Tensor:
@@ -740,33 +783,20 @@ class _NoTimer:
         return fn(*a, **k)
 
 
-def analyze_stack(img_zxy: torch.Tensor, fiber_zxy: torch.Tensor, notnuc_zxy: torch.Tensor, sigma=2.0,
-                  t_spot=0.025, sampling_xyz=(1.0, 1.0, 1.0), snr=None, timer=None):
-    """The whole hot path on device-resident inputs (general_pipeline/fish_analysis.py:199 +
-    nocodazole/fish_analysis_noco.py:218-221,297-298): normalise -> LoG -> NMS -> prune -> mask ->
-    P25 baseline -> blur at spots -> SNR filter, then EDT of the NOT-nucleus mask and the per-spot
-    distance gather.  ``img_zxy`` float32 [nz,nx,ny]; masks uint8.  Returns a dict of host arrays."""
-    t = timer or _NoTimer()
-    nz, nx, ny = img_zxy.shape
+def _spot_list_tail(vol, fiber_zxy, peaks, baseline_f, sigma, snr, dist_ready, t, fiber_ready=None):
+    """Second half of the hot path, shared by the device-resident and the host-buffer entry: wait for the
+    peak count, then rank / prune / mask filter / blur at the spots / SNR cut on the high-priority stream,
+    and gather the distance map (``dist_ready()`` -> float32 [nz,nx,ny], valid on the main stream)."""
+    nz, nx, ny = vol.data.shape
     dims = (1, nx, ny, nz)
-    # everything that does not depend on the spot list is queued first, so the host round trips of
-    # the list handling (count, D2H, decode) overlap the remaining device work
-    # normalize_image's bounds come out of the baseline percentile's pass over the voxels
-    vol, baseline_f = t.run("quantile_minmax", masked_percentile_minmax_async, img_zxy, fiber_zxy, 25)
-    log = WS.get("log_out", img_zxy.shape, torch.float32, img_zxy.device)
-    _, peaks = t.run("log3d_nms", log_peaks_async, vol, sigma, t_spot, log)
-    # the distance transform runs on a side stream, after the streaming kernels above, so that the
-    # small kernels and host round trips of the spot-list handling proceed while it runs
     main = torch.cuda.current_stream()
-    side = _side_stream()
-    side.wait_stream(main)
-    with torch.cuda.stream(side):
-        dist = t.run("edt", edt, notnuc_zxy, sampling_xyz)
     idx, val = peaks()
     spots = np.empty((0, 4))
     hp = _list_stream() if os.environ.get("MFISH_LIST_PRIO", "1") != "0" else main
     hp.wait_stream(main)
     with torch.cuda.stream(hp):
+        if fiber_ready is not None:
+            fiber_zxy = fiber_ready()
         if idx.numel():
             cutoff = max(T.prune_cutoff_sq(float(sigma), None, 0.5), 0)
             idx_r, _, alive = t.run("rank_prune", rank_prune_equal, idx, val, dims, cutoff)
@@ -782,8 +812,79 @@ def analyze_stack(img_zxy: torch.Tensor, fiber_zxy: torch.Tensor, notnuc_zxy: to
         thresh = np.percentile(inten, 90) / (baseline * np.sqrt(10))
         snr = max(thresh, np.sqrt(10))
     keep = (inten / baseline > snr) if len(spots) else np.zeros(0, bool)
-    main.wait_stream(side)
-    dist.record_stream(main)
+    dist = dist_ready()
     spot_dist = gather(dist, spots[keep]).astype(np.float64) if keep.any() else np.empty(0)
     return {"spots": spots[keep], "spots_masked": spots, "intensity": inten, "baseline": baseline, "snr": snr,
             "spot_dist": spot_dist, "dist": dist}
+
+
+def analyze_stack(img_zxy: torch.Tensor, fiber_zxy: torch.Tensor, notnuc_zxy: torch.Tensor, sigma=2.0,
+                  t_spot=0.025, sampling_xyz=(1.0, 1.0, 1.0), snr=None, timer=None):
+    """The whole hot path on device-resident inputs (general_pipeline/fish_analysis.py:199 +
+    nocodazole/fish_analysis_noco.py:218-221,297-298): normalise -> LoG -> NMS -> prune -> mask ->
+    P25 baseline -> blur at spots -> SNR filter, then EDT of the NOT-nucleus mask and the per-spot
+    distance gather.  ``img_zxy`` float32 [nz,nx,ny]; masks uint8.  Returns a dict of host arrays."""
+    t = timer or _NoTimer()
+    # everything that does not depend on the spot list is queued first, so the host round trips of
+    # the list handling (count, D2H, decode) overlap the remaining device work
+    # normalize_image's bounds come out of the baseline percentile's pass over the voxels
+    vol, baseline_f = t.run("quantile_minmax", masked_percentile_minmax_async, img_zxy, fiber_zxy, 25)
+    log = WS.get("log_out", img_zxy.shape, torch.float32, img_zxy.device)
+    _, peaks = t.run("log3d_nms", log_peaks_async, vol, sigma, t_spot, log)
+    # the distance transform runs on a side stream, after the streaming kernels above, so that the
+    # small kernels and host round trips of the spot-list handling proceed while it runs
+    main = torch.cuda.current_stream()
+    side = _side_stream()
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        dist = t.run("edt", edt, notnuc_zxy, sampling_xyz)
+
+    def dist_ready():
+        main.wait_stream(side)
+        dist.record_stream(main)
+        return dist
+
+    return _spot_list_tail(vol, fiber_zxy, peaks, baseline_f, sigma, snr, dist_ready, t)
+
+
+def analyze_host(img_fish, fiber_mask, region_nuc, sigma=2.0, t_spot=0.025, sampling_xyz=(1.0, 1.0, 1.0), snr=None,
+                 z_first=False, timer=None):
+    """The same path from HOST arrays in the reference's (x, y, z) order (any dtype: uint16 stacks go over
+    PCIe as 2 bytes per voxel), arranged so that PCIe -- the slow link -- never waits for the GPU and the
+    GPU's work after the last byte is as short as possible:
+
+      copy stream :  nucleus mask | image ............................ | fibre mask |
+      side stream :               | ingest + EDT (3 passes)            |
+      main stream :                                  ingest(+min/max), LoG + NMS    | P25, list handling
+
+    ``region_nuc`` is the nucleus mask itself (the NOT is taken on ingest, nocodazole/fish_analysis_noco.py:218).
+    Returns the dict of ``analyze_stack``."""
+    t = timer or _NoTimer()
+    (tn, en), (ti, ei), (tf, ef) = host_to_device_many([region_nuc, img_fish, fiber_mask])
+    main = torch.cuda.current_stream()
+    side = _side_stream()
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        notnuc = ingest(tn, z_first=z_first, as_mask=True, negate=True, ready=en)
+        dist = t.run("edt", edt, notnuc, sampling_xyz)
+    vol = ingest(ti, z_first=z_first, want_minmax=True, ready=ei)
+    log = WS.get("log_out", vol.data.shape, torch.float32, vol.data.device)
+    _, peaks = t.run("log3d_nms", log_peaks_async, vol, sigma, t_spot, log)
+    state = {}
+
+    def fiber_ready():  # on the list stream, after the peak count has been read
+        state["fiber"] = ingest(tf, z_first=z_first, as_mask=True, ready=ef)
+        if tuple(state["fiber"].shape) != tuple(vol.data.shape):
+            raise IndexError("mask and image shapes differ")
+        state["baseline"] = masked_percentile_async(vol, state["fiber"], 25)
+        return state["fiber"]
+
+    def baseline_f():
+        return state["baseline"]()
+
+    def dist_ready():
+        main.wait_stream(side)
+        dist.record_stream(main)
+        return dist
+
+    return _spot_list_tail(vol, None, peaks, baseline_f, sigma, snr, dist_ready, t, fiber_ready=fiber_ready)

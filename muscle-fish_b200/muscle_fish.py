@@ -36,8 +36,12 @@ class _Lazy:
 
 
 def _prep(img_fish, mask, z_first):
-    (ti, ei), (tm, em) = D.host_to_device_many([img_fish, mask])
-    vol = D.ingest(ti, z_first=z_first, ready=ei)
+    vol = D.HANDOFF.lookup(img_fish, z_first)  # an array this package returned: already on the device
+    if vol is not None:
+        (tm, em), = D.host_to_device_many([mask])
+    else:
+        (ti, ei), (tm, em) = D.host_to_device_many([img_fish, mask])
+        vol = D.ingest(ti, z_first=z_first, ready=ei)
     m = _Lazy(tm, em, z_first, vol.data.shape) if mask is not None else None
     return vol, m
 
@@ -99,6 +103,13 @@ def find_spots_snrfilter(img_fish, snr=None, sigma=1., t_spot=0.025, mask=None, 
     spot_int = D.blur_at_points(vol, spots_masked, (3, 3, 0.3), mode="nearest")
     baseline = pending["baseline"]()
 
+    spots_filtered, spot_data, _ = _snr_outputs(spots_masked, spot_int, baseline, snr, z_first)
+    return _nonempty(spots_filtered), spot_data
+
+
+def _snr_outputs(spots_masked, spot_int, baseline, snr, z_first):
+    """modules/muscle_fish.py:367-402: automatic SNR threshold, its print, the filtered spots, the
+    per-spot table of ALL mask-passing spots -- and which of them were kept."""
     if snr is None:
         thresh = np.percentile(spot_int, 90) / (baseline * np.sqrt(10))
         snr_min = np.sqrt(10)
@@ -108,14 +119,37 @@ def find_spots_snrfilter(img_fish, snr=None, sigma=1., t_spot=0.025, mask=None, 
 
     # the reference's per-spot loop (modules/muscle_fish.py:382-400), vectorised
     ratio = spot_int / baseline
-    spots_filtered = spots_masked[ratio > snr]
+    keep = ratio > snr
+    spots_filtered = spots_masked[keep]
     if z_first:
         spots_filtered = spots_filtered[:, [2, 0, 1, 3]]
     spot_data = np.column_stack([np.zeros(len(spot_int)), spots_masked[:, 0:3], spot_int, ratio]).tolist()
     for c, r in enumerate(spot_data):
         r[0] = c  # integer spot id, as the reference's enumerate()
     spot_data.insert(0, ['spot_id', 'x', 'y', 'z', 'intensity', 'SNR'])
-    return _nonempty(spots_filtered), spot_data
+    return spots_filtered, spot_data, keep
+
+
+def find_spots_snrfilter_with_distances(img_fish, region_nuc, dims_xyz, snr=None, sigma=1., t_spot=0.025, mask=None,
+                                        z_first=False, draw=False, imgprefix='fiber'):
+    """``find_spots_snrfilter(img_fish, snr, sigma, t_spot, mask, z_first)`` AND the distance of every
+    kept spot to the nearest nucleus voxel -- the ``distance_transform_edt(np.logical_not(region_nuc),
+    sampling=dims_xyz)`` + ``interpn`` pair of nocodazole/fish_analysis_noco.py:218-221,297-298 -- from one
+    call, so that the three uploads are queued back to back and the distance transform runs while the
+    image is still crossing PCIe (``device.analyze_host``).  Returns ``(spots, spot_data, distances)``:
+    the first two exactly as ``find_spots_snrfilter`` returns them, ``distances`` float64 per kept spot."""
+    if mask is None:
+        raise IndexError("find_spots_snrfilter needs a mask: percentile of an empty selection")
+    from .ndimage import _sampling3
+    # every mask-passing spot comes back with its distance (snr = -inf keeps all); the SNR rule is applied
+    # here, with the reference's own arithmetic
+    res = D.analyze_host(img_fish, mask, region_nuc, sigma=sigma, t_spot=t_spot, sampling_xyz=_sampling3(dims_xyz),
+                         snr=-np.inf, z_first=z_first)
+    if len(res["spots_masked"]) == 0:
+        return _row_stack([]), None, np.empty(0)
+    spots_filtered, spot_data, keep = _snr_outputs(res["spots_masked"], res["intensity"], res["baseline"], snr,
+                                                   z_first)
+    return _nonempty(spots_filtered), spot_data, res["spot_dist"][keep]
 
 
 def fix_bleaching(img, second_half=True, mask=None, z_first=False, draw=False, imgprefix='fiber'):
@@ -127,7 +161,7 @@ def fix_bleaching(img, second_half=True, mask=None, z_first=False, draw=False, i
         return A * np.exp(k * x)
 
     img = np.asarray(img)
-    vol = D.ingest(img, z_first=z_first, want_minmax=False)
+    vol = D.HANDOFF.lookup(img, z_first) or D.ingest(img, z_first=z_first, want_minmax=False)
     m = D.ingest(mask, z_first=z_first, as_mask=True) if mask is not None else None
     nz = vol.data.shape[0]
     start_frame = nz // 2 if second_half else 0
@@ -148,4 +182,5 @@ def fix_bleaching(img, second_half=True, mask=None, z_first=False, draw=False, i
         return img
     correction = np.array([expo_fit(z, 1, -1. * e_params[1]) for z in range(nz)])
     out = D.scale_planes(vol.data, correction)
-    return D.export_f64(out, z_first=z_first).cpu().numpy()
+    res = D.export_f64(out, z_first=z_first).cpu().numpy()
+    return D.HANDOFF.register(res, D.Volume(out, D.minmax(out)), z_first)

@@ -87,6 +87,124 @@ def split_bounds(n: int, parts: int):
     return out
 
 
+def bind_to_gpu_numa(device_index: int):
+    """Restrict this process to the CPUs the driver reports as local to its GPU, BEFORE pinned staging
+    buffers are allocated, so that first-touch places them on the GPU's NUMA node.  Best effort: returns
+    the CPU list used, or None when NVML has no affinity information."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1]
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return allowed
+    except Exception:
+        pass
+    return None
+
+
+class _StagingSlot:
+    """One stack's worth of pinned host staging + device landing buffers (reference (x, y, z) order)."""
+
+    def __init__(self, shape_xyz, img_dtype, device):
+        self.img_h = torch.empty(shape_xyz, dtype=img_dtype).pin_memory()
+        self.fib_h = torch.empty(shape_xyz, dtype=torch.uint8).pin_memory()
+        self.nuc_h = torch.empty(shape_xyz, dtype=torch.uint8).pin_memory()
+        self.img_d = torch.empty(shape_xyz, dtype=img_dtype, device=device)
+        self.fib_d = torch.empty(shape_xyz, dtype=torch.uint8, device=device)
+        self.nuc_d = torch.empty(shape_xyz, dtype=torch.uint8, device=device)
+        self.copied = torch.cuda.Event()
+        self.bytes = sum(t.numel() * t.element_size() for t in (self.img_h, self.fib_h, self.nuc_h))
+
+    def host_views(self):
+        return self.img_h.numpy(), self.fib_h.numpy(), self.nuc_h.numpy()
+
+
+def run_batch(n_stacks: int, loader, shape_xyz, img_dtype=torch.uint16, sigma=2.0, t_spot=0.025,
+              sampling_xyz=(1.0, 1.0, 1.0), snr=None, rank=None, world=None, on_result=None):
+    """The batch mode of the reference (general_pipeline/batch_process.py:28-52 writes one job per image; here
+    one process per GPU takes every ``world``-th stack) with the slow link kept busy: two pinned staging
+    slots per GPU, so that while stack i is analysed, stack i+1 crosses PCIe and stack i+2 is being read.
+
+    ``loader(index, img, fiber_mask, nuc_mask)`` fills three pinned host arrays in the reference's (x, y, z)
+    order (``img`` of ``img_dtype`` -- raw uint16 counts need no widening on the host -- masks uint8 0/1), or
+    returns its own three (pinned) buffers instead; it runs in a worker thread and stands for reading one
+    image file.  No collective is involved.
+    Returns ``[(index, result dict of device.analyze_host)]`` for this rank's stacks; ``on_result(index, res)``
+    is called as each stack finishes."""
+    import threading
+    from . import device as D
+    D._require_cuda()
+    rank = (dist.get_rank() if dist.is_initialized() else 0) if rank is None else rank
+    world = (dist.get_world_size() if dist.is_initialized() else 1) if world is None else world
+    mine = shard_stacks(n_stacks, rank, world)
+    if not mine:
+        return []
+    dev = torch.device("cuda", torch.cuda.current_device())
+    slots = [_StagingSlot(tuple(shape_xyz), img_dtype, dev) for _ in range(2)]
+    copy_stream = torch.cuda.Stream()
+    errors = []
+
+    def fill(slot, index):
+        try:
+            slot.copied.synchronize()  # the previous upload out of this slot has left the host buffer
+            ret = loader(index, *slot.host_views())
+            # a loader that already holds the stack in pinned memory returns (img, fiber, nuc) instead of
+            # filling the staging views; those buffers are then uploaded as they are
+            slot.src = (slot.img_h, slot.fib_h, slot.nuc_h) if ret is None else tuple(
+                t if isinstance(t, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(t)) for t in ret)
+        except BaseException as e:  # surfaced in the main thread
+            errors.append(e)
+
+    def start_fill(k):
+        th = threading.Thread(target=fill, args=(slots[k % 2], mine[k]), daemon=True)
+        th.start()
+        return th
+
+    def upload(k):
+        s = slots[k % 2]
+        # the landing buffers of this slot were last read by the analysis of stack k-2 on the compute stream
+        copy_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(copy_stream):
+            img_h, fib_h, nuc_h = s.src
+            s.nuc_d.copy_(nuc_h, non_blocking=True)  # the distance transform starts first
+            s.img_d.copy_(img_h, non_blocking=True)
+            s.fib_d.copy_(fib_h, non_blocking=True)
+            s.copied.record(copy_stream)
+
+    results = []
+    start_fill(0).join()
+    upload(0)
+    pending = start_fill(1) if len(mine) > 1 else None  # thread reading stack k+1
+    for k, index in enumerate(mine):
+        if pending is not None:  # stack k+1 has been read: queue its upload behind stack k's
+            pending.join()
+            pending = None
+            if errors:
+                raise errors[0]
+            upload(k + 1)
+        if k + 2 < len(mine):
+            # stack k+2 goes into the pinned slot stack k is leaving; fill() waits for that DMA itself, so the
+            # read overlaps the analysis of stack k below
+            pending = start_fill(k + 2)
+        s = slots[k % 2]
+        torch.cuda.current_stream().wait_event(s.copied)
+        res = D.analyze_host(s.img_d, s.fib_d, s.nuc_d, sigma=sigma, t_spot=t_spot, sampling_xyz=sampling_xyz,
+                             snr=snr)
+        res.pop("dist", None)  # the dense map stays a per-stack temporary
+        results.append((index, res))
+        if on_result is not None:
+            on_result(index, res)
+    if errors:
+        raise errors[0]
+    return results
+
+
 class SlabLayout:
     """z-slab ownership (filters, NMS) and x-slab ownership (EDT z pass) of a [nz][nx][ny] mosaic."""
 

@@ -18,7 +18,11 @@ def normalize_image(image, vmin=0, vmax=1):
     a = np.asarray(image)
     t = D.host_to_device(a)
     out = D.normalize_f64(t, vmin, vmax)
-    return out.cpu().numpy().reshape(a.shape)
+    res = out.cpu().numpy().reshape(a.shape)
+    if a.ndim == 3 and D.HANDOFF.enabled:
+        # keep what ingest(res) would upload again in the next call of the script (see device.Handoff)
+        D.HANDOFF.register(res, D.ingest(out.reshape(a.shape)), z_first=False)
+    return res
 
 
 def optimize_threshold_blob_log(image, min_sigma=1., max_sigma=50., num_sigma=10, tmin=0., tmax=0.1, num=20,

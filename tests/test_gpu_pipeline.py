@@ -1,0 +1,158 @@
+"""GPU: the host-buffer entries around the hot path -- overlapped uploads (device.analyze_host and the
+fused drop-in call), the device-resident hand-off between the reference's consecutive calls
+(general_pipeline/fish_analysis.py:132-142,196-199) and the stack-per-GPU batch driver
+(general_pipeline/batch_process.py:28-52).  Each is compared with the plain call sequence / the oracle."""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import match_fraction
+
+pytestmark = pytest.mark.gpu
+
+ANISO = (0.0577, 0.0577, 0.5)
+
+
+def _two_calls(st, sigma=2.0, t_spot=0.025, snr=None):
+    from muscle_fish_b200 import muscle_fish as mf, ndimage as nd
+    spots, data = mf.find_spots_snrfilter(st["img"], snr=snr, sigma=sigma, t_spot=t_spot, mask=st["fiber_mask"])
+    return spots, data, nd.spot_distances(st["nuc_mask"], spots, ANISO)
+
+
+@pytest.mark.parametrize("cfg", ["tiny", "small"])
+def test_fused_call_equals_the_two_reference_calls_and_the_oracle(cfg, capsys):
+    from muscle_fish_b200 import muscle_fish as mf, synth
+    st = synth.make_config(cfg)
+    spots, data, dist = _two_calls(st)
+    f_spots, f_data, f_dist = mf.find_spots_snrfilter_with_distances(st["img"], st["nuc_mask"], ANISO, sigma=2.0,
+                                                                     t_spot=0.025, mask=st["fiber_mask"])
+    assert capsys.readouterr().out.count("SNR threshold = ") == 2
+    np.testing.assert_array_equal(f_spots, spots)
+    assert f_data == data
+    np.testing.assert_array_equal(f_dist, dist)
+    ref_spots, _ = oracle.find_spots_snrfilter(st["img"], sigma=2.0, t_spot=0.025, mask=st["fiber_mask"],
+                                               pair_order="sorted")
+    grass = oracle.distance_transform_edt(np.logical_not(st["nuc_mask"]), sampling=ANISO)
+    assert match_fraction(f_spots, ref_spots) >= 0.999
+    np.testing.assert_allclose(f_dist, oracle.edt_gather(grass, f_spots, ANISO), rtol=1e-6)
+    # explicit snr, int64 masks (np.where(..., 1, 0) upstream), z-first stacks
+    a = mf.find_spots_snrfilter_with_distances(st["img"], st["nuc_mask"].astype(np.int64), ANISO, snr=4.0, sigma=2.0,
+                                               t_spot=0.025, mask=st["fiber_mask"].astype(np.int64))
+    b = _two_calls(st, snr=4.0)
+    np.testing.assert_array_equal(a[0], b[0])
+    np.testing.assert_array_equal(a[2], b[2])
+    zf = lambda v: np.ascontiguousarray(v.transpose(2, 0, 1))
+    c = mf.find_spots_snrfilter_with_distances(zf(st["img"]), zf(st["nuc_mask"]), ANISO, snr=4.0, sigma=2.0,
+                                               t_spot=0.025, mask=zf(st["fiber_mask"]), z_first=True)
+    np.testing.assert_array_equal(c[0], b[0][:, [2, 0, 1, 3]])
+    np.testing.assert_array_equal(c[2], b[2])
+
+
+def test_fused_call_error_behaviour():
+    from muscle_fish_b200 import muscle_fish as mf, synth
+    st = synth.make_config("tiny")
+    with pytest.raises(ValueError):  # nothing inside the mask: np.row_stack([]) upstream
+        mf.find_spots_snrfilter_with_distances(st["img"], st["nuc_mask"], ANISO, sigma=2.0, t_spot=0.025,
+                                               mask=np.zeros(st["img"].shape, np.uint8))
+    with pytest.raises(IndexError):
+        mf.find_spots_snrfilter_with_distances(st["img"], st["nuc_mask"], ANISO, sigma=2.0, mask=None)
+
+
+def test_uint16_stack_goes_up_as_it_is():
+    """raw detector counts: 2 bytes per voxel over PCIe, same spots as the widened copy"""
+    from muscle_fish_b200 import device as D, synth
+    st = synth.make_config("small")
+    u16 = np.clip(np.rint(st["img"] * 16.0), 0, 65535).astype(np.uint16)
+    a = D.analyze_host(u16, st["fiber_mask"], st["nuc_mask"], 2.0, 0.025, ANISO)
+    b = D.analyze_host(u16.astype(np.float64), st["fiber_mask"], st["nuc_mask"], 2.0, 0.025, ANISO)
+    np.testing.assert_array_equal(a["spots"], b["spots"])
+    np.testing.assert_array_equal(a["spot_dist"], b["spot_dist"])
+    ref, _ = oracle.find_spots_snrfilter(u16, sigma=2.0, t_spot=0.025, mask=st["fiber_mask"], pair_order="sorted")
+    assert match_fraction(a["spots"], ref) >= 0.999
+
+
+def test_device_handoff_between_consecutive_calls():
+    """normalize_image -> fix_bleaching -> find_spots_snrfilter as general_pipeline/fish_analysis.py:132-199
+    chains them: with the hand-off the image is uploaded once; the results are bit-identical to the chain
+    that goes through host memory at every step"""
+    from muscle_fish_b200 import device as D, muscle_fish as mf, scope_utils3 as su, synth
+    st = synth.make_config("small")
+    raw = np.clip(np.rint(st["img"] * 16.0 * np.exp(-0.01 * np.arange(st["img"].shape[2]))), 0, 65535)
+    raw = raw.astype(np.uint16)
+    fiber = np.zeros(raw.shape, np.int64)
+    fiber[:, 40:150, :] = 1
+
+    def chain():
+        img = su.normalize_image(raw)
+        corr = mf.fix_bleaching(img, mask=fiber, draw=False)
+        spots, data = mf.find_spots_snrfilter(corr, sigma=2, snr=None, t_spot=0.025, mask=fiber)
+        return img, corr, spots, data
+
+    assert D.HANDOFF.enabled
+    h0 = D.HANDOFF.hits
+    img, corr, spots, data = chain()
+    assert D.HANDOFF.hits == h0 + 2  # fix_bleaching and find_spots_snrfilter found their argument on the device
+    assert not img.flags.writeable and not corr.flags.writeable
+    assert img.dtype == np.float64 and corr.dtype == np.float64
+    np.testing.assert_array_equal(img, oracle.normalize_image(raw))
+    D.HANDOFF.enabled = False
+    try:
+        img2, corr2, spots2, data2 = chain()
+    finally:
+        D.HANDOFF.enabled = True
+    assert img2.flags.writeable
+    np.testing.assert_array_equal(img, img2)
+    np.testing.assert_array_equal(corr, corr2)
+    np.testing.assert_array_equal(spots, spots2)
+    assert data == data2
+    # an edited copy is an ordinary array again
+    mine = img.copy()
+    mine[:8] = 0.0
+    h1 = D.HANDOFF.hits
+    s3 = mf.find_spots(mine, sigma=2.0, t_spot=0.025)
+    assert D.HANDOFF.hits == h1
+    np.testing.assert_array_equal(s3, mf.find_spots(np.array(mine), sigma=2.0, t_spot=0.025))
+    with pytest.raises(ValueError):
+        img[0, 0, 0] = 1.0  # read-only: the pairing with the device copy cannot be broken silently
+    # the entry dies with the array
+    n = len(D.HANDOFF._entries)
+    del img, corr
+    import gc
+    gc.collect()
+    assert len(D.HANDOFF._entries) <= n - 2
+
+
+def test_run_batch_equals_stack_by_stack():
+    """config-3 driver: round-robin shards, double-buffered staging; every stack's result equals the
+    one-at-a-time call on the same arrays"""
+    import torch
+    from muscle_fish_b200 import device as D, parallel as P, synth
+    shape = (96, 80, 24)
+    n = 7
+    stacks = [synth.make_stack(shape=shape, n_spots=40, n_nuclei=3, seed=100 + i) for i in range(n)]
+    u16 = [np.clip(np.rint(s["img"] * 16.0), 0, 65535).astype(np.uint16) for s in stacks]
+    calls = []
+
+    def loader(i, img, fiber, nuc):
+        calls.append(i)
+        img[...] = u16[i]
+        fiber[...] = stacks[i]["fiber_mask"]
+        nuc[...] = stacks[i]["nuc_mask"]
+
+    seen = []
+    out = []
+    for rank in range(2):
+        out += P.run_batch(n, loader, shape, torch.uint16, 2.0, 0.025, ANISO, rank=rank, world=2,
+                           on_result=lambda i, r: seen.append(i))
+    assert sorted(i for i, _ in out) == list(range(n)) and sorted(calls) == list(range(n))
+    assert seen == [0, 2, 4, 6, 1, 3, 5]
+    for i, res in out:
+        ref = D.analyze_host(u16[i], stacks[i]["fiber_mask"], stacks[i]["nuc_mask"], 2.0, 0.025, ANISO)
+        np.testing.assert_array_equal(res["spots"], ref["spots"])
+        np.testing.assert_array_equal(res["spot_dist"], ref["spot_dist"])
+        assert res["baseline"] == ref["baseline"] and "dist" not in res
+    assert P.run_batch(1, loader, shape, torch.uint16, rank=1, world=2) == []
+    with pytest.raises(RuntimeError, match="boom"):
+        def bad(i, *a):
+            raise RuntimeError("boom")
+        P.run_batch(3, bad, shape, torch.uint16, rank=0, world=1)
