@@ -265,6 +265,30 @@ int mfish_edt_zpass(const void* f2_dev, int f2_kind, int64_t nz, int64_t nx, int
                     const double* spacing_zxy_host, int64_t f2_bound, float* out_dist_dev,
                     int32_t* out_sq_dev, void* link_ws_dev, void* stream);
 
+/* ---- compartment masks ---------------------------------------------------- *
+ * The erosion / dilation loops that build the nuclear, perinuclear and sarcoplasmic
+ * regions (general_pipeline/fish_analysis.py:169-187, nocodazole/fish_analysis_noco.py:193-208,
+ * rna_decay/fish_analysis_actd.py:165-183):
+ *     n3d x skimage.morphology.binary_dilation(mask)            (3-D cross)
+ *     n2d x binary_dilation(mask[:, :, z]) for every plane z    (2-D cross)
+ * computed as one capped city-block distance transform (n dilations by the cross = one
+ * dilation by the L1 ball of radius n).  MFISH_MORPH_ERODE follows skimage's
+ * binary_erosion (border_value=True: the volume's faces do not erode).  mask_dev: nonzero =
+ * set; out_dev: 0/1.  n3d + n2d <= 254.  Workspace: mfish_morph_workspace_bytes().       */
+#define MFISH_MORPH_DILATE 0
+#define MFISH_MORPH_ERODE 1
+int64_t mfish_morph_workspace_bytes(int64_t nz, int64_t nx, int64_t ny);
+int mfish_binary_morph_u8(const uint8_t* mask_dev, int64_t nz, int64_t nx, int64_t ny, int op, int n3d,
+                          int n2d, uint8_t* out_dev, void* workspace_dev, void* stream);
+/* region_nuc  = erode(nuc; erode3d, erode2d)
+ * dilated     = dilate(nuc; dilate3d, dilate2d)
+ * region_peri = (dilated > region_nuc) & (fiber | nuc)
+ * region_cyt  = fiber > dilated                    (general_pipeline/fish_analysis.py:169-186) */
+int mfish_compartments_u8(const uint8_t* nuc_dev, const uint8_t* fiber_dev, int64_t nz, int64_t nx,
+                          int64_t ny, int erode3d, int erode2d, int dilate3d, int dilate2d,
+                          uint8_t* region_nuc_dev, uint8_t* region_peri_dev, uint8_t* region_cyt_dev,
+                          void* workspace_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,6 +23,7 @@ CONV_G, CONV_GD, CONV_MID, CONV_LAST = 0, 1, 2, 3
 QUANTILE_WS_BYTES = 64 * 1024
 EDT_F2_I32, EDT_F2_F32 = 0, 1
 ORDER_RESPONSE, ORDER_REVERSE_RASTER = 0, 1
+MORPH_DILATE, MORPH_ERODE = 0, 1
 
 
 class MfishError(RuntimeError):
@@ -67,6 +68,9 @@ SIGNATURES = {
     "mfish_edt_inplane_u8": (_i, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p]),
     "mfish_edt_zpass": (_i, [_p, _i, _i64, _i64, _i64, _p, _i64, _p, _p, _p, _p]),
     "mfish_export_f64": (_i, [_p, _i64, _i64, _i64, _i, _p, _p]),
+    "mfish_morph_workspace_bytes": (_i64, [_i64, _i64, _i64]),
+    "mfish_binary_morph_u8": (_i, [_p, _i64, _i64, _i64, _i, _i, _i, _p, _p, _p]),
+    "mfish_compartments_u8": (_i, [_p, _p, _i64, _i64, _i64, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
 }
 
 _lib = None

@@ -44,6 +44,10 @@ static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStre
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 __device__ __forceinline__ bool aligned16_dev(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// edt.cu: distance along y to the nearest site of each row (u16, 0xFFFF = none); sites are the zero
+// voxels, or the nonzero ones when site_nonzero
+int launch_scan_y(const uint8_t* mask, uint16_t* dy, int64_t nrows, int64_t ny, int site_nonzero, cudaStream_t st);
+
 // Number of SMs on the current device (cached).
 int num_sms();
 // launch accounting (mfish_launch_count)

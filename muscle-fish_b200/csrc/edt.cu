@@ -42,7 +42,8 @@ struct ScanArgs {
   uint16_t* dy;
   int64_t nrows;
   int ny;
-  int nwords;  // ceil(ny / 32)
+  int nwords;       // ceil(ny / 32)
+  int site_nonzero;  // 0: sites are the ZERO voxels (EDT); 1: the nonzero ones (dilation of a mask)
 };
 
 constexpr int SCAN_WARPS = 8;
@@ -77,6 +78,10 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) edt_scan_y_kernel(const ScanA
           const int y = y0 + j;
           if (y < ny && __ldg(src + y) == 0) b |= (1u << j);
         }
+      }
+      if (a.site_nonzero) {  // complement inside the row
+        const int rem = ny - y0;
+        b = ~b & (rem >= 32 ? 0xFFFFFFFFu : ((1u << rem) - 1u));
       }
       bits[w] = b;
     }
@@ -169,6 +174,21 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) edt_scan_y_kernel(const ScanA
     }
     __syncwarp();
   }
+}
+
+// distance along y to the nearest site of each of the nrows rows (u16, 0xFFFF = no site in the row)
+int launch_scan_y(const uint8_t* mask, uint16_t* dy, int64_t nrows, int64_t ny, int site_nonzero, cudaStream_t st) {
+  MFISH_REQUIRE(ny > 0 && ny < 65535, "row scan: ny must be < 65535 (u16 row distances)");
+  ScanArgs a{mask, dy, nrows, (int)ny, (int)((ny + 31) / 32), site_nonzero};
+  size_t smem = (size_t)SCAN_WARPS * 3 * a.nwords * sizeof(uint32_t);
+  MFISH_REQUIRE(smem <= 200 * 1024, "row scan: row too long");
+  if (smem > 48 * 1024)
+    MFISH_CUDA(cudaFuncSetAttribute(edt_scan_y_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int64_t blocks = std::min<int64_t>((a.nrows + SCAN_WARPS - 1) / SCAN_WARPS, (int64_t)num_sms() * 32);
+  ProfScope prof("edt_scan_y", st);
+  edt_scan_y_kernel<<<(unsigned)blocks, SCAN_WARPS * 32, smem, st>>>(a);
+  count_launch(1);
+  return check_launch("edt_scan_y");
 }
 
 // ------------------------------------------------------------------------------------------
@@ -582,19 +602,8 @@ extern "C" int mfish_edt_inplane_u8(const uint8_t* mask_dev, int64_t nz, int64_t
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace_dev);
   uint16_t* dy = reinterpret_cast<uint16_t*>(ws);
   void* link = ws + align256(n * 2);
-  {
-    ScanArgs a{mask_dev, dy, nz * nx, (int)ny, (int)((ny + 31) / 32)};
-    size_t smem = (size_t)SCAN_WARPS * 3 * a.nwords * sizeof(uint32_t);
-    MFISH_REQUIRE(smem <= 200 * 1024, "edt: row too long");
-    if (smem > 48 * 1024)
-      MFISH_CUDA(cudaFuncSetAttribute(edt_scan_y_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int64_t blocks = std::min<int64_t>((a.nrows + SCAN_WARPS - 1) / SCAN_WARPS, (int64_t)num_sms() * 32);
-    ProfScope prof("edt_scan_y", st);
-    edt_scan_y_kernel<<<(unsigned)blocks, SCAN_WARPS * 32, smem, st>>>(a);
-    count_launch(1);
-    rc = check_launch("edt_scan_y");
-    if (rc != MFISH_OK) return rc;
-  }
+  rc = launch_scan_y(mask_dev, dy, nz * nx, ny, 0, st);
+  if (rc != MFISH_OK) return rc;
   const bool link16 = nx <= 32767;
   if (plane_int) {
     *f2_kind_host = MFISH_EDT_F2_I32;

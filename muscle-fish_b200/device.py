@@ -754,6 +754,35 @@ def edt_zpass(f2: torch.Tensor, kind: int, sampling_xyz=None, out: torch.Tensor 
     return out
 
 
+# ---------------------------------------------------------- compartment masks
+def binary_morph(mask_zxy: torch.Tensor, op: str, n3d: int, n2d: int, out: torch.Tensor | None = None):
+    """``n3d`` 3-D + ``n2d`` per-plane cross dilations ('dilate') or skimage-style erosions ('erode') of a
+    uint8 mask [nz,nx,ny] in one capped city-block distance transform.  Returns uint8 0/1."""
+    nz, nx, ny = mask_zxy.shape
+    dev = mask_zxy.device
+    ws = WS.get("morph_ws", (int(L.lib().mfish_morph_workspace_bytes(nz, nx, ny)),), torch.uint8, dev)
+    if out is None:
+        out = torch.empty((nz, nx, ny), dtype=torch.uint8, device=dev)
+    code = {"dilate": L.MORPH_DILATE, "erode": L.MORPH_ERODE}[op]
+    L.check(L.lib().mfish_binary_morph_u8(mask_zxy.data_ptr(), nz, nx, ny, code, int(n3d), int(n2d), out.data_ptr(),
+                                          ws.data_ptr(), _stream()))
+    return out
+
+
+def compartments(nuc_zxy: torch.Tensor, fiber_zxy: torch.Tensor, erode=(1, 10), dilate=(4, 40)):
+    """(region_nuc, region_peri, region_cyt) uint8 [nz,nx,ny] of general_pipeline/fish_analysis.py:169-186."""
+    nz, nx, ny = nuc_zxy.shape
+    dev = nuc_zxy.device
+    if tuple(fiber_zxy.shape) != (nz, nx, ny):
+        raise ValueError("nuclear and fibre masks differ in shape")
+    ws = WS.get("morph_ws", (int(L.lib().mfish_morph_workspace_bytes(nz, nx, ny)),), torch.uint8, dev)
+    r_nuc, r_peri, r_cyt = (torch.empty((nz, nx, ny), dtype=torch.uint8, device=dev) for _ in range(3))
+    L.check(L.lib().mfish_compartments_u8(nuc_zxy.data_ptr(), fiber_zxy.data_ptr(), nz, nx, ny, int(erode[0]),
+                                          int(erode[1]), int(dilate[0]), int(dilate[1]), r_nuc.data_ptr(),
+                                          r_peri.data_ptr(), r_cyt.data_ptr(), ws.data_ptr(), _stream()))
+    return r_nuc, r_peri, r_cyt
+
+
 # ----------------------------------------------------- device-resident pipeline
 class StageTimer:
     """CUDA-event timing of the individual C-ABI calls of a step, on the launching stream."""
@@ -806,7 +835,9 @@ def _spot_list_tail(vol, fiber_zxy, peaks, baseline_f, sigma, snr, dist_ready, t
         if len(spots):
             spots = spots[gather(fiber_zxy, spots) != 0]
         inten = t.run("blur_pts", blur_at_points, vol, spots, (3, 3, 0.3), "nearest")
-        baseline = baseline_f()
+        # no spot inside the mask: the reference fails on the empty row stack before it ever takes the
+        # percentile (modules/muscle_fish.py:341), so an empty mask must not raise from here
+        baseline = baseline_f() if len(spots) else None
     main.wait_stream(hp)
     if snr is None and len(spots):
         thresh = np.percentile(inten, 90) / (baseline * np.sqrt(10))

@@ -179,6 +179,8 @@ def run_batch(n_stacks: int, loader, shape_xyz, img_dtype=torch.uint16, sigma=2.
 
     results = []
     start_fill(0).join()
+    if errors:
+        raise errors[0]
     upload(0)
     pending = start_fill(1) if len(mine) > 1 else None  # thread reading stack k+1
     for k, index in enumerate(mine):

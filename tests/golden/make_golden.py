@@ -50,5 +50,27 @@ def main():
     print("wrote", path, {k: getattr(v, "shape", None) for k, v in out.items()}, os.path.getsize(path), "bytes")
 
 
+def main_morph():
+    """tests/golden/golden_morph.npz: the compartment masks of general_pipeline/fish_analysis.py:165-187 by
+    the real scipy.ndimage binary_erosion / binary_dilation, driven by the oracle's literal restatement of
+    the script's loops (skimage's wrappers only add border_value=True to the erosion)."""
+    st = synth.make_stack(shape=(72, 64, 20), n_spots=10, n_nuclei=3, seed=98, nuc_semi=(14.0, 9.0, 5.0))
+    nuc, fib = st["nuc_mask"], st["fiber_mask"]
+    out = {"nuc_mask": nuc, "fiber_mask": fib}
+    for tag, er, di in (("ref", (1, 10), (4, 40)), ("small", (1, 2), (2, 5))):
+        reg = oracle.ref_morph.compartments(nuc, fib, er, di)
+        for k, v in reg.items():
+            out[f"{tag}_{k}"] = v.astype(np.uint8)
+    out["erode_3d_1"] = ndi.binary_erosion(nuc, border_value=True)
+    out["dilate_3d_1"] = ndi.binary_dilation(nuc)
+    out["dilate_2d_plane7"] = ndi.binary_dilation(nuc[:, :, 7])
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_morph.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, {k: (v.shape, int(v.sum())) for k, v in out.items()}, os.path.getsize(path), "bytes")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "morph":
+        main_morph()
+    else:
+        main()

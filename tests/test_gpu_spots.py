@@ -444,7 +444,7 @@ def test_peak_orders_on_a_dense_stack_vs_oracle_and_each_other():
     for po in ("response", "reverse_raster"):
         ref = oracle.blob_log(img, 2.0, 2.0, 1, 0.025, pair_order="sorted", peak_order=po)
         got = D.blob_log(vol, 2.0, 2.0, 1, 0.025, peak_order=po)
-        assert len(ref) > 2000
+        assert len(ref) > 1500
         assert match_fraction(got, ref) >= MIN_MATCH, po
         res[po] = got
     # reverse raster order of the rows themselves

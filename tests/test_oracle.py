@@ -208,3 +208,33 @@ def test_oracle_reproduces_golden(golden):
     np.testing.assert_array_equal(golden["edt_iso_sq"], oracle.edt_bruteforce_sq(not_nuc))
     assert match_fraction(oracle.find_spots(img, sigma=2.0, t_spot=0.025, pair_order="sorted"),
                           golden["spots_s2"]) == 1.0
+
+
+def test_compartment_oracle_matches_golden_and_the_closed_form():
+    """general_pipeline/fish_analysis.py:165-187: the loop nest equals one L1-ball dilation per plane window
+    (what the device computes), and reproduces the committed golden masks"""
+    import os
+    from scipy import ndimage as ndi
+    from oracle import ref_morph as M
+    gm = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_morph.npz"))
+    nuc, fib = gm["nuc_mask"], gm["fiber_mask"]
+    reg = M.compartments(nuc, fib, (1, 2), (2, 5))
+    for k in reg:
+        assert reg[k].dtype == np.int64
+        np.testing.assert_array_equal(reg[k], gm[f"small_{k}"])
+
+    def closed(mask, op, n3, n2):
+        src = mask if op == "dilate" else ~mask
+        nx, ny, nz = mask.shape
+        d2 = np.stack([ndi.distance_transform_cdt(~src[:, :, z], metric="taxicab") if src[:, :, z].any()
+                       else np.full((nx, ny), 10 ** 6) for z in range(nz)], axis=2)
+        out = np.zeros(mask.shape, bool)
+        for z in range(nz):
+            for dz in range(-n3, n3 + 1):
+                if 0 <= z + dz < nz:
+                    out[:, :, z] |= d2[:, :, z + dz] <= n2 + n3 - abs(dz)
+        return out if op == "dilate" else ~out
+
+    m = nuc.astype(bool)
+    for op, n3, n2 in [("dilate", 4, 7), ("erode", 1, 3), ("dilate", 0, 5), ("erode", 2, 0)]:
+        np.testing.assert_array_equal(M.iterate(m, op, n3, n2), closed(m, op, n3, n2))
