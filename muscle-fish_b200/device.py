@@ -813,28 +813,47 @@ class _NoTimer:
 
 
 def _spot_list_tail(vol, fiber_zxy, peaks, baseline_f, sigma, snr, dist_ready, t, fiber_ready=None):
-    """Second half of the hot path, shared by the device-resident and the host-buffer entry: wait for the
-    peak count, then rank / prune / mask filter / blur at the spots / SNR cut on the high-priority stream,
-    and gather the distance map (``dist_ready()`` -> float32 [nz,nx,ny], valid on the main stream)."""
+    """Second half of the hot path, shared by the device-resident and the host-buffer entry.  After the
+    peak count is known, everything per spot -- rank / prune, decode, blurred intensity, fibre-mask and
+    distance look-ups -- runs on the high-priority stream for ALL pruned peaks and comes back in ONE small
+    device-to-host copy; the mask / SNR rules are then applied on the host.  What needs the fibre mask
+    (``fiber_ready()``, possibly still crossing PCIe) is queued last, so that the list work overlaps its
+    arrival.  ``dist_ready()`` -> float32 [nz,nx,ny] distance map, valid on the calling stream."""
     nz, nx, ny = vol.data.shape
     dims = (1, nx, ny, nz)
+    dev = vol.data.device
     main = torch.cuda.current_stream()
     idx, val = peaks()
-    spots = np.empty((0, 4))
     hp = _list_stream() if os.environ.get("MFISH_LIST_PRIO", "1") != "0" else main
     hp.wait_stream(main)
     with torch.cuda.stream(hp):
-        if fiber_ready is not None:
-            fiber_zxy = fiber_ready()
+        packed = None
         if idx.numel():
             cutoff = max(T.prune_cutoff_sq(float(sigma), None, 0.5), 0)
             idx_r, _, alive = t.run("rank_prune", rank_prune_equal, idx, val, dims, cutoff)
-            idx_h = idx_r[alive.bool()].cpu().numpy()
-            x, y, z, _ = decode_raster(idx_h, dims)
-            spots = np.stack([x, y, z, np.full(len(x), float(sigma))], axis=1).astype(np.float64)
-        if len(spots):
-            spots = spots[gather(fiber_zxy, spots) != 0]
-        inten = t.run("blur_pts", blur_at_points, vol, spots, (3, 3, 0.3), "nearest")
+            ras = idx_r[alive.bool()]  # survivors in peak order; raster index over (x, y, z)
+            if ras.numel():
+                z = ras % nz
+                xy = ras // nz
+                pts = torch.stack([z, xy // ny, xy % ny], dim=1).to(torch.int32)
+                inten_d = t.run("blur_pts", blur_at_points_dev, vol, pts, (3, 3, 0.3), "nearest")
+                dist = dist_ready()
+                dist_d = gather_points(dist, pts)
+                if fiber_ready is not None:
+                    fiber_zxy = fiber_ready()
+                inm_d = gather_points(fiber_zxy, pts)
+                packed = torch.stack([ras.to(torch.float64), inten_d, dist_d.to(torch.float64),
+                                      inm_d.to(torch.float64)]).cpu().numpy()
+        if packed is None:
+            if fiber_ready is not None:
+                fiber_ready()
+            dist = dist_ready()
+            packed = np.empty((4, 0))
+        inside = packed[3] != 0
+        x, y, z, _ = decode_raster(packed[0, inside].astype(np.int64), dims)
+        spots = np.stack([x, y, z, np.full(len(x), float(sigma))], axis=1).astype(np.float64)
+        inten = packed[1, inside]
+        dists = packed[2, inside]
         # no spot inside the mask: the reference fails on the empty row stack before it ever takes the
         # percentile (modules/muscle_fish.py:341), so an empty mask must not raise from here
         baseline = baseline_f() if len(spots) else None
@@ -843,10 +862,8 @@ def _spot_list_tail(vol, fiber_zxy, peaks, baseline_f, sigma, snr, dist_ready, t
         thresh = np.percentile(inten, 90) / (baseline * np.sqrt(10))
         snr = max(thresh, np.sqrt(10))
     keep = (inten / baseline > snr) if len(spots) else np.zeros(0, bool)
-    dist = dist_ready()
-    spot_dist = gather(dist, spots[keep]).astype(np.float64) if keep.any() else np.empty(0)
     return {"spots": spots[keep], "spots_masked": spots, "intensity": inten, "baseline": baseline, "snr": snr,
-            "spot_dist": spot_dist, "dist": dist}
+            "spot_dist": dists[keep], "dist": dist}
 
 
 def analyze_stack(img_zxy: torch.Tensor, fiber_zxy: torch.Tensor, notnuc_zxy: torch.Tensor, sigma=2.0,
@@ -871,8 +888,9 @@ def analyze_stack(img_zxy: torch.Tensor, fiber_zxy: torch.Tensor, notnuc_zxy: to
         dist = t.run("edt", edt, notnuc_zxy, sampling_xyz)
 
     def dist_ready():
-        main.wait_stream(side)
-        dist.record_stream(main)
+        cur = torch.cuda.current_stream()
+        cur.wait_stream(side)
+        dist.record_stream(cur)
         return dist
 
     return _spot_list_tail(vol, fiber_zxy, peaks, baseline_f, sigma, snr, dist_ready, t)
@@ -885,8 +903,9 @@ def analyze_host(img_fish, fiber_mask, region_nuc, sigma=2.0, t_spot=0.025, samp
     GPU's work after the last byte is as short as possible:
 
       copy stream :  nucleus mask | image ............................ | fibre mask |
-      side stream :               | ingest + EDT (3 passes)            |
-      main stream :                                  ingest(+min/max), LoG + NMS    | P25, list handling
+      side stream :               | ingest + EDT (3 passes)                         | ingest, P25 pass
+      main stream :                                  ingest(+min/max), LoG + NMS | count
+      list stream :                                                               | rank, prune, blur, look-ups | D2H
 
     ``region_nuc`` is the nucleus mask itself (the NOT is taken on ingest, nocodazole/fish_analysis_noco.py:218).
     Returns the dict of ``analyze_stack``."""
@@ -898,24 +917,38 @@ def analyze_host(img_fish, fiber_mask, region_nuc, sigma=2.0, t_spot=0.025, samp
     with torch.cuda.stream(side):
         notnuc = ingest(tn, z_first=z_first, as_mask=True, negate=True, ready=en)
         dist = t.run("edt", edt, notnuc, sampling_xyz)
+        edt_done = torch.cuda.Event()
+        edt_done.record(side)
     vol = ingest(ti, z_first=z_first, want_minmax=True, ready=ei)
+    vol_ready = torch.cuda.Event()
+    vol_ready.record(main)
     log = WS.get("log_out", vol.data.shape, torch.float32, vol.data.device)
     _, peaks = t.run("log3d_nms", log_peaks_async, vol, sigma, t_spot, log)
-    state = {}
-
-    def fiber_ready():  # on the list stream, after the peak count has been read
-        state["fiber"] = ingest(tf, z_first=z_first, as_mask=True, ready=ef)
-        if tuple(state["fiber"].shape) != tuple(vol.data.shape):
+    # the fibre mask is the last buffer to arrive; its ingest and the P25 pass over the fibre voxels follow the
+    # distance transform on the side stream, so neither the peak count's read-back (main stream) nor the list
+    # handling (high-priority stream) queues behind PCIe
+    fiber_arrived = torch.cuda.Event()
+    with torch.cuda.stream(side):
+        fiber = ingest(tf, z_first=z_first, as_mask=True, ready=ef)
+        if tuple(fiber.shape) != tuple(vol.data.shape):
             raise IndexError("mask and image shapes differ")
-        state["baseline"] = masked_percentile_async(vol, state["fiber"], 25)
-        return state["fiber"]
+        fiber_arrived.record(side)
+        side.wait_event(vol_ready)
+        pending = masked_percentile_async(vol, fiber, 25)
+
+    def fiber_ready():
+        torch.cuda.current_stream().wait_event(fiber_arrived)
+        fiber.record_stream(torch.cuda.current_stream())
+        return fiber
 
     def baseline_f():
-        return state["baseline"]()
+        torch.cuda.current_stream().wait_stream(side)
+        return pending()
 
     def dist_ready():
-        main.wait_stream(side)
-        dist.record_stream(main)
+        cur = torch.cuda.current_stream()
+        cur.wait_event(edt_done)  # not wait_stream: the side stream goes on to wait for the fibre mask
+        dist.record_stream(cur)
         return dist
 
     return _spot_list_tail(vol, None, peaks, baseline_f, sigma, snr, dist_ready, t, fiber_ready=fiber_ready)
