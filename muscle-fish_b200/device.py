@@ -815,45 +815,52 @@ class _NoTimer:
 def _spot_list_tail(vol, fiber_zxy, peaks, baseline_f, sigma, snr, dist_ready, t, fiber_ready=None):
     """Second half of the hot path, shared by the device-resident and the host-buffer entry.  After the
     peak count is known, everything per spot -- rank / prune, decode, blurred intensity, fibre-mask and
-    distance look-ups -- runs on the high-priority stream for ALL pruned peaks and comes back in ONE small
-    device-to-host copy; the mask / SNR rules are then applied on the host.  What needs the fibre mask
-    (``fiber_ready()``, possibly still crossing PCIe) is queued last, so that the list work overlaps its
-    arrival.  ``dist_ready()`` -> float32 [nz,nx,ny] distance map, valid on the calling stream."""
+    distance look-ups -- runs on the high-priority stream for ALL pruned peaks and comes back in two small
+    device-to-host copies: first what is ready, then the one look-up whose input arrives last (the distance
+    map when the transform is still running beside the list work, the fibre mask when it is still crossing
+    PCIe: ``fiber_ready`` given), so that the host's share of the work overlaps that wait.  The mask / SNR
+    rules are applied on the host.  ``dist_ready()`` -> float32 [nz,nx,ny] distance map, valid on the calling
+    stream."""
     nz, nx, ny = vol.data.shape
     dims = (1, nx, ny, nz)
-    dev = vol.data.device
     main = torch.cuda.current_stream()
     idx, val = peaks()
     hp = _list_stream() if os.environ.get("MFISH_LIST_PRIO", "1") != "0" else main
     hp.wait_stream(main)
+    fiber_last = fiber_ready is not None
     with torch.cuda.stream(hp):
-        packed = None
+        n = 0
         if idx.numel():
             cutoff = max(T.prune_cutoff_sq(float(sigma), None, 0.5), 0)
             idx_r, _, alive = t.run("rank_prune", rank_prune_equal, idx, val, dims, cutoff)
             ras = idx_r[alive.bool()]  # survivors in peak order; raster index over (x, y, z)
-            if ras.numel():
-                z = ras % nz
-                xy = ras // nz
-                pts = torch.stack([z, xy // ny, xy % ny], dim=1).to(torch.int32)
-                inten_d = t.run("blur_pts", blur_at_points_dev, vol, pts, (3, 3, 0.3), "nearest")
+            n = int(ras.numel())
+        if n:
+            z = ras % nz
+            xy = ras // nz
+            pts = torch.stack([z, xy // ny, xy % ny], dim=1).to(torch.int32)
+            inten_d = t.run("blur_pts", blur_at_points_dev, vol, pts, (3, 3, 0.3), "nearest")
+            if fiber_last:
                 dist = dist_ready()
-                dist_d = gather_points(dist, pts)
-                if fiber_ready is not None:
-                    fiber_zxy = fiber_ready()
-                inm_d = gather_points(fiber_zxy, pts)
-                packed = torch.stack([ras.to(torch.float64), inten_d, dist_d.to(torch.float64),
-                                      inm_d.to(torch.float64)]).cpu().numpy()
-        if packed is None:
-            if fiber_ready is not None:
+                early_d = gather_points(dist, pts)
+            else:
+                early_d = gather_points(fiber_zxy, pts)
+            early = torch.stack([ras.to(torch.float64), inten_d, early_d.to(torch.float64)]).cpu().numpy()
+            x, y, zz, _ = decode_raster(early[0].astype(np.int64), dims)
+            spots = np.stack([x, y, zz, np.full(n, float(sigma))], axis=1).astype(np.float64)
+            if fiber_last:
+                late = gather_points(fiber_ready(), pts).cpu().numpy()
+                inside, dists = late != 0, early[2]
+            else:
+                dist = dist_ready()
+                late = gather_points(dist, pts).cpu().numpy()
+                inside, dists = early[2] != 0, late.astype(np.float64)
+            spots, inten, dists = spots[inside], early[1][inside], dists[inside]
+        else:
+            if fiber_last:
                 fiber_ready()
             dist = dist_ready()
-            packed = np.empty((4, 0))
-        inside = packed[3] != 0
-        x, y, z, _ = decode_raster(packed[0, inside].astype(np.int64), dims)
-        spots = np.stack([x, y, z, np.full(len(x), float(sigma))], axis=1).astype(np.float64)
-        inten = packed[1, inside]
-        dists = packed[2, inside]
+            spots, inten, dists = np.empty((0, 4)), np.empty(0), np.empty(0)
         # no spot inside the mask: the reference fails on the empty row stack before it ever takes the
         # percentile (modules/muscle_fish.py:341), so an empty mask must not raise from here
         baseline = baseline_f() if len(spots) else None
