@@ -22,20 +22,25 @@ void set_error(const char* fmt, ...) {
 }
 
 int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-    // the small per-call scratch (sort buffers, tap tables) comes from the stream-ordered pool;
-    // keep freed blocks cached instead of returning them to the driver at every synchronise
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-      unsigned long long keep = ~0ull;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
+  // per device: a process that drives several GPUs sizes each one's grids with its own SM count
+  static std::mutex mu;
+  static std::map<int, int> cache;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> g(mu);
+  auto it = cache.find(dev);
+  if (it != cache.end()) return it->second;
+  int n = 0;
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  if (n <= 0) n = 148;
+  // the small per-call scratch (sort buffers, tap tables) comes from the stream-ordered pool;
+  // keep freed blocks cached instead of returning them to the driver at every synchronise
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
   }
+  cache[dev] = n;
   return n;
 }
 

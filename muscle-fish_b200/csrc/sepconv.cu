@@ -1080,10 +1080,13 @@ static int launch_strided(const PassDesc& p) {
       auto go = [&](auto kern, size_t smem) {
         // every op of one radius shares a function-pointer type, so remember the configured kernels by
         // address: the walker wants the large shared-memory carve-out (5 blocks x 35 KB per SM)
-        static std::vector<const void*> configured;
+        // (function attributes are per device: the key carries the current device)
+        static std::vector<std::pair<int, const void*>> configured;
         static std::mutex configured_lock;
         std::lock_guard<std::mutex> guard(configured_lock);
-        const void* key = reinterpret_cast<const void*>(kern);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const std::pair<int, const void*> key(dev, reinterpret_cast<const void*>(kern));
         if (std::find(configured.begin(), configured.end(), key) == configured.end()) {
           cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
           if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -297,6 +297,8 @@ __global__ void __launch_bounds__(QSCAN_THREADS) qsel_scan_kernel(QWs* ws, float
   for (int i = t; i < 2 * QBINS; i += QSCAN_THREADS) (&ws->hist[0][0])[i] = 0;
 }
 
+__global__ void qsel_set_cap_kernel(QWs* ws, unsigned long long cap) { ws->ctl.cap = cap; }
+
 // bracket -> control block (after the sample select)
 __global__ void qsel_bracket_kernel(QWs* ws, const float* pair) {
   if (threadIdx.x != 0) return;
@@ -701,7 +703,7 @@ static int quantile_fast_impl(const float* vol_dev, const uint8_t* mask_dev, int
   qsel_bracket_kernel<<<1, 32, 0, st>>>(ws, pair);
   // 2. the one full pass
   MFISH_CUDA(cudaMemsetAsync(cand, 0x7f, (size_t)cap * sizeof(float), st));  // 3.39e38: sorts above any voxel
-  MFISH_CUDA(cudaMemcpyAsync(&ws->ctl.cap, &cap, sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+  qsel_set_cap_kernel<<<1, 1, 0, st>>>(ws, (unsigned long long)cap);  // (a pageable H2D copy would stall the stream)
   if (mm) {
     qsel_mm_init_kernel<<<1, 1, 0, st>>>(mm);
     qsel_range_kernel<true><<<blocks, 256, 0, st>>>(vol_dev, mask_dev, n, ws, cand, mm);

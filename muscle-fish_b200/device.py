@@ -675,6 +675,13 @@ def masked_quantile_distributed(vol: torch.Tensor, mask: torch.Tensor, q: float,
     out = torch.empty(2, dtype=torch.float32, device=dev)
     info = torch.empty(2, dtype=torch.float64, device=dev)
     hist = ws[:2 * 2048 * 4].view(torch.int32)
+    n_local = torch.tensor([float(vol.numel())], dtype=torch.float64, device=dev)
+    reduce_hist(n_local)
+    if float(n_local.item()) >= 2.0 ** 32:
+        # the bins are uint32: a mosaic with >= 2^32 voxels could wrap one (sign + exponent + 2 mantissa bits
+        # decide the first pass's bin) without anything noticing
+        raise OverflowError("distributed masked quantile: the mosaic has 2^32 voxels or more, a 32-bit histogram "
+                            "bin could overflow")
     L.check(L.lib().mfish_qsel_begin(ws.data_ptr(), float(q), _stream()))
     for p in range(3):
         L.check(L.lib().mfish_qsel_hist(vol.data_ptr(), mask.data_ptr(), vol.numel(), p, ws.data_ptr(), _stream()))

@@ -170,7 +170,9 @@ def make_stack_device(shape, n_spots, n_nuclei, seed, device="cuda", z_first=Tru
     near = (cz >= za - hz - 1) & (cz <= zb + hz + 1)  # spots that can touch this slab
     cx, cy, cz, amp = cx[near], cy[near], cz[near], amp[near]
     n_spots = int(near.sum())
-    flat = img.view(-1)
+    # spot patches are accumulated as 2^-16 fixed-point integers: integer atomics commute, so the voxels do
+    # not depend on the order the patches land in, nor on which slab of a decomposition draws them
+    acc = torch.zeros(ZL * X * Y, dtype=torch.int64, device=device)
     ox = torch.arange(-hx, hx + 1, device=device)
     oz = torch.arange(-hz, hz + 1, device=device)
     chunk = 16384
@@ -189,11 +191,13 @@ def make_stack_device(shape, n_spots, n_nuclei, seed, device="cuda", z_first=Tru
         gx = gx * ((xs >= 0) & (xs < X))
         gy = gy * ((ys >= 0) & (ys < Y))
         gz = gz * ((zs >= za) & (zs < zb))
-        val = (tam[:, None, None, None] * gz[:, :, None, None] * gx[:, None, :, None]
-               * gy[:, None, None, :]).to(torch.float32)
+        val = torch.round(tam[:, None, None, None] * gz[:, :, None, None] * gx[:, None, :, None]
+                          * gy[:, None, None, :] * 65536.0).to(torch.int64)
         lin = (((zs - za).clamp(0, ZL - 1)[:, :, None, None] * X + xs.clamp(0, X - 1)[:, None, :, None]) * Y
                + ys.clamp(0, Y - 1)[:, None, None, :])
-        flat.index_add_(0, lin.reshape(-1), val.reshape(-1))
+        acc.index_add_(0, lin.reshape(-1), val.reshape(-1))
+    img += (acc.to(torch.float64) * (1.0 / 65536.0)).to(torch.float32).view(ZL, X, Y)
+    del acc
 
     nuc = torch.zeros((ZL, X, Y), dtype=torch.uint8, device=device)
     a, b, c = NUC_SEMI
