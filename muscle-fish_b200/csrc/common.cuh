@@ -48,6 +48,10 @@ __device__ __forceinline__ bool aligned16_dev(const void* p) { return (reinterpr
 // voxels, or the nonzero ones when site_nonzero
 int launch_scan_y(const uint8_t* mask, uint16_t* dy, int64_t nrows, int64_t ny, int site_nonzero, cudaStream_t st);
 
+// bigconv.cu: one plain-Gaussian pass with a large radius (FMA-bound regime); taps_dev = radius + 1 half taps
+int big_gauss_pass(const float* in, float* out, int64_t nz, int64_t nx, int64_t ny, int axis, const float* taps_dev,
+                   int radius, int boundary, const float* mm, cudaStream_t st);
+
 // Number of SMs on the current device (cached).
 int num_sms();
 // launch accounting (mfish_launch_count)

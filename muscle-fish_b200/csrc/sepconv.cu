@@ -1134,6 +1134,14 @@ static int launch_strided(const PassDesc& p) {
 
 static int launch_generic(const PassDesc& p);
 
+static bool big_gauss_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("MFISH_BIG_GAUSS");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
 template <int R>
 static int launch_R(const PassDesc& p);
 
@@ -1141,6 +1149,12 @@ static int launch_generic(const PassDesc& p) {
   float *dg = nullptr, *dd = nullptr;
   int rc = upload_taps(p, &dg, &dd);
   if (rc != MFISH_OK) return rc;
+  if (p.op == MFISH_CONV_G && p.radius > 16 && p.out_begin == 0 && p.out_end < 0 && big_gauss_enabled()) {
+    // plain Gaussian with many taps (segmentation blurs): the FMA-organised kernels of bigconv.cu
+    rc = big_gauss_pass(p.in0, p.out0, p.nz, p.nx, p.ny, p.axis, dg, p.radius, p.boundary, p.mm, p.st);
+    cudaFreeAsync(dg, p.st);
+    return rc;
+  }
   ProfScope prof(p.axis == MFISH_AXIS_Y ? "conv_y_generic" : "conv_strided_generic", p.st);
   if (p.axis == MFISH_AXIS_Y) {
     YGenArgs a;

@@ -169,6 +169,23 @@ def test_gaussian3d_nearest(sigma):
     assert _rel_err(got, ref) < REL_TOL
 
 
+@pytest.mark.parametrize("shape", [(90, 100, 21), (300, 530, 9), (47, 33, 5)])
+@pytest.mark.parametrize("sigma", [(10, 10, 1), (20, 20, 2), (5, 30, 6)])
+def test_segmentation_blurs_large_radius(shape, sigma):
+    """threshold_fiber's (10,10,1) and threshold_nuclei's (20,20,2) (modules/muscle_fish.py:239,166): radii 40
+    and 80, longer than the short axes of the small shapes (the 'nearest' rule folds everything beyond the
+    ends onto the edge voxel); a radius-24 z pass exercises the strided large-radius kernel along z as well"""
+    import os
+    from muscle_fish_b200 import ndimage as nd
+    rng = np.random.default_rng(8)
+    a = rng.random(shape) + np.linspace(0, 3, shape[0])[:, None, None]
+    ref = oracle.gaussian(a, sigma)
+    got = nd.gaussian(a, sigma)
+    assert _rel_err(got, ref) < REL_TOL
+    # reflect mode through the same kernels
+    assert _rel_err(nd.gaussian(a, sigma, mode="reflect"), oracle.gaussian(a, sigma, mode="reflect")) < REL_TOL
+
+
 @pytest.mark.parametrize("sigma", [1.0, 1.5, 2.0, 2.5, 3.0])
 def test_log_volume_matches_gaussian_laplace(sigma):
     from muscle_fish_b200 import device as D, synth
