@@ -289,6 +289,24 @@ int mfish_compartments_u8(const uint8_t* nuc_dev, const uint8_t* fiber_dev, int6
                           uint8_t* region_nuc_dev, uint8_t* region_peri_dev, uint8_t* region_cyt_dev,
                           void* workspace_dev, void* stream);
 
+/* ---- segmentation thresholds ---------------------------------------------- *
+ * The statistics behind threshold_fiber / threshold_nuclei (modules/muscle_fish.py:165-198,
+ * 238-272) on the blurred float32 volume.
+ * mfish_histogram_f32: np.histogram(vol, bins=nbins, range=(first, last)) as skimage's
+ *   threshold_otsu takes it; edges_dev = np.linspace(first, last, nbins + 1) (float64);
+ *   hist_dev: nbins uint64 counts.  nbins <= 1024.
+ * mfish_split_moments_f32: out4 = {count, sum} of the voxels <= threshold, {count, sum} of
+ *   those > threshold (float64) -- one iteration of skimage's threshold_li.
+ * mfish_binarize_f32: out = (vol > threshold) as uint8; with norm_minmax_dev the compare is
+ *   on (vol - min) / (max - min) (threshold_nuclei binarises the normalised, unblurred
+ *   image, modules/muscle_fish.py:181).                                                   */
+int mfish_histogram_f32(const float* vol_dev, int64_t n, double first, double last, int nbins,
+                        const double* edges_dev, unsigned long long* hist_dev, void* stream);
+int mfish_split_moments_f32(const float* vol_dev, int64_t n, float threshold, double* out4_dev,
+                            void* stream);
+int mfish_binarize_f32(const float* vol_dev, int64_t n, float threshold, const float* norm_minmax_dev,
+                       uint8_t* out_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

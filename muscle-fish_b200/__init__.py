@@ -7,6 +7,7 @@ root (``import muscle_fish_b200``).  Sub-modules:
 * ``muscle_fish`` / ``scope_utils3``  drop-in host API with the reference's signatures
   (``modules/muscle_fish.py``, ``modules/scope_utils3.py``)
 * ``ndimage``      ``distance_transform_edt`` / ``gaussian`` / ``gaussian_laplace`` replacements
+* ``segmentation`` ``threshold_fiber`` / ``threshold_nuclei`` (blurs, Li / Otsu statistics on the GPU)
 * ``morphology``   ``binary_erosion`` / ``binary_dilation`` / ``compartments`` (the compartment masks)
 * ``device``       device-resident pipeline on torch CUDA tensors
 * ``parallel``     multi-GPU drivers (stack-per-GPU batches, z-slab mosaics)
@@ -23,6 +24,6 @@ from . import taps, synth  # noqa: F401  (pure numpy, importable anywhere)
 
 def __getattr__(name):
     import importlib
-    if name in ("device", "muscle_fish", "scope_utils3", "ndimage", "morphology", "parallel", "_lib"):
+    if name in ("device", "muscle_fish", "scope_utils3", "ndimage", "morphology", "segmentation", "parallel", "_lib"):
         return importlib.import_module(f"{__name__}.{name}")
     raise AttributeError(name)

@@ -70,6 +70,9 @@ SIGNATURES = {
     "mfish_export_f64": (_i, [_p, _i64, _i64, _i64, _i, _p, _p]),
     "mfish_morph_workspace_bytes": (_i64, [_i64, _i64, _i64]),
     "mfish_binary_morph_u8": (_i, [_p, _i64, _i64, _i64, _i, _i, _i, _p, _p, _p]),
+    "mfish_histogram_f32": (_i, [_p, _i64, _d, _d, _i, _p, _p, _p]),
+    "mfish_split_moments_f32": (_i, [_p, _i64, _f, _p, _p]),
+    "mfish_binarize_f32": (_i, [_p, _i64, _f, _p, _p, _p]),
     "mfish_compartments_u8": (_i, [_p, _p, _i64, _i64, _i64, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
 }
 

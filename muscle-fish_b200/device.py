@@ -761,6 +761,40 @@ def edt_zpass(f2: torch.Tensor, kind: int, sampling_xyz=None, out: torch.Tensor 
     return out
 
 
+# ------------------------------------------------------ segmentation thresholds
+def histogram(vol: torch.Tensor, nbins=256, value_range=None):
+    """np.histogram(vol, bins=nbins, range=value_range or (min, max)) -> (hist int64, bin_edges float64), host"""
+    if value_range is None:
+        lo, hi = [float(v) for v in minmax(vol).tolist()]
+    else:
+        lo, hi = float(value_range[0]), float(value_range[1])
+    if lo == hi:  # numpy widens a degenerate range by half a unit each way
+        lo, hi = lo - 0.5, hi + 0.5
+    edges = np.linspace(lo, hi, nbins + 1, endpoint=True)
+    e_d = torch.from_numpy(edges).to(vol.device)
+    h_d = torch.empty(nbins, dtype=torch.int64, device=vol.device)
+    L.check(L.lib().mfish_histogram_f32(vol.data_ptr(), vol.numel(), lo, hi, int(nbins), e_d.data_ptr(),
+                                        h_d.data_ptr(), _stream()))
+    return h_d.cpu().numpy(), edges
+
+
+def split_moments(vol: torch.Tensor, threshold: float):
+    """(count, sum) of the voxels <= threshold and (count, sum) of those above, float64 on the host"""
+    out = torch.empty(4, dtype=torch.float64, device=vol.device)
+    L.check(L.lib().mfish_split_moments_f32(vol.data_ptr(), vol.numel(), float(threshold), out.data_ptr(), _stream()))
+    c0, s0, c1, s1 = out.tolist()
+    return (c0, s0), (c1, s1)
+
+
+def binarize(vol: torch.Tensor, threshold: float, minmax_dev: torch.Tensor | None = None) -> torch.Tensor:
+    """uint8 (vol > threshold); with ``minmax_dev`` the compare is on the normalised voxels"""
+    out = torch.empty(vol.shape, dtype=torch.uint8, device=vol.device)
+    L.check(L.lib().mfish_binarize_f32(vol.data_ptr(), vol.numel(), float(threshold),
+                                       minmax_dev.data_ptr() if minmax_dev is not None else None, out.data_ptr(),
+                                       _stream()))
+    return out
+
+
 # ---------------------------------------------------------- compartment masks
 def binary_morph(mask_zxy: torch.Tensor, op: str, n3d: int, n2d: int, out: torch.Tensor | None = None):
     """``n3d`` 3-D + ``n2d`` per-plane cross dilations ('dilate') or skimage-style erosions ('erode') of a
