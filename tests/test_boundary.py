@@ -96,7 +96,7 @@ print("RESULT " + json.dumps(out))
 '''
 
 
-def _run_script(tmp_path, stack, via_env=False):
+def _run_script(tmp_path, stack, via_env=False, segmentation=False):
     orig = tmp_path / "modules"
     orig.mkdir()
     (orig / "muscle_fish.py").write_text(textwrap.dedent(STUB_MF))
@@ -106,6 +106,8 @@ def _run_script(tmp_path, stack, via_env=False):
     img = np.stack([stack["img"], (stack["nuc_mask"] * 900.0 + 100.0).astype(np.float32)], axis=0)  # (c,x,y,z)
     np.savez(tmp_path / "stack.npz", img=img)
     env = {k: v for k, v in os.environ.items() if k not in ("PYTHONPATH", "MUSCLE_FISH_MODULES")}
+    # threshold_fiber / threshold_nuclei: the drop-in's own (GPU blurs + thresholds) or the original's
+    env["MFISH_DROPIN_SEGMENTATION"] = "1" if segmentation else "0"
     if via_env:
         env["PYTHONPATH"] = DROPIN
         env["MUSCLE_FISH_MODULES"] = str(orig)
@@ -215,3 +217,22 @@ def test_fish_analysis_call_sequence_end_to_end_vs_oracle(tmp_path):
     assert len(ref_spots) > 50
     assert match_fraction(got["spots"], ref_spots) >= 0.999
     assert abs(len(got["table"]) - (len(ref_data) - 1)) <= 1
+
+
+@pytest.mark.gpu
+def test_fish_analysis_call_sequence_with_the_dropin_segmentation(tmp_path):
+    """the same script with threshold_fiber / threshold_nuclei served by the drop-in as well: the fibre mask
+    equals the oracle's restatement of modules/muscle_fish.py:201-278 up to voxels within float32 rounding of
+    the threshold, and the spot calls run on it"""
+    import oracle
+    from oracle import ref_segment as S
+    import muscle_fish_b200  # noqa: F401
+    from muscle_fish_b200 import synth
+    st = synth.make_config("small")
+    out, stdout = _run_script(tmp_path, st, segmentation=True)
+    assert out["stage"] == "done", out
+    assert "Fiber threshold: " in stdout and "DAPI threshold = " in stdout
+    got = np.load(tmp_path / "out.npz")
+    ref_fiber = S.threshold_fiber(oracle.normalize_image(st["img"]))
+    assert got["fiber"].dtype == ref_fiber.dtype and (got["fiber"] != ref_fiber).mean() < 2e-3
+    assert len(got["spots"]) > 50
