@@ -405,90 +405,109 @@ def _mosaic_for(world, quick):
 
 
 def bench_slab(ctx, args):
-    """configs[3]: z-slab decomposed mosaic through parallel.slab_analyze (strong scaling), its phases, and a
-    correctness check of the slab path against one GPU on a mosaic that fits one GPU"""
+    """configs[3]: one mosaic split across the ranks (strong scaling) through parallel.slab_analyze, in the
+    mandated z-slab decomposition and in the x-slab decomposition beside it; per-phase times; and a check of
+    each decomposition against one GPU on a mosaic that fits one GPU"""
     import torch
     import torch.distributed as dist
     from muscle_fish_b200 import device as D, parallel as P, synth
     world, rank = ctx.world, ctx.rank
     edt_group = dist.new_group()
-    out = {}
 
-    def slabs(shape, ns, nn, seed):
+    def slabs(kind, shape, ns, nn, seed):
         X, Y, Z = shape
-        lay = P.SlabLayout(Z, X, Y)
-        st = synth.make_stack_device(shape, ns, nn, seed, z_range=(lay.z0, lay.z1))
+        if kind == "z":
+            lay = P.SlabLayout(Z, X, Y)
+            st = synth.make_stack_device(shape, ns, nn, seed, z_range=(lay.z0, lay.z1))
+        else:
+            lay = P.XSlabLayout(Z, X, Y)
+            st = synth.make_stack_device(shape, ns, nn, seed, x_range=(lay.x0, lay.x1))
         notnuc = (st["nuc_mask"] == 0).to(torch.uint8)
         return lay, st["img"], st["fiber_mask"], notnuc
 
+    def cleanup():
+        P.clear_buffers()
+        D.WS.clear()
+        torch.cuda.empty_cache()
+
     # -- 1. same result as one GPU (a quarter-length mosaic fits one B200)
     cshape, cns, cnn, cseed = ((4096, 2048, 200), 160000, 1000, 4) if not args.quick else ((512, 256, 48), 600, 8, 4)
-    lay, img, fib, notnuc = slabs(cshape, cns, cnn, cseed)
-    res = P.slab_analyze(img, fib, notnuc, lay, sigma=SIGMA, t_spot=T_SPOT, sampling_xyz=SAMPLING,
-                         edt_group=edt_group)
-    del img, fib, notnuc
-    P.clear_buffers()
-    D.WS.clear()
-    torch.cuda.empty_cache()
-    verdict = torch.zeros(4, dtype=torch.float64, device="cuda")
+    got = {}
+    for kind in ("z", "x"):
+        lay, img, fib, notnuc = slabs(kind, cshape, cns, cnn, cseed)
+        got[kind] = P.slab_analyze(img, fib, notnuc, lay, sigma=SIGMA, t_spot=T_SPOT, sampling_xyz=SAMPLING,
+                                   edt_group=edt_group)
+        got[kind].pop("dist_slab", None)
+        got[kind].pop("dist_xslab", None)
+        del img, fib, notnuc
+        cleanup()
+    verdict = torch.zeros(6, dtype=torch.float64, device="cuda")
     if rank == 0:
         st = synth.make_stack_device(cshape, cns, cnn, cseed)
         nn1 = (st["nuc_mask"] == 0).to(torch.uint8)
         one = D.analyze_stack(st["img"], st["fiber_mask"], nn1, SIGMA, T_SPOT, SAMPLING)
-        same_spots = np.array_equal(one["spots"], res["spots"])
-        same_dist = same_spots and np.array_equal(one["spot_dist"], res["spot_dist"])
-        verdict[:] = torch.tensor([float(same_spots), float(same_dist), len(one["spots"]), len(res["spots"])])
+        flags = []
+        for kind in ("z", "x"):
+            same_spots = np.array_equal(one["spots"], got[kind]["spots"])
+            flags += [float(same_spots), float(same_spots and np.array_equal(one["spot_dist"], got[kind]["spot_dist"]))]
+        verdict[:] = torch.tensor(flags + [len(one["spots"]), len(got["z"]["spots"])])
         del st, nn1, one
-        D.WS.clear()
-        torch.cuda.empty_cache()
+        cleanup()
     dist.broadcast(verdict, 0)
     v = verdict.tolist()
-    out["matches_n1"] = {"mosaic": list(cshape), "spots_identical": bool(v[0]), "distances_identical": bool(v[1]),
-                         "spots_one_gpu": int(v[2]), "spots_slabs": int(v[3]),
-                         "how": "spot list (coordinates, order) and per-spot distances of parallel.slab_analyze on "
-                                f"{world} ranks == device.analyze_stack on rank 0 over the same voxels, bit for bit"}
+    matches = {k: {"spots_identical": bool(v[2 * i]), "distances_identical": bool(v[2 * i + 1])}
+               for i, k in enumerate(("z_slabs", "x_slabs"))}
+    matches.update({"mosaic": list(cshape), "spots_one_gpu": int(v[4]), "spots_slabs": int(v[5]),
+                    "how": f"spot list (coordinates, order) and per-spot distances of parallel.slab_analyze on {world} "
+                           "ranks == device.analyze_stack on rank 0 over the same voxels, bit for bit"})
     ctx.barrier()
 
-    # -- 2. timing on the mosaic itself
+    # -- 2. timing on the mosaic itself, both decompositions
     shape, ns, nn, seed = _mosaic_for(world, args.quick)
     X, Y, Z = shape
-    lay, img, fib, notnuc = slabs(shape, ns, nn, seed)
     nvox = float(X) * Y * Z
-
-    def step():
-        return P.slab_analyze(img, fib, notnuc, lay, sigma=SIGMA, t_spot=T_SPOT, sampling_xyz=SAMPLING,
-                              edt_group=edt_group, full_table=False)
-
     steps = max(1, min(args.steps, args.slab_steps))
-    dt, res = ctx.timed(step, steps, 2)
-    ms = dt / steps * 1e3
-    # one more step with per-phase wall clocks (synchronising: the chains run one after the other)
-    P.PHASES = {}
-    P.slab_analyze(img, fib, notnuc, lay, sigma=SIGMA, t_spot=T_SPOT, sampling_xyz=SAMPLING, full_table=False)
-    phases = {k: round(v * 1e3, 3) for k, v in P.PHASES.items()}
-    P.PHASES = None
+    out = {"matches_n1": matches, "mosaic": [X, Y, Z], "n_gpus": world, "unit": UNIT, "steps": steps,
+           "scaling": "strong", "nvlink_peer_copy_reference_gbs": 770.0}
     radius = 8
-    halo_bytes = 2 * (radius + 1) * X * Y * 4  # received by an interior rank
-    a2a_bytes = (Z / world) * X * Y * 4 * (world - 1) / world  # sent by every rank
-    out.update({
-        "workload": f"configs[3]: mosaic {X}x{Y}x{Z} in {world} z-slabs, parallel.slab_analyze (spot path + EDT + "
-                    f"per-spot distances), device-resident slabs",
-        "mosaic": [X, Y, Z], "n_gpus": world, "ms_per_step": ms, "value": nvox / ms / 1e6, "unit": UNIT,
-        "steps": steps, "found_spots": int(len(res["spots"])), "scaling": "strong",
-        "phases_ms_serialised": phases,
-        "nvlink": {
-            "halo_bytes_in_per_rank": int(halo_bytes),
-            "halo_gbs": halo_bytes / max(phases.get("halo", 0.0), 1e-9) / 1e6 if "halo" in phases else None,
-            "all_to_all_bytes_out_per_rank": int(a2a_bytes),
-            "all_to_all_gbs": a2a_bytes / max(phases.get("edt_all_to_all", 0.0), 1e-9) / 1e6
-            if "edt_all_to_all" in phases else None,
-            "peer_copy_reference_gbs": 770.0},
-        "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9,
-    })
-    del img, fib, notnuc
-    P.clear_buffers()
-    D.WS.clear()
-    torch.cuda.empty_cache()
+    for kind in ("z", "x"):
+        lay, img, fib, notnuc = slabs(kind, shape, ns, nn, seed)
+
+        def step():
+            return P.slab_analyze(img, fib, notnuc, lay, sigma=SIGMA, t_spot=T_SPOT, sampling_xyz=SAMPLING,
+                                  edt_group=edt_group, full_table=False)
+
+        torch.cuda.reset_peak_memory_stats()
+        dt, res = ctx.timed(step, steps, 2)
+        ms = dt / steps * 1e3
+        # one more step with per-phase wall clocks (synchronising: the two chains then run one after the other)
+        P.PHASES = {}
+        P.slab_analyze(img, fib, notnuc, lay, sigma=SIGMA, t_spot=T_SPOT, sampling_xyz=SAMPLING, full_table=False)
+        phases = {k: round(val * 1e3, 3) for k, val in P.PHASES.items()}
+        P.PHASES = None
+        if kind == "z":
+            halo_bytes = 2 * (radius + 1) * X * Y * 4  # received by an interior rank
+            a2a_bytes = (Z / world) * X * Y * 4 * (world - 1) / world  # sent by every rank (int32 f2)
+        else:
+            halo_bytes = 2 * 12 * Z * Y * 4
+            a2a_bytes = Z * (X / world) * Y * 2 * (world - 1) / world  # uint16 row distances
+        gbs = lambda nbytes, key: (nbytes / (phases[key] * 1e-3) / 1e9) if phases.get(key, 0) > 0 else None
+        out[kind + "_slabs"] = {
+            "workload": f"configs[3]: mosaic {X}x{Y}x{Z} in {world} {kind}-slabs, parallel.slab_analyze (spot path + "
+                        "EDT + per-spot distances), device-resident slabs",
+            "ms_per_step": ms, "value": nvox / ms / 1e6, "found_spots": int(len(res["spots"])),
+            "phases_ms_serialised": phases,
+            "halo_bytes_in_per_rank": int(halo_bytes), "halo_gbs": gbs(halo_bytes, "halo"),
+            "all_to_all_bytes_out_per_rank": int(a2a_bytes), "all_to_all_gbs": gbs(a2a_bytes, "edt_all_to_all"),
+            "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9,
+        }
+        del img, fib, notnuc, res
+        cleanup()
+        ctx.barrier()
+    # the headline of the object: the mandated decomposition; the comparison beside it
+    out["ms_per_step"] = out["z_slabs"]["ms_per_step"]
+    out["value"] = out["z_slabs"]["value"]
+    out["workload"] = out["z_slabs"]["workload"]
     return out
 
 

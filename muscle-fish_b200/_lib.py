@@ -65,6 +65,8 @@ SIGNATURES = {
     "mfish_scale_planes_f32": (_i, [_p, _p, _i64, _i64, _i64, _p, _p]),
     "mfish_edt_workspace_bytes": (_i64, [_i64, _i64, _i64]),
     "mfish_edt3d_u8": (_i, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p]),
+    "mfish_edt_rowscan_u8": (_i, [_p, _i64, _i64, _p, _p]),
+    "mfish_edt_xpass_u16": (_i, [_p, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _p]),
     "mfish_edt_inplane_u8": (_i, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p]),
     "mfish_edt_zpass": (_i, [_p, _i, _i64, _i64, _i64, _p, _i64, _p, _p, _p, _p]),
     "mfish_export_f64": (_i, [_p, _i64, _i64, _i64, _i, _p, _p]),

@@ -585,39 +585,59 @@ static int edt_spacing(const double* spacing_zxy_host, double& wz, double& wx, d
 
 // passes 1 + 2: squared in-plane distance.  *f2_kind_host tells how f2 is encoded:
 // MFISH_EDT_F2_I32 (exact integer voxel^2, x and y spacing equal) or MFISH_EDT_F2_F32 (physical^2).
+// pass 1 alone: |dy| to the nearest zero voxel of every row (u16, 0xFFFF = none)
+extern "C" int mfish_edt_rowscan_u8(const uint8_t* mask_dev, int64_t nrows, int64_t ny, uint16_t* dy_out_dev,
+                                    void* stream) {
+  MFISH_REQUIRE(mask_dev && dy_out_dev, "edt: null pointer");
+  MFISH_REQUIRE(nrows > 0 && ny > 0, "edt: empty volume");
+  return launch_scan_y(mask_dev, dy_out_dev, nrows, ny, 0, as_stream(stream));
+}
+
+// pass 2 alone, on row distances: lower envelope along x.  ny_full = length of the rows the distances were
+// measured over (a y-slab of a wider mosaic holds |dy| up to ny_full - 1).  link_ws_dev: nz*nx*ny*4 bytes.
+extern "C" int mfish_edt_xpass_u16(const uint16_t* dy_dev, int64_t nz, int64_t nx, int64_t ny, int64_t ny_full,
+                                   const double* spacing_zxy_host, void* f2_out_dev, int* f2_kind_host,
+                                   void* link_ws_dev, void* stream) {
+  MFISH_REQUIRE(dy_dev && link_ws_dev && f2_out_dev && f2_kind_host, "edt: null pointer");
+  MFISH_REQUIRE(nz > 0 && nx > 0 && ny > 0, "edt: empty volume");
+  MFISH_REQUIRE(nz < (1 << 24) && nx < (1 << 24), "edt: dimension too large");
+  if (ny_full < ny) ny_full = ny;
+  MFISH_REQUIRE(ny_full < 65535, "edt: ny must be < 65535 (u16 row distances)");
+  double wz, wx, wy;
+  int rc = edt_spacing(spacing_zxy_host, wz, wx, wy);
+  if (rc != MFISH_OK) return rc;
+  const double plane_sq = (double)(nx - 1) * (nx - 1) + (double)(ny_full - 1) * (ny_full - 1);
+  const bool plane_int = (wx == wy) && plane_sq < 2147483000.0;
+  cudaStream_t st = as_stream(stream);
+  const bool link16 = nx <= 32767;
+  if (plane_int) {
+    *f2_kind_host = MFISH_EDT_F2_I32;
+    // all-integer hull tests need max(F) + L^2 = (ny-1)^2 + nx^2 below 2^31
+    const bool int_arith = (double)(ny_full - 1) * (ny_full - 1) + (double)nx * nx < 2147483000.0;
+    if (int_arith)
+      return launch_env_l<uint16_t, EDT_OUT_I32, 0, true>(dy_dev, link_ws_dev, link16, f2_out_dev, nullptr,
+                                                          MFISH_AXIS_X, nz, nx, ny, 1.0, 1.0, 1.0, st);
+    return launch_env_l<uint16_t, EDT_OUT_I32, 0, false>(dy_dev, link_ws_dev, link16, f2_out_dev, nullptr,
+                                                         MFISH_AXIS_X, nz, nx, ny, 1.0, 1.0, 1.0, st);
+  }
+  *f2_kind_host = MFISH_EDT_F2_F32;
+  return launch_env_l<uint16_t, EDT_OUT_F32, 0, false>(dy_dev, link_ws_dev, link16, f2_out_dev, nullptr, MFISH_AXIS_X,
+                                                       nz, nx, ny, wy * wy, wx * wx, 1.0, st);
+}
+
 extern "C" int mfish_edt_inplane_u8(const uint8_t* mask_dev, int64_t nz, int64_t nx, int64_t ny,
                                     const double* spacing_zxy_host, void* f2_out_dev, int* f2_kind_host,
                                     void* workspace_dev, void* stream) {
   MFISH_REQUIRE(mask_dev && workspace_dev && f2_out_dev && f2_kind_host, "edt: null pointer");
   MFISH_REQUIRE(nz > 0 && nx > 0 && ny > 0, "edt: empty volume");
   MFISH_REQUIRE(ny < 65535, "edt: ny must be < 65535 (u16 row distances)");
-  MFISH_REQUIRE(nz < (1 << 24) && nx < (1 << 24), "edt: dimension too large");
-  double wz, wx, wy;
-  int rc = edt_spacing(spacing_zxy_host, wz, wx, wy);
-  if (rc != MFISH_OK) return rc;
-  const double plane_sq = (double)(nx - 1) * (nx - 1) + (double)(ny - 1) * (ny - 1);
-  const bool plane_int = (wx == wy) && plane_sq < 2147483000.0;
-  cudaStream_t st = as_stream(stream);
   const int64_t n = nz * nx * ny;
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace_dev);
   uint16_t* dy = reinterpret_cast<uint16_t*>(ws);
   void* link = ws + align256(n * 2);
-  rc = launch_scan_y(mask_dev, dy, nz * nx, ny, 0, st);
+  int rc = launch_scan_y(mask_dev, dy, nz * nx, ny, 0, as_stream(stream));
   if (rc != MFISH_OK) return rc;
-  const bool link16 = nx <= 32767;
-  if (plane_int) {
-    *f2_kind_host = MFISH_EDT_F2_I32;
-    // all-integer hull tests need max(F) + L^2 = (ny-1)^2 + nx^2 below 2^31
-    const bool int_arith = (double)(ny - 1) * (ny - 1) + (double)nx * nx < 2147483000.0;
-    if (int_arith)
-      return launch_env_l<uint16_t, EDT_OUT_I32, 0, true>(dy, link, link16, f2_out_dev, nullptr, MFISH_AXIS_X, nz, nx,
-                                                          ny, 1.0, 1.0, 1.0, st);
-    return launch_env_l<uint16_t, EDT_OUT_I32, 0, false>(dy, link, link16, f2_out_dev, nullptr, MFISH_AXIS_X, nz, nx,
-                                                         ny, 1.0, 1.0, 1.0, st);
-  }
-  *f2_kind_host = MFISH_EDT_F2_F32;
-  return launch_env_l<uint16_t, EDT_OUT_F32, 0, false>(dy, link, link16, f2_out_dev, nullptr, MFISH_AXIS_X, nz, nx, ny,
-                                                       wy * wy, wx * wx, 1.0, st);
+  return mfish_edt_xpass_u16(dy, nz, nx, ny, ny, spacing_zxy_host, f2_out_dev, f2_kind_host, link, stream);
 }
 
 // pass 3 along z.  link_ws_dev: nz*nx*ny*4 bytes of scratch.

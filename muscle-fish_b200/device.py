@@ -744,6 +744,30 @@ def edt_inplane(mask_zxy: torch.Tensor, sampling_xyz=None, out: torch.Tensor | N
     return f2, kind.value
 
 
+def edt_rowscan(mask_zxy: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """pass 1 alone: uint16 distance along y to the nearest zero voxel of each row (0xFFFF = none)"""
+    nz, nx, ny = mask_zxy.shape
+    dy = out if out is not None else torch.empty((nz, nx, ny), dtype=torch.uint16, device=mask_zxy.device)
+    L.check(L.lib().mfish_edt_rowscan_u8(mask_zxy.data_ptr(), nz * nx, ny, dy.data_ptr(), _stream()))
+    return dy
+
+
+def edt_xpass(dy: torch.Tensor, sampling_xyz=None, ny_full=None, out: torch.Tensor | None = None):
+    """pass 2 alone on row distances [nz,nx,ny] (possibly a y-slab of rows ``ny_full`` long): squared in-plane
+    distance (int32 or float32) + its kind"""
+    import ctypes
+    nz, nx, ny = dy.shape
+    sx, sy, sz = [float(s) for s in (sampling_xyz or (1.0, 1.0, 1.0))]
+    link = WS.get("edt_link", (nz * nx * ny,), torch.int32, dy.device)
+    f2 = out if out is not None else torch.empty((nz, nx, ny), dtype=torch.int32, device=dy.device)
+    kind = ctypes.c_int(-1)
+    L.check(L.lib().mfish_edt_xpass_u16(dy.data_ptr(), nz, nx, ny, int(ny_full or ny), L.darray([sz, sx, sy]),
+                                        f2.data_ptr(), ctypes.byref(kind), link.data_ptr(), _stream()))
+    if kind.value == L.EDT_F2_F32:
+        f2 = f2.view(torch.float32)
+    return f2, kind.value
+
+
 def edt_zpass(f2: torch.Tensor, kind: int, sampling_xyz=None, out: torch.Tensor | None = None, plane_xy=None):
     """z pass on (possibly re-partitioned) in-plane squared distances -> float32 distances.
     ``plane_xy=(nx, ny)``: extents of the plane the in-plane pass ran over when ``f2`` is an x-slab of

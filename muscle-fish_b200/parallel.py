@@ -237,6 +237,27 @@ class SlabLayout:
         return min(e - b for b, e in self.zb)
 
 
+class XSlabLayout:
+    """x-slab ownership (filters, NMS, row scan) and y-slab ownership (EDT envelope passes) of a [nz][nx][ny]
+    mosaic.  x is the fibre axis of a stitched mosaic (16384 of 16384 x 2048 x 200): slabs along it pay a
+    12-row halo on 2048 own rows (1 %), where 25-plane z-slabs pay 9 + 9 planes (72 %)."""
+
+    def __init__(self, nz, nx, ny, rank=None, world=None):
+        self.nz, self.nx, self.ny = int(nz), int(nx), int(ny)
+        self.rank = dist.get_rank() if rank is None else rank
+        self.world = dist.get_world_size() if world is None else world
+        self.xb = split_bounds(self.nx, self.world)
+        self.yb = split_bounds(self.ny, self.world)
+
+    x0 = property(lambda self: self.xb[self.rank][0])
+    x1 = property(lambda self: self.xb[self.rank][1])
+    y0 = property(lambda self: self.yb[self.rank][0])
+    y1 = property(lambda self: self.yb[self.rank][1])
+
+    def min_slab(self):
+        return min(e - b for b, e in self.xb)
+
+
 # ----------------------------------------------------------------------------- communication
 def exchange_halo(slab: torch.Tensor, halo: int, lay: SlabLayout, group=None):
     """Append up to `halo` planes of each z-neighbour.  Returns (ext, lo, hi): the extended slab and
@@ -264,6 +285,65 @@ def exchange_halo(slab: torch.Tensor, halo: int, lay: SlabLayout, group=None):
     for w in dist.batch_isend_irecv(ops):
         w.wait()
     return ext, lo, hi
+
+
+def exchange_halo_x(slab: torch.Tensor, halo: int, lay: "XSlabLayout", group=None):
+    """x-slab [nz][nx_local][ny]: append up to `halo` x-rows of each x-neighbour.  Returns (ext, lo, hi)."""
+    r, P = lay.rank, lay.world
+    if halo <= 0 or P == 1:
+        return slab, 0, 0
+    if lay.min_slab() < halo:
+        raise ValueError(f"slab width {lay.min_slab()} < halo {halo}: use fewer ranks for this mosaic")
+    lo = halo if r > 0 else 0
+    hi = halo if r < P - 1 else 0
+    nz, nxl, ny = slab.shape
+    ext = _buf("halo_ext_x", (nz, lo + nxl + hi, ny), slab.dtype, slab.device)
+    ext[:, lo:lo + nxl] = slab
+    ops, keep = [], []
+    if r > 0:
+        snd = slab[:, :halo].contiguous()
+        rcv = _buf("halo_rx_lo", (nz, halo, ny), slab.dtype, slab.device)
+        keep.append((rcv, slice(0, lo)))
+        ops += [dist.P2POp(dist.isend, snd, r - 1, group), dist.P2POp(dist.irecv, rcv, r - 1, group)]
+    if r < P - 1:
+        snd2 = slab[:, nxl - halo:].contiguous()
+        rcv2 = _buf("halo_rx_hi", (nz, halo, ny), slab.dtype, slab.device)
+        keep.append((rcv2, slice(lo + nxl, lo + nxl + hi)))
+        ops += [dist.P2POp(dist.isend, snd2, r + 1, group), dist.P2POp(dist.irecv, rcv2, r + 1, group)]
+    for w in dist.batch_isend_irecv(ops):
+        w.wait()
+    for buf, sl in keep:
+        ext[:, sl] = buf
+    return ext, lo, hi
+
+
+def repartition_x_to_y(t: torch.Tensor, lay: "XSlabLayout", group=None) -> torch.Tensor:
+    """[nz][nx_local][ny] (x-slab) -> [nz][nx][ny_local] (y-slab): the all-to-all between the EDT's row scan and
+    its two envelope passes (2 bytes per voxel on the wire: the row distances are uint16)."""
+    P, r = lay.world, lay.rank
+    if P == 1:
+        return t
+    nz = lay.nz
+    out = _buf("x2y_out", (nz, lay.nx, lay.y1 - lay.y0), t.dtype, t.device)
+    ops, recvs = [], {}
+    for s in range(P):
+        if s == r:
+            continue
+        yb, ye = lay.yb[s]
+        snd = _buf(f"x2y_send{s}", (nz, t.shape[1], ye - yb), t.dtype, t.device)
+        snd.copy_(t[:, :, yb:ye])
+        xb, xe = lay.xb[s]
+        rcv = _buf(f"x2y_recv{s}", (nz, xe - xb, lay.y1 - lay.y0), t.dtype, t.device)
+        recvs[s] = rcv
+        ops.append(dist.P2POp(dist.isend, snd, s, group))
+        ops.append(dist.P2POp(dist.irecv, rcv, s, group))
+    out[:, lay.x0:lay.x1] = t[:, :, lay.y0:lay.y1]
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    for s, rcv in recvs.items():
+        out[:, lay.xb[s][0]:lay.xb[s][1]] = rcv
+    return out
 
 
 def repartition_z_to_x(t: torch.Tensor, lay: SlabLayout, group=None) -> torch.Tensor:
@@ -360,6 +440,22 @@ class DeviceOps:
     def masked_quantile(self, vol, mask, q, reduce):
         return self.D.masked_quantile_distributed(vol, mask, q, reduce)
 
+    def log_peaks(self, ext, mm, sigma, thr):
+        """LoG + thresholded NMS of a whole (extended) slab in one library call
+        -> (raster (x*ny + y)*nz + z int64 [n], value float32 [n]), unordered"""
+        out = _buf("log_ext", ext.shape, torch.float32, ext.device)
+        _, finish = self.D.log_peaks_async(self.D.Volume(ext, mm), sigma, thr, out=out)
+        return finish()
+
+    def edt_rowscan(self, mask):
+        return self.D.edt_rowscan(mask, out=_buf("edt_dy", mask.shape, torch.uint16, mask.device))
+
+    def edt_xz(self, dy, sampling_xyz, ny_full):
+        """both envelope passes on row distances [nz][nx][ny_local] -> float32 distances, same layout"""
+        f2, kind = self.D.edt_xpass(dy, sampling_xyz, ny_full, out=_buf("edt_f2y", dy.shape, torch.int32, dy.device))
+        return self.D.edt_zpass(f2, kind, sampling_xyz, out=_buf("edt_disty", dy.shape, torch.float32, dy.device),
+                                plane_xy=(dy.shape[1], ny_full))
+
     def edt_inplane(self, mask, sampling_xyz):
         return self.D.edt_inplane(mask, sampling_xyz, out=_buf("edt_f2", mask.shape, torch.int32, mask.device))
 
@@ -369,15 +465,87 @@ class DeviceOps:
 
 
 # ------------------------------------------------------------------------ slab-mode pipeline
-def slab_find_spots_snrfilter(img_slab: torch.Tensor, mask_slab: torch.Tensor, lay: SlabLayout, sigma=2.0,
+class _ZDecomp:
+    """z-slabs [nz_local][nx][ny]: what differs between the decompositions of the spot pipeline"""
+
+    def __init__(self, lay: SlabLayout):
+        self.lay = lay
+
+    def detect(self, ops, img_slab, mm, sigma, t_spot, radius, group):
+        """halo exchange + LoG + NMS; -> (extended slab, GLOBAL raster of the own peaks, their values)"""
+        lay = self.lay
+        nz = lay.nz
+        # r planes for the z filter pass + 1 plane of LoG for the NMS (the blur at the spots reaches 1 plane)
+        with _phase("halo"):
+            ext, lo, hi = exchange_halo(img_slab, radius + 1, lay, group)
+        self.lo = lo
+        # LoG on the extended slab (planes within `radius` of an interior cut are contaminated by the boundary
+        # rule and are not used); reflect applies only at the global faces
+        a = radius if lo else 0
+        b = ext.shape[0] - (radius if hi else 0)
+        with _phase("log"):
+            log_ext = ops.log(ext, mm, sigma, z_range=(a, b))
+        nzs = b - a
+        with _phase("peaks"):
+            ras_l, val = ops.peaks(log_ext[a:b], t_spot)
+            # local raster ((x*ny + y)*nzs + zs) -> global raster ((x*ny + y)*nz + zg); keep own planes
+            zs = ras_l % nzs
+            xy = ras_l // nzs
+            zg = zs + (a - lo + lay.z0)
+            own = (zg >= lay.z0) & (zg < lay.z1)
+            return ext, (xy * nz + zg)[own], val[own]
+
+    def own(self, z, x, y):
+        return (z >= self.lay.z0) & (z < self.lay.z1)
+
+    def mask_pts(self, z, x, y):
+        return torch.stack([z - self.lay.z0, x, y], dim=1)
+
+    def ext_pts(self, z, x, y):
+        return torch.stack([z - self.lay.z0 + self.lo, x, y], dim=1)
+
+
+class _XDecomp:
+    """x-slabs [nz][nx_local][ny]"""
+
+    def __init__(self, lay: XSlabLayout):
+        self.lay = lay
+
+    def detect(self, ops, img_slab, mm, sigma, t_spot, radius, group):
+        lay = self.lay
+        nz, ny = lay.nz, lay.ny
+        # radius rows for the x filter pass + 1 row of LoG for the NMS; the blur at the spots (sigma 3) reaches 12
+        with _phase("halo"):
+            ext, lo, hi = exchange_halo_x(img_slab, max(radius + 1, 12), lay, group)
+        self.lo = lo
+        with _phase("log"):
+            ras_l, val = ops.log_peaks(ext, mm, sigma, t_spot)  # raster (x_e*ny + y)*nz + z over the extended slab
+        with _phase("peaks"):
+            xe = ras_l // (ny * nz)
+            own = (xe >= lo) & (xe < lo + img_slab.shape[1])
+            return ext, ras_l[own] + (lay.x0 - lo) * ny * nz, val[own]
+
+    def own(self, z, x, y):
+        return (x >= self.lay.x0) & (x < self.lay.x1)
+
+    def mask_pts(self, z, x, y):
+        return torch.stack([z, x - self.lay.x0, y], dim=1)
+
+    def ext_pts(self, z, x, y):
+        return torch.stack([z, x - self.lay.x0 + self.lo, y], dim=1)
+
+
+def slab_find_spots_snrfilter(img_slab: torch.Tensor, mask_slab: torch.Tensor, lay, sigma=2.0,
                               t_spot=0.025, snr=None, ops=None, group=None, full_table=True):
-    """``find_spots_snrfilter`` (modules/muscle_fish.py:281-402) on a z-slab decomposed mosaic.
-    ``img_slab`` float32 / ``mask_slab`` uint8, both ``[nz_local][nx][ny]``.  Every rank returns the
-    same global result: dict(spots (N,4) float64 [x,y,z,sigma], spots_masked, intensity, baseline, snr).
+    """``find_spots_snrfilter`` (modules/muscle_fish.py:281-402) on a slab-decomposed mosaic: ``lay`` a
+    ``SlabLayout`` (z-slabs ``[nz_local][nx][ny]``) or an ``XSlabLayout`` (x-slabs ``[nz][nx_local][ny]``);
+    ``img_slab`` float32 / ``mask_slab`` uint8.  Every rank returns the same global result:
+    dict(spots (N,4) float64 [x,y,z,sigma], spots_masked, intensity, baseline, snr).
     ``full_table=False`` skips the host copy of the per-spot table of ALL mask-passing spots
     (``spots_masked`` / ``intensity``, the reference's ``spot_data``) and returns only the kept spots."""
     with _phase("setup"):
         ops = ops or DeviceOps()
+        dec = _XDecomp(lay) if isinstance(lay, XSlabLayout) else _ZDecomp(lay)
     dev = img_slab.device
     nz, nx, ny = lay.nz, lay.nx, lay.ny
     # 1. global min / max
@@ -389,26 +557,9 @@ def slab_find_spots_snrfilter(img_slab: torch.Tensor, mask_slab: torch.Tensor, l
         dist.all_reduce(hi_t, op=dist.ReduceOp.MAX, group=group)
         mm = torch.cat([lo_t, hi_t])
         lo_v, hi_v = float(lo_t.item()), float(hi_t.item())
-    # 2. halo of raw input: r planes for the z filter pass + 1 plane of LoG for the NMS
+    # 2./3. halo of raw input, LoG and NMS on the extended slab; every rank keeps the peaks it owns
     radius = T.gaussian_radius(sigma)
-    with _phase("halo"):
-        ext, lo, hi = exchange_halo(img_slab, radius + 1, lay, group)
-    # 3. LoG on the extended slab (planes within `radius` of an interior cut are contaminated by the
-    #    boundary rule and are not used); reflect applies only at the global faces
-    a = radius if lo else 0
-    b = ext.shape[0] - (radius if hi else 0)
-    with _phase("log"):
-        log_ext = ops.log(ext, mm, sigma, z_range=(a, b))
-    nzs = b - a
-    with _phase("peaks"):
-        ras_l, val = ops.peaks(log_ext[a:b], t_spot)
-        # local raster ((x*ny + y)*nzs + zs) -> global raster ((x*ny + y)*nz + zg); keep own planes
-        zs = ras_l % nzs
-        xy = ras_l // nzs
-        zg = zs + (a - lo + lay.z0)
-        own = (zg >= lay.z0) & (zg < lay.z1)
-        ras_g = (xy * nz + zg)[own]
-        val = val[own]
+    ext, ras_g, val = dec.detect(ops, img_slab, mm, sigma, t_spot, radius, group)
     # 4. all-gather the peak lists (padded to the longest), prune identically everywhere
     with _phase("gather_peaks"):
         n_loc = torch.tensor([ras_g.numel()], dtype=torch.int64, device=dev)
@@ -439,16 +590,16 @@ def slab_find_spots_snrfilter(img_slab: torch.Tensor, mask_slab: torch.Tensor, l
         t = ranked // nz
         y = t % ny
         x = t // ny
-    # 5. mask filter + 7. blurred intensity: the owner of each spot (its z-slab) evaluates both on its
+    # 5. mask filter + 7. blurred intensity: the owner of each spot (its slab) evaluates both on its
     #    mask slab / extended raw slab; one all-reduce carries them to every rank
-    ownz = (z >= lay.z0) & (z < lay.z1)
+    ownz = dec.own(z, x, y)
     with _phase("mask_blur"):
         both = torch.zeros((2, ranked.numel()), dtype=torch.float64, device=dev)
         if bool(ownz.any()):
             zo, xo, yo = z[ownz], x[ownz], y[ownz]
-            inm = ops.gather_u8(mask_slab, torch.stack([zo - lay.z0, xo, yo], dim=1))
+            inm = ops.gather_u8(mask_slab, dec.mask_pts(zo, xo, yo))
             both[0, ownz] = (inm != 0).to(torch.float64)
-            both[1, ownz] = ops.blur_at_points(ext, mm, torch.stack([zo - lay.z0 + lo, xo, yo], dim=1), (3, 3, 0.3))
+            both[1, ownz] = ops.blur_at_points(ext, mm, dec.ext_pts(zo, xo, yo), (3, 3, 0.3))
         dist.all_reduce(both, op=dist.ReduceOp.SUM, group=group)
     # 6. P25 baseline over the (global) mask
     def reduce_hist(h):
@@ -530,22 +681,58 @@ def slab_spot_distances(dist_xslab: torch.Tensor, spots_xyz: np.ndarray, lay: Sl
     return out.cpu().numpy()
 
 
-def slab_analyze(img_slab: torch.Tensor, mask_slab: torch.Tensor, notnuc_slab: torch.Tensor, lay: SlabLayout,
+def xslab_edt(notnuc_slab: torch.Tensor, lay: XSlabLayout, sampling_xyz=(1.0, 1.0, 1.0), ops=None, group=None):
+    """The distance transform on an x-slab decomposed mask ``[nz][nx_local][ny]``: row scan on the x-slab, ONE
+    all-to-all of the uint16 row distances into y-slabs, both envelope passes there.  Returns the distance
+    map in y-slab layout ``[nz][nx][ny_local]``."""
+    ops = ops or DeviceOps()
+    with _phase("edt_rowscan"):
+        dy = ops.edt_rowscan(notnuc_slab)
+    with _phase("edt_all_to_all"):
+        wire = dy.view(torch.int16) if dy.dtype == torch.uint16 else dy  # NCCL has no uint16
+        dyy = repartition_x_to_y(wire, lay, group)
+        dyy = dyy.view(torch.uint16) if dy.dtype == torch.uint16 else dyy
+    with _phase("edt_xz"):
+        return ops.edt_xz(dyy, sampling_xyz, lay.ny)
+
+
+def xslab_spot_distances(dist_yslab: torch.Tensor, spots_xyz: np.ndarray, lay: XSlabLayout, ops=None, group=None):
+    """EDT value at each spot from the y-slab partitioned distance map; every rank gets the full vector."""
+    ops = ops or DeviceOps()
+    dev = dist_yslab.device
+    s = torch.as_tensor(np.ascontiguousarray(np.asarray(spots_xyz)[:, :3]).astype(np.int64)).to(dev)
+    out = torch.zeros(s.shape[0], dtype=torch.float64, device=dev)
+    if s.shape[0]:
+        y = s[:, 1]
+        own = (y >= lay.y0) & (y < lay.y1)
+        if bool(own.any()):
+            so = s[own]
+            loc = torch.stack([so[:, 2], so[:, 0], so[:, 1] - lay.y0], dim=1)
+            out[own] = ops.gather_f32(dist_yslab, loc).to(torch.float64)
+    dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
+    return out.cpu().numpy()
+
+
+def slab_analyze(img_slab: torch.Tensor, mask_slab: torch.Tensor, notnuc_slab: torch.Tensor, lay,
                  sigma=2.0, t_spot=0.025, sampling_xyz=(1.0, 1.0, 1.0), snr=None, ops=None, group=None,
                  edt_group=None, full_table=True):
-    """The whole path on a z-slab decomposed mosaic: ``slab_find_spots_snrfilter`` + ``slab_edt`` +
-    ``slab_spot_distances``.  The distance transform does not depend on the spots and its chain has no
-    host round trip: given ``edt_group`` (a second communicator over the same ranks, ``dist.new_group()``)
-    on CUDA tensors it is queued first on a side stream, so its all-to-all and kernels run beside the
-    spot chain's halo exchange, small collectives and host round trips.  Returns the spot dict plus
-    ``spot_dist`` (float64 per kept spot) and ``dist_xslab`` (the x-slab partitioned distance map)."""
+    """The whole path on a slab-decomposed mosaic (``lay``: ``SlabLayout`` = z-slabs, ``XSlabLayout`` = x-slabs):
+    ``slab_find_spots_snrfilter`` + the distance transform + the per-spot distances.  The distance transform
+    does not depend on the spots and its chain has no host round trip: given ``edt_group`` (a second
+    communicator over the same ranks, ``dist.new_group()``) on CUDA tensors it is queued first on a side
+    stream, so its all-to-all and kernels run beside the spot chain's halo exchange, small collectives and
+    host round trips.  Returns the spot dict plus ``spot_dist`` (float64 per kept spot) and ``dist_slab`` (the
+    distance map: x-slab partitioned for z-slab input, y-slab partitioned for x-slab input)."""
+    xs = isinstance(lay, XSlabLayout)
+    edt_fn = xslab_edt if xs else slab_edt
+    dist_fn = xslab_spot_distances if xs else slab_spot_distances
     if edt_group is not None and img_slab.is_cuda:
         from . import device as D
         cur = torch.cuda.current_stream()
         side = D._side_stream()
         side.wait_stream(cur)
         with torch.cuda.stream(side):
-            dmap = slab_edt(notnuc_slab, lay, sampling_xyz, ops=ops, group=edt_group)
+            dmap = edt_fn(notnuc_slab, lay, sampling_xyz, ops=ops, group=edt_group)
         res = slab_find_spots_snrfilter(img_slab, mask_slab, lay, sigma=sigma, t_spot=t_spot, snr=snr, ops=ops,
                                         group=group, full_table=full_table)
         cur.wait_stream(side)
@@ -553,7 +740,9 @@ def slab_analyze(img_slab: torch.Tensor, mask_slab: torch.Tensor, notnuc_slab: t
     else:
         res = slab_find_spots_snrfilter(img_slab, mask_slab, lay, sigma=sigma, t_spot=t_spot, snr=snr, ops=ops,
                                         group=group, full_table=full_table)
-        dmap = slab_edt(notnuc_slab, lay, sampling_xyz, ops=ops, group=group)
-    res["spot_dist"] = slab_spot_distances(dmap, res["spots"], lay, ops=ops, group=group)
-    res["dist_xslab"] = dmap
+        dmap = edt_fn(notnuc_slab, lay, sampling_xyz, ops=ops, group=group)
+    res["spot_dist"] = dist_fn(dmap, res["spots"], lay, ops=ops, group=group)
+    res["dist_slab"] = dmap
+    if not xs:
+        res["dist_xslab"] = dmap
     return res

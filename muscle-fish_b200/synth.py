@@ -130,10 +130,11 @@ def make_threshold_stack(shape=(72, 72, 24)):
     return img
 
 
-def make_stack_device(shape, n_spots, n_nuclei, seed, device="cuda", z_first=True, z_range=None):
+def make_stack_device(shape, n_spots, n_nuclei, seed, device="cuda", z_first=True, z_range=None, x_range=None):
     """Same distribution drawn on the GPU with torch (bench inputs only).
 
-    ``z_range=(z0, z1)`` draws only those planes of the stack (one z-slab of a mosaic): spots,
+    ``z_range=(z0, z1)`` / ``x_range=(x0, x1)`` draw only those planes / x-rows of the stack (one slab of a
+    mosaic): spots,
     fibre and nuclei are the global ones and the noise is seeded per global plane, so the slabs of any
     decomposition are exactly the planes of the whole stack.
 
@@ -146,15 +147,22 @@ def make_stack_device(shape, n_spots, n_nuclei, seed, device="cuda", z_first=Tru
 
     X, Y, Z = shape
     za, zb = (0, Z) if z_range is None else (int(z_range[0]), int(z_range[1]))
-    ZL = zb - za
+    xa, xb_ = (0, X) if x_range is None else (int(x_range[0]), int(x_range[1]))
+    ZL, XL = zb - za, xb_ - xa
     rng = np.random.default_rng(seed)
     g = torch.Generator(device=device)
-    img = torch.empty((ZL, X, Y), dtype=torch.float32, device=device)
+    img = torch.empty((ZL, XL, Y), dtype=torch.float32, device=device)
+    plane = torch.empty((X, Y), dtype=torch.float32, device=device) if XL != X else None
     for z in range(za, zb):  # one noise stream per GLOBAL plane: a slab of any decomposition draws the same voxels
         g.manual_seed((int(seed) * 1000003 + z * 7919) & 0x7FFFFFFFFFFFFFFF)
-        img[z - za].normal_(100.0, 10.0, generator=g)
+        if plane is None:
+            img[z - za].normal_(100.0, 10.0, generator=g)
+        else:
+            plane.normal_(100.0, 10.0, generator=g)
+            img[z - za] = plane[xa:xb_]
+    del plane
     y0, y1, z0, z1 = _fiber_bounds(shape)
-    fiber = torch.zeros((ZL, X, Y), dtype=torch.uint8, device=device)
+    fiber = torch.zeros((ZL, XL, Y), dtype=torch.uint8, device=device)
     fz0, fz1 = max(z0, za) - za, min(z1, zb) - za
     if fz1 > fz0:
         fiber[fz0:fz1, :, y0:y1] = 1
@@ -167,12 +175,13 @@ def make_stack_device(shape, n_spots, n_nuclei, seed, device="cuda", z_first=Tru
     cz = rng.uniform(z0 + mz, z1 - mz, n_spots)
     amp = rng.uniform(300.0, 1500.0, n_spots)
     hx, hz = 6, 3
-    near = (cz >= za - hz - 1) & (cz <= zb + hz + 1)  # spots that can touch this slab
+    near = ((cz >= za - hz - 1) & (cz <= zb + hz + 1)  # spots that can touch this slab
+            & (cx >= xa - hx - 1) & (cx <= xb_ + hx + 1))
     cx, cy, cz, amp = cx[near], cy[near], cz[near], amp[near]
     n_spots = int(near.sum())
     # spot patches are accumulated as 2^-16 fixed-point integers: integer atomics commute, so the voxels do
     # not depend on the order the patches land in, nor on which slab of a decomposition draws them
-    acc = torch.zeros(ZL * X * Y, dtype=torch.int64, device=device)
+    acc = torch.zeros(ZL * XL * Y, dtype=torch.int64, device=device)
     ox = torch.arange(-hx, hx + 1, device=device)
     oz = torch.arange(-hz, hz + 1, device=device)
     chunk = 16384
@@ -188,18 +197,18 @@ def make_stack_device(shape, n_spots, n_nuclei, seed, device="cuda", z_first=Tru
         gx = torch.exp(-0.5 * ((xs - tcx[:, None]) / SPOT_SIGMA_XY) ** 2)
         gy = torch.exp(-0.5 * ((ys - tcy[:, None]) / SPOT_SIGMA_XY) ** 2)
         gz = torch.exp(-0.5 * ((zs - tcz[:, None]) / SPOT_SIGMA_Z) ** 2)
-        gx = gx * ((xs >= 0) & (xs < X))
+        gx = gx * ((xs >= xa) & (xs < xb_))
         gy = gy * ((ys >= 0) & (ys < Y))
         gz = gz * ((zs >= za) & (zs < zb))
         val = torch.round(tam[:, None, None, None] * gz[:, :, None, None] * gx[:, None, :, None]
                           * gy[:, None, None, :] * 65536.0).to(torch.int64)
-        lin = (((zs - za).clamp(0, ZL - 1)[:, :, None, None] * X + xs.clamp(0, X - 1)[:, None, :, None]) * Y
+        lin = (((zs - za).clamp(0, ZL - 1)[:, :, None, None] * XL + (xs - xa).clamp(0, XL - 1)[:, None, :, None]) * Y
                + ys.clamp(0, Y - 1)[:, None, None, :])
         acc.index_add_(0, lin.reshape(-1), val.reshape(-1))
-    img += (acc.to(torch.float64) * (1.0 / 65536.0)).to(torch.float32).view(ZL, X, Y)
+    img += (acc.to(torch.float64) * (1.0 / 65536.0)).to(torch.float32).view(ZL, XL, Y)
     del acc
 
-    nuc = torch.zeros((ZL, X, Y), dtype=torch.uint8, device=device)
+    nuc = torch.zeros((ZL, XL, Y), dtype=torch.uint8, device=device)
     a, b, c = NUC_SEMI
     a = min(a, X / 4.0)
     b = min(b, (y1 - y0) / 4.0)
@@ -208,16 +217,16 @@ def make_stack_device(shape, n_spots, n_nuclei, seed, device="cuda", z_first=Tru
     ncy = rng.uniform(y0, y1, n_nuclei)
     ncz = rng.uniform(z0, z1, n_nuclei)
     for i in range(n_nuclei):
-        xa, xb = max(0, int(ncx[i] - a) - 1), min(X, int(ncx[i] + a) + 2)
+        xlo, xhi = max(xa, int(ncx[i] - a) - 1), min(xb_, int(ncx[i] + a) + 2)
         ya, yb = max(0, int(ncy[i] - b) - 1), min(Y, int(ncy[i] + b) + 2)
         na, nb = max(za, int(ncz[i] - c) - 1), min(zb, int(ncz[i] + c) + 2)
-        if nb <= na:
+        if nb <= na or xhi <= xlo:
             continue
-        gx = ((torch.arange(xa, xb, device=device) - ncx[i]) / a) ** 2
+        gx = ((torch.arange(xlo, xhi, device=device) - ncx[i]) / a) ** 2
         gy = ((torch.arange(ya, yb, device=device) - ncy[i]) / b) ** 2
         gz = ((torch.arange(na, nb, device=device) - ncz[i]) / c) ** 2
         inside = (gz[:, None, None] + gx[None, :, None] + gy[None, None, :]) <= 1.0
-        nuc[na - za:nb - za, xa:xb, ya:yb] |= inside.to(torch.uint8)
+        nuc[na - za:nb - za, xlo - xa:xhi - xa, ya:yb] |= inside.to(torch.uint8)
 
     if not z_first:
         img = img.permute(1, 2, 0).contiguous()

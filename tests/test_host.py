@@ -178,3 +178,21 @@ def test_dropin_modules_expose_reference_signatures():
         sys.path.remove(d)
         sys.modules.pop("muscle_fish", None)
         sys.modules.pop("scope_utils3", None)
+
+
+def test_slab_generators_draw_the_voxels_of_the_whole_stack():
+    """the bench's mosaic is generated slab by slab on each rank: any z- or x-slab must be bit-identical to the
+    same voxels of the whole stack (noise seeded per global plane, spots accumulated in fixed point)"""
+    import torch
+    shape, ns, nn, seed = (96, 64, 20), 400, 5, 4
+    full = synth.make_stack_device(shape, ns, nn, seed, device="cpu")
+    for z0, z1 in ((0, 7), (7, 20)):
+        part = synth.make_stack_device(shape, ns, nn, seed, device="cpu", z_range=(z0, z1))
+        for k in ("img", "fiber_mask", "nuc_mask"):
+            assert torch.equal(part[k], full[k][z0:z1]), (k, z0)
+    for x0, x1 in ((0, 31), (31, 64), (64, 96)):
+        part = synth.make_stack_device(shape, ns, nn, seed, device="cpu", x_range=(x0, x1))
+        for k in ("img", "fiber_mask", "nuc_mask"):
+            assert torch.equal(part[k], full[k][:, x0:x1]), (k, x0)
+    again = synth.make_stack_device(shape, ns, nn, seed, device="cpu")
+    assert torch.equal(again["img"], full["img"])

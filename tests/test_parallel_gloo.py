@@ -104,6 +104,33 @@ class OracleOps:
             out.append(float(np.array([uu], dtype=np.uint32).view(np.float32)[0]))
         return out[0], out[1], float(gamma), n
 
+    def log_peaks(self, ext, mm, sigma, thr):
+        log = self.log(ext, mm, sigma)
+        cube = log.numpy()
+        nz, nx, ny = cube.shape
+        pk = oracle.peak_local_max(cube[..., None], threshold_abs=thr)[:, :3]
+        raster = (pk[:, 1].astype(np.int64) * ny + pk[:, 2]) * nz + pk[:, 0]
+        return torch.from_numpy(raster), torch.from_numpy(cube[tuple(pk.T)].astype(np.float32))
+
+    def edt_rowscan(self, mask):
+        """distance along y to the nearest zero voxel of the row; 0x7FFF = no zero in the row (int16 on the wire)"""
+        m = mask.numpy() != 0
+        ny = m.shape[2]
+        yy = np.arange(ny)
+        d = np.where(m[:, :, None, :], 10 ** 6, np.abs(yy[:, None] - yy[None, :])[None, None]).min(axis=3)
+        return torch.from_numpy(np.where(d >= 10 ** 6, 0x7FFF, d).astype(np.int16))
+
+    def edt_xz(self, dy, sampling_xyz, ny_full):
+        sx, sy, sz = sampling_xyz
+        d = dy.numpy().astype(np.float64)
+        f = np.where(d >= 0x7FFF, np.inf, (d * sy) ** 2)  # [nz][nx][nyl]
+        nz, nx, _ = f.shape
+        dx = ((np.arange(nx)[:, None] - np.arange(nx)[None, :]) * sx) ** 2
+        f2 = (f[:, None, :, :] + dx[None, :, :, None]).min(axis=2)  # [z][p][y] = min_u f[z][u][y] + dx[p][u]
+        dz = ((np.arange(nz)[:, None] - np.arange(nz)[None, :]) * sz) ** 2
+        out = (f2[None, :, :, :] + dz[:, :, None, None]).min(axis=1)
+        return torch.from_numpy(np.sqrt(out).astype(np.float32))
+
     def edt_inplane(self, mask, sampling_xyz):
         sx, sy, _ = sampling_xyz
         m = mask.numpy()
@@ -221,3 +248,58 @@ def test_slab_pipeline_world2_equals_unsplit_oracle():
         np.testing.assert_allclose(sd, oracle.edt_gather(grass, spots, ANISO), rtol=1e-6)
         np.testing.assert_allclose(dz, grass.transpose(2, 0, 1)[z0:z1], rtol=1e-6)
     np.testing.assert_array_equal(res[0][0], res[1][0])  # every rank holds the same global result
+
+
+# ------------------------------------------------------------------------------------ x-slabs
+def _xcomm_job(rank, world, nz, nx, ny, halo):
+    full = torch.arange(nz * nx * ny, dtype=torch.float32).reshape(nz, nx, ny)
+    lay = P.XSlabLayout(nz, nx, ny)
+    slab = full[:, lay.x0:lay.x1].clone()
+    ext, lo, hi = P.exchange_halo_x(slab, halo, lay)
+    ok_halo = torch.equal(ext, full[:, lay.x0 - lo:lay.x1 + hi])
+    ys = P.repartition_x_to_y(slab.to(torch.int16), lay)
+    ok_y = torch.equal(ys, full[:, :, lay.y0:lay.y1].to(torch.int16))
+    return [bool(ok_halo), bool(ok_y), lo, hi]
+
+
+@pytest.mark.parametrize("world,shape,halo", [(2, (5, 10, 8), 3), (3, (4, 13, 7), 2)])
+def test_x_halo_exchange_and_x_to_y_all_to_all(world, shape, halo):
+    res = run_ranks(world, _xcomm_job, *shape, halo)
+    for r, (a, b, lo, hi) in enumerate(res):
+        assert a and b
+        assert (lo, hi) == (halo if r > 0 else 0, halo if r < world - 1 else 0)
+
+
+def _xspots_job(rank, world, seed, shape):
+    st = synth.make_stack(shape=shape, n_spots=60, n_nuclei=2, seed=seed, nuc_semi=(10.0, 7.0, 4.0))
+    img = torch.from_numpy(np.ascontiguousarray(st["img"].transpose(2, 0, 1)))
+    fib = torch.from_numpy(np.ascontiguousarray(st["fiber_mask"].transpose(2, 0, 1)))
+    notnuc = torch.from_numpy(np.ascontiguousarray((st["nuc_mask"] == 0).astype(np.uint8).transpose(2, 0, 1)))
+    lay = P.XSlabLayout(*img.shape)
+    ops = OracleOps(2.0)
+    xs = slice(lay.x0, lay.x1)
+    res = P.slab_analyze(img[:, xs].clone(), fib[:, xs].clone(), notnuc[:, xs].clone(), lay, sigma=2.0, t_spot=0.025,
+                         sampling_xyz=ANISO, ops=ops)
+    return [res["spots"], res["spots_masked"], res["intensity"], res["baseline"], res["spot_dist"],
+            res["dist_slab"].numpy(), (lay.y0, lay.y1)]
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_xslab_pipeline_equals_unsplit_oracle(world):
+    """x-slabs for the filters / NMS / row scan, y-slabs for the EDT's envelope passes: the same global result
+    as the un-split oracle on every rank"""
+    seed, shape = 33, (96, 64, 20)
+    res = run_ranks(world, _xspots_job, seed, shape)
+    st = synth.make_stack(shape=shape, n_spots=60, n_nuclei=2, seed=seed, nuc_semi=(10.0, 7.0, 4.0))
+    ref_spots, ref_data = oracle.find_spots_snrfilter(st["img"], sigma=2.0, t_spot=0.025, mask=st["fiber_mask"],
+                                                      pair_order="sorted")
+    grass = oracle.distance_transform_edt(np.logical_not(st["nuc_mask"]), sampling=ANISO)
+    assert len(ref_spots) > 10
+    for r in range(world):
+        spots, masked, inten, baseline, sd, dmap, (y0, y1) = res[r]
+        assert match_fraction(spots, ref_spots) >= 0.999
+        assert len(masked) == len(ref_data) - 1
+        np.testing.assert_allclose(np.sort(inten), np.sort([row[4] for row in ref_data[1:]]), rtol=1e-6)
+        np.testing.assert_allclose(sd, oracle.edt_gather(grass, spots, ANISO), rtol=1e-6)
+        np.testing.assert_allclose(dmap, grass.transpose(2, 0, 1)[:, :, y0:y1], rtol=1e-6)
+        np.testing.assert_array_equal(spots, res[0][0])
