@@ -864,6 +864,12 @@ class StageTimer:
         self.events.append((name, s, e))
         return out
 
+    def mark(self, name):
+        """host time stamp (the host blocks on every read-back, so these trace the step's critical path)"""
+        import time
+        self.marks = getattr(self, "marks", [])
+        self.marks.append((name, time.perf_counter()))
+
     def totals_ms(self):
         """{stage: [ms per recorded call]} -- call after a synchronize."""
         out = {}
@@ -875,6 +881,9 @@ class StageTimer:
 class _NoTimer:
     def run(self, name, fn, *a, **k):
         return fn(*a, **k)
+
+    def mark(self, name):
+        pass
 
 
 def _spot_list_tail(vol, fiber_zxy, peaks, baseline_f, sigma, snr, dist_ready, t, fiber_ready=None):
@@ -889,7 +898,9 @@ def _spot_list_tail(vol, fiber_zxy, peaks, baseline_f, sigma, snr, dist_ready, t
     nz, nx, ny = vol.data.shape
     dims = (1, nx, ny, nz)
     main = torch.cuda.current_stream()
+    t.mark("tail_begin")
     idx, val = peaks()
+    t.mark("peak_count")
     hp = _list_stream() if os.environ.get("MFISH_LIST_PRIO", "1") != "0" else main
     hp.wait_stream(main)
     fiber_last = fiber_ready is not None
@@ -900,6 +911,7 @@ def _spot_list_tail(vol, fiber_zxy, peaks, baseline_f, sigma, snr, dist_ready, t
             idx_r, _, alive = t.run("rank_prune", rank_prune_equal, idx, val, dims, cutoff)
             ras = idx_r[alive.bool()]  # survivors in peak order; raster index over (x, y, z)
             n = int(ras.numel())
+            t.mark("pruned")
         if n:
             z = ras % nz
             xy = ras // nz
@@ -911,8 +923,10 @@ def _spot_list_tail(vol, fiber_zxy, peaks, baseline_f, sigma, snr, dist_ready, t
             else:
                 early_d = gather_points(fiber_zxy, pts)
             early = torch.stack([ras.to(torch.float64), inten_d, early_d.to(torch.float64)]).cpu().numpy()
+            t.mark("early_readback")
             x, y, zz, _ = decode_raster(early[0].astype(np.int64), dims)
             spots = np.stack([x, y, zz, np.full(n, float(sigma))], axis=1).astype(np.float64)
+            t.mark("decoded")
             if fiber_last:
                 late = gather_points(fiber_ready(), pts).cpu().numpy()
                 inside, dists = late != 0, early[2]
@@ -920,6 +934,7 @@ def _spot_list_tail(vol, fiber_zxy, peaks, baseline_f, sigma, snr, dist_ready, t
                 dist = dist_ready()
                 late = gather_points(dist, pts).cpu().numpy()
                 inside, dists = early[2] != 0, late.astype(np.float64)
+            t.mark("late_readback")
             spots, inten, dists = spots[inside], early[1][inside], dists[inside]
         else:
             if fiber_last:
@@ -929,11 +944,13 @@ def _spot_list_tail(vol, fiber_zxy, peaks, baseline_f, sigma, snr, dist_ready, t
         # no spot inside the mask: the reference fails on the empty row stack before it ever takes the
         # percentile (modules/muscle_fish.py:341), so an empty mask must not raise from here
         baseline = baseline_f() if len(spots) else None
+        t.mark("baseline")
     main.wait_stream(hp)
     if snr is None and len(spots):
         thresh = np.percentile(inten, 90) / (baseline * np.sqrt(10))
         snr = max(thresh, np.sqrt(10))
     keep = (inten / baseline > snr) if len(spots) else np.zeros(0, bool)
+    t.mark("tail_end")
     return {"spots": spots[keep], "spots_masked": spots, "intensity": inten, "baseline": baseline, "snr": snr,
             "spot_dist": dists[keep], "dist": dist}
 

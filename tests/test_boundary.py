@@ -229,6 +229,13 @@ def test_fish_analysis_call_sequence_with_the_dropin_segmentation(tmp_path):
     import muscle_fish_b200  # noqa: F401
     from muscle_fish_b200 import synth
     st = synth.make_config("small")
+    # the synthetic fibre stops short of the first / last planes; fix_bleaching's fit needs fibre voxels in
+    # every fitted plane (an empty plane mean is NaN and curve_fit raises, upstream too): extend it over z
+    y0, y1, z0, z1 = synth._fiber_bounds(st["img"].shape)
+    img = st["img"].copy()
+    img[:, y0:y1, :z0] += 60.0
+    img[:, y0:y1, z1:] += 60.0
+    st = dict(st, img=img)
     out, stdout = _run_script(tmp_path, st, segmentation=True)
     assert out["stage"] == "done", out
     assert "Fiber threshold: " in stdout and "DAPI threshold = " in stdout
