@@ -904,6 +904,22 @@ def _spot_list_tail(vol, fiber_zxy, peaks, baseline_f, sigma, snr, dist_ready, t
     hp = _list_stream() if os.environ.get("MFISH_LIST_PRIO", "1") != "0" else main
     hp.wait_stream(main)
     fiber_last = fiber_ready is not None
+    spots, inten, dists_all, inside = np.empty((0, 4)), np.empty(0), None, None
+    baseline, keep = None, np.zeros(0, bool)
+
+    def apply_rules():
+        """mask filter, baseline, SNR rule: as soon as the mask look-up is on the host"""
+        nonlocal spots, inten, baseline, snr, keep
+        spots, inten = spots[inside], inten[inside]
+        # no spot inside the mask: the reference fails on the empty row stack before it ever takes the
+        # percentile (modules/muscle_fish.py:341), so an empty mask must not raise from here
+        baseline = baseline_f() if len(spots) else None
+        t.mark("baseline")
+        if snr is None and len(spots):
+            thresh = np.percentile(inten, 90) / (baseline * np.sqrt(10))
+            snr = max(thresh, np.sqrt(10))
+        keep = (inten / baseline > snr) if len(spots) else np.zeros(0, bool)
+
     with torch.cuda.stream(hp):
         n = 0
         if idx.numel():
@@ -926,33 +942,29 @@ def _spot_list_tail(vol, fiber_zxy, peaks, baseline_f, sigma, snr, dist_ready, t
             t.mark("early_readback")
             x, y, zz, _ = decode_raster(early[0].astype(np.int64), dims)
             spots = np.stack([x, y, zz, np.full(n, float(sigma))], axis=1).astype(np.float64)
+            inten = early[1]
             t.mark("decoded")
             if fiber_last:
-                late = gather_points(fiber_ready(), pts).cpu().numpy()
-                inside, dists = late != 0, early[2]
+                inside = gather_points(fiber_ready(), pts).cpu().numpy() != 0
+                t.mark("late_readback")
+                dists_all = early[2]
+                apply_rules()
             else:
+                inside = early[2] != 0
+                apply_rules()  # everything but the distances, while the transform is still running
                 dist = dist_ready()
-                late = gather_points(dist, pts).cpu().numpy()
-                inside, dists = early[2] != 0, late.astype(np.float64)
-            t.mark("late_readback")
-            spots, inten, dists = spots[inside], early[1][inside], dists[inside]
+                dists_all = gather_points(dist, pts).cpu().numpy().astype(np.float64)
+                t.mark("late_readback")
+            dists = dists_all[inside][keep]
         else:
             if fiber_last:
                 fiber_ready()
             dist = dist_ready()
-            spots, inten, dists = np.empty((0, 4)), np.empty(0), np.empty(0)
-        # no spot inside the mask: the reference fails on the empty row stack before it ever takes the
-        # percentile (modules/muscle_fish.py:341), so an empty mask must not raise from here
-        baseline = baseline_f() if len(spots) else None
-        t.mark("baseline")
+            dists = np.empty(0)
     main.wait_stream(hp)
-    if snr is None and len(spots):
-        thresh = np.percentile(inten, 90) / (baseline * np.sqrt(10))
-        snr = max(thresh, np.sqrt(10))
-    keep = (inten / baseline > snr) if len(spots) else np.zeros(0, bool)
     t.mark("tail_end")
     return {"spots": spots[keep], "spots_masked": spots, "intensity": inten, "baseline": baseline, "snr": snr,
-            "spot_dist": dists[keep], "dist": dist}
+            "spot_dist": dists, "dist": dist}
 
 
 def analyze_stack(img_zxy: torch.Tensor, fiber_zxy: torch.Tensor, notnuc_zxy: torch.Tensor, sigma=2.0,
