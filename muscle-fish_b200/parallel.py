@@ -317,6 +317,13 @@ def exchange_halo_x(slab: torch.Tensor, halo: int, lay: "XSlabLayout", group=Non
     return ext, lo, hi
 
 
+def _wire(t: torch.Tensor) -> torch.Tensor:
+    """A contiguous buffer as NCCL can carry it: 16-bit integers travel as bytes (NCCL has no Short)."""
+    if t.dtype in (torch.int16, torch.uint16):
+        return t.view(torch.uint8)
+    return t
+
+
 def repartition_x_to_y(t: torch.Tensor, lay: "XSlabLayout", group=None) -> torch.Tensor:
     """[nz][nx_local][ny] (x-slab) -> [nz][nx][ny_local] (y-slab): the all-to-all between the EDT's row scan and
     its two envelope passes (2 bytes per voxel on the wire: the row distances are uint16)."""
@@ -335,8 +342,8 @@ def repartition_x_to_y(t: torch.Tensor, lay: "XSlabLayout", group=None) -> torch
         xb, xe = lay.xb[s]
         rcv = _buf(f"x2y_recv{s}", (nz, xe - xb, lay.y1 - lay.y0), t.dtype, t.device)
         recvs[s] = rcv
-        ops.append(dist.P2POp(dist.isend, snd, s, group))
-        ops.append(dist.P2POp(dist.irecv, rcv, s, group))
+        ops.append(dist.P2POp(dist.isend, _wire(snd), s, group))
+        ops.append(dist.P2POp(dist.irecv, _wire(rcv), s, group))
     out[:, lay.x0:lay.x1] = t[:, :, lay.y0:lay.y1]
     if ops:
         for w in dist.batch_isend_irecv(ops):
@@ -689,7 +696,7 @@ def xslab_edt(notnuc_slab: torch.Tensor, lay: XSlabLayout, sampling_xyz=(1.0, 1.
     with _phase("edt_rowscan"):
         dy = ops.edt_rowscan(notnuc_slab)
     with _phase("edt_all_to_all"):
-        wire = dy.view(torch.int16) if dy.dtype == torch.uint16 else dy  # NCCL has no uint16
+        wire = dy
         dyy = repartition_x_to_y(wire, lay, group)
         dyy = dyy.view(torch.uint16) if dy.dtype == torch.uint16 else dyy
     with _phase("edt_xz"):
