@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MFISH_ABI_VERSION 4
+#define MFISH_ABI_VERSION 5
 
 #define MFISH_OK 0
 #define MFISH_ERR_INVALID (-1)
@@ -210,6 +210,34 @@ int mfish_qsel_begin(void* ws_dev, double q, void* stream);
 int mfish_qsel_hist(const float* vol_dev, const uint8_t* mask_dev, int64_t n, int pass, void* ws_dev,
                     void* stream);
 int mfish_qsel_scan(int pass, void* ws_dev, float* out_dev, double* info_dev, void* stream);
+/* mfish_qsel_scan on a histogram the caller holds in 64 bits (hist64_dev: 2*2048 uint64, the 32-bit bins of
+ * every slab widened BEFORE the all-reduce): mosaics of 2^32 voxels and more (config 4 is 6.7e9).        */
+int mfish_qsel_scan_u64(int pass, void* ws_dev, const unsigned long long* hist64_dev, float* out_dev,
+                        double* info_dev, void* stream);
+
+/* The bracketed select (mfish_masked_quantile_fast_f32: ONE full pass) in steps, for a volume split across
+ * ranks -- the fibre baseline np.percentile(img[mask], 25) of modules/muscle_fish.py:355-356 on a mosaic:
+ *   mfish_qselb_begin(ws, q)
+ *   pass 0, 1, 2:  mfish_qselb_sample_hist(...)  -> all-reduce the first 2*2048 uint32 of ws (1/64 sample:
+ *                  no overflow below 2^38 voxels) -> mfish_qsel_scan(pass, ws, pair_dev, scratch_dev)
+ *   mfish_qselb_collect(...)   pair_dev = the bracketing values; one pass over the slab counts the masked
+ *                  voxels, those below the bracket, and appends those inside it to cand_dev (cap floats,
+ *                  cap % 64 == 0); counts_dev = int64 {n_masked, n_below, n_cand, overflow}
+ *                  -> all-reduce counts_dev (sum)
+ *   mfish_qselb_ranks(ws, q, counts_dev, out, info)   global ranks relative to the candidates;
+ *                  info_dev = {gamma, n_masked, status}; status 1: bracket missed / a buffer overflowed,
+ *                  run the three-pass select instead
+ *   pass 0, 1, 2:  mfish_qselb_cand_hist(cand, cap, pass, ws) -> all-reduce the histogram
+ *                  -> mfish_qsel_scan(pass, ws, out_dev, info_dev);  out_dev = the two order statistics  */
+int mfish_qselb_begin(void* ws_dev, double q, void* stream);
+int mfish_qselb_sample_hist(const float* vol_dev, const uint8_t* mask_dev, int64_t n, int pass, void* ws_dev,
+                            void* stream);
+int mfish_qselb_collect(const float* vol_dev, const uint8_t* mask_dev, int64_t n, void* ws_dev,
+                        const float* pair_dev, float* cand_dev, int64_t cap, long long* counts_dev,
+                        void* stream);
+int mfish_qselb_ranks(void* ws_dev, double q, const long long* counts_dev, float* out_dev, double* info_dev,
+                      void* stream);
+int mfish_qselb_cand_hist(const float* cand_dev, int64_t cap, int pass, void* ws_dev, void* stream);
 
 /* img_blur[pos] of skimage.filters.gaussian(normalize(img), sigma)
  * (modules/muscle_fish.py:357-365,385-388), evaluated only at the given
@@ -315,6 +343,23 @@ int mfish_split_moments_f32(const float* vol_dev, int64_t n, float threshold, do
                             void* stream);
 int mfish_binarize_f32(const float* vol_dev, int64_t n, float threshold, const float* norm_minmax_dev,
                        uint8_t* out_dev, void* stream);
+
+/* ---- per-nucleus faded masks (nuclear-mesh step) --------------------------- *
+ * nocodazole/fish_analysis_noco.py:233-235 computes, once per nucleus over the whole volume,
+ *     nuc_fade = filters.gaussian(np.where(region_nuc_labeled == i, 1, 0).astype(float), (3, 3, 1)).
+ * mfish_label_bbox_i32: tight bounding boxes of the labels first_label .. first_label+n_labels-1 of an
+ *   int32 label volume [z][x][y]; boxes_dev[l] = {z0, z1, x0, x1, y0, y1} (half-open; z1 <= z0: absent).
+ * mfish_onehot_gaussian_f32: the Gaussian (boundary rule `nearest`, truncate 4) of the one-hot mask of
+ *   each listed label inside its crop.  crops_dev[c] = {z0, z1, x0, x1, y0, y1, label, 0}; a crop must
+ *   contain the label's bounding box grown by the filter radius (clipped to the volume) -- outside of it
+ *   the result is exactly 0.  offsets_dev[c] .. offsets_dev[c+1] (int64, n_crops + 1 entries) is the crop's
+ *   range in out_dev / tmp_dev (total_elems floats each), layout [z][x][y] per crop.                     */
+int mfish_label_bbox_i32(const int32_t* labels_dev, int64_t nz, int64_t nx, int64_t ny, int32_t first_label,
+                         int32_t n_labels, int32_t* boxes_dev, void* stream);
+int mfish_onehot_gaussian_f32(const int32_t* labels_dev, int64_t nz, int64_t nx, int64_t ny,
+                              const int32_t* crops_dev, const int64_t* offsets_dev, int32_t n_crops,
+                              int64_t total_elems, const double* sigma_zxy_host, float* out_dev,
+                              float* tmp_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -9,6 +9,7 @@ root (``import muscle_fish_b200``).  Sub-modules:
 * ``ndimage``      ``distance_transform_edt`` / ``gaussian`` / ``gaussian_laplace`` replacements
 * ``segmentation`` ``threshold_fiber`` / ``threshold_nuclei`` (blurs, Li / Otsu statistics on the GPU)
 * ``morphology``   ``binary_erosion`` / ``binary_dilation`` / ``compartments`` (the compartment masks)
+* ``filters``      ``gaussian`` and the batched per-nucleus faded masks of the nuclear-mesh step
 * ``device``       device-resident pipeline on torch CUDA tensors
 * ``parallel``     multi-GPU drivers (stack-per-GPU batches, z-slab mosaics)
 * ``taps`` / ``synth``  host-side filter taps and the synthetic stack generator
@@ -24,6 +25,7 @@ from . import taps, synth  # noqa: F401  (pure numpy, importable anywhere)
 
 def __getattr__(name):
     import importlib
-    if name in ("device", "muscle_fish", "scope_utils3", "ndimage", "morphology", "segmentation", "parallel", "_lib"):
+    if name in ("device", "muscle_fish", "scope_utils3", "ndimage", "morphology", "segmentation", "filters", "parallel",
+                "_lib"):
         return importlib.import_module(f"{__name__}.{name}")
     raise AttributeError(name)

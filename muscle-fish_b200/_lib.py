@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmfish_sm100.so")
 
 # constants mirrored from include/mfish.h
-ABI_VERSION = 4
+ABI_VERSION = 5
 OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 U8, U16, I16, I32, I64, F32, F64 = range(7)
 LAYOUT_XYZ, LAYOUT_ZXY = 0, 1
@@ -58,6 +58,12 @@ SIGNATURES = {
     "mfish_qsel_begin": (_i, [_p, _d, _p]),
     "mfish_qsel_hist": (_i, [_p, _p, _i64, _i, _p, _p]),
     "mfish_qsel_scan": (_i, [_i, _p, _p, _p, _p]),
+    "mfish_qsel_scan_u64": (_i, [_i, _p, _p, _p, _p, _p]),
+    "mfish_qselb_begin": (_i, [_p, _d, _p]),
+    "mfish_qselb_sample_hist": (_i, [_p, _p, _i64, _i, _p, _p]),
+    "mfish_qselb_collect": (_i, [_p, _p, _i64, _p, _p, _p, _i64, _p, _p]),
+    "mfish_qselb_ranks": (_i, [_p, _d, _p, _p, _p, _p]),
+    "mfish_qselb_cand_hist": (_i, [_p, _i64, _i, _p, _p]),
     "mfish_blur_at_points": (_i, [_p, _i64, _i64, _i64, _p, _i64, _p, _i, _p, _i, _p, _i, _i, _p, _p, _p]),
     "mfish_gather_f32": (_i, [_p, _i64, _i64, _i64, _p, _i64, _p, _p]),
     "mfish_gather_u8": (_i, [_p, _i64, _i64, _i64, _p, _i64, _p, _p]),
@@ -76,6 +82,8 @@ SIGNATURES = {
     "mfish_split_moments_f32": (_i, [_p, _i64, _f, _p, _p]),
     "mfish_binarize_f32": (_i, [_p, _i64, _f, _p, _p, _p]),
     "mfish_compartments_u8": (_i, [_p, _p, _i64, _i64, _i64, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
+    "mfish_label_bbox_i32": (_i, [_p, _i64, _i64, _i64, C.c_int32, C.c_int32, _p, _p]),
+    "mfish_onehot_gaussian_f32": (_i, [_p, _i64, _i64, _i64, _p, _p, C.c_int32, _i64, _p, _p, _p, _p]),
 }
 
 _lib = None

@@ -175,7 +175,8 @@ __global__ void qsel_init_kernel(QWs* ws, double q, int mode) {
 constexpr int QSCAN_THREADS = QBINS / 8;
 
 template <int PASS>
-__global__ void __launch_bounds__(QSCAN_THREADS) qsel_scan_kernel(QWs* ws, float* out, double* info) {
+__global__ void __launch_bounds__(QSCAN_THREADS) qsel_scan_kernel(QWs* ws, float* out, double* info,
+                                                                  const unsigned long long* h64 = nullptr) {
   __shared__ unsigned long long s_part[2][QSCAN_THREADS];
   __shared__ unsigned long long s_tot[2];
   __shared__ int s_bin[2];
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(QSCAN_THREADS) qsel_scan_kernel(QWs* ws, float
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int bin = 8 * t + i;
-      const unsigned long long c = bin < nb ? h[bin] : 0ull;
+      const unsigned long long c = bin < nb ? (h64 ? h64[(same ? 0 : j) * QBINS + bin] : (unsigned long long)h[bin]) : 0ull;
       loc[j][i] = c;
       acc += c;
     }
@@ -455,10 +456,17 @@ __global__ void qsel_mm_finalize_kernel(uint32_t* mm) {
 }
 
 // exact ranks of the population quantile, relative to the candidate buffer; verifies the bracket
-__global__ void qsel_ranks_kernel(QWs* ws, float* out, double* info) {
+// (counts: {n_masked, n_below, n_cand, overflow} summed over the ranks of a split volume, else null)
+__global__ void qsel_ranks_kernel(QWs* ws, float* out, double* info, const long long* counts = nullptr) {
   if (threadIdx.x != 0) return;
   QCtl& c = ws->ctl;
   QState& s = ws->st;
+  if (counts) {
+    c.n_masked = (unsigned long long)counts[0];
+    c.n_below = (unsigned long long)counts[1];
+    c.n_cand = (unsigned long long)counts[2];
+    c.seg_count[0] = counts[3] != 0 ? 1u : 0u;
+  }
   const unsigned long long n = c.n_masked;
   info[1] = (double)n;
   const bool overflow = c.seg_count[0] != 0;  // a warp outgrew its region of the candidate buffer
@@ -648,6 +656,100 @@ extern "C" int mfish_qsel_scan(int pass, void* ws_dev, float* out_dev, double* i
     qsel_scan_kernel<2><<<1, QSCAN_THREADS, 0, st>>>(ws, out_dev, info_dev);
   count_launch(1);
   return check_launch("qsel_scan");
+}
+
+extern "C" int mfish_qsel_scan_u64(int pass, void* ws_dev, const unsigned long long* hist64_dev, float* out_dev,
+                                  double* info_dev, void* stream) {
+  MFISH_REQUIRE(ws_dev && out_dev && info_dev && hist64_dev, "qsel_scan_u64: null pointer");
+  MFISH_REQUIRE(pass >= 0 && pass <= 2, "qsel_scan_u64: pass must be 0, 1 or 2");
+  cudaStream_t st = as_stream(stream);
+  QWs* ws = reinterpret_cast<QWs*>(ws_dev);
+  if (pass == 0)
+    qsel_scan_kernel<0><<<1, QSCAN_THREADS, 0, st>>>(ws, out_dev, info_dev, hist64_dev);
+  else if (pass == 1)
+    qsel_scan_kernel<1><<<1, QSCAN_THREADS, 0, st>>>(ws, out_dev, info_dev, hist64_dev);
+  else
+    qsel_scan_kernel<2><<<1, QSCAN_THREADS, 0, st>>>(ws, out_dev, info_dev, hist64_dev);
+  count_launch(1);
+  return check_launch("qsel_scan_u64");
+}
+
+// ---- the bracketed select in steps, for a volume split across ranks (see include/mfish.h) ----
+__global__ void qsel_export_counts_kernel(const QWs* ws, long long* counts) {
+  counts[0] = (long long)ws->ctl.n_masked;
+  counts[1] = (long long)ws->ctl.n_below;
+  counts[2] = (long long)ws->ctl.n_cand;
+  counts[3] = ws->ctl.seg_count[0] != 0 ? 1 : 0;
+}
+
+extern "C" int mfish_qselb_begin(void* ws_dev, double q, void* stream) {
+  MFISH_REQUIRE(ws_dev && q >= 0.0 && q <= 1.0, "qselb_begin: bad arguments");
+  qsel_init_kernel<<<1, 256, 0, as_stream(stream)>>>(reinterpret_cast<QWs*>(ws_dev), q, QMODE_BRACKET);
+  count_launch(1);
+  return check_launch("qselb_begin");
+}
+
+extern "C" int mfish_qselb_sample_hist(const float* vol_dev, const uint8_t* mask_dev, int64_t n, int pass,
+                                       void* ws_dev, void* stream) {
+  MFISH_REQUIRE(vol_dev && mask_dev && ws_dev && n > 0, "qselb_sample_hist: bad arguments");
+  MFISH_REQUIRE(pass >= 0 && pass <= 2, "qselb_sample_hist: pass must be 0, 1 or 2");
+  cudaStream_t st = as_stream(stream);
+  QWs* ws = reinterpret_cast<QWs*>(ws_dev);
+  constexpr int SAMPLE = 64;
+  const int sblocks = (int)std::min<int64_t>((n / 4 / 64 + 255) / 256 + 1, (int64_t)num_sms() * 8);
+  if (pass == 0)
+    qsel_hist_kernel<0><<<sblocks, 256, 0, st>>>(vol_dev, mask_dev, n, ws, SAMPLE, nullptr);
+  else if (pass == 1)
+    qsel_hist_kernel<1><<<sblocks, 256, 0, st>>>(vol_dev, mask_dev, n, ws, SAMPLE, nullptr);
+  else
+    qsel_hist_kernel<2><<<sblocks, 256, 0, st>>>(vol_dev, mask_dev, n, ws, SAMPLE, nullptr);
+  count_launch(1);
+  return check_launch("qselb_sample_hist");
+}
+
+extern "C" int mfish_qselb_collect(const float* vol_dev, const uint8_t* mask_dev, int64_t n, void* ws_dev,
+                                   const float* pair_dev, float* cand_dev, int64_t cap, long long* counts_dev,
+                                   void* stream) {
+  MFISH_REQUIRE(vol_dev && mask_dev && ws_dev && pair_dev && cand_dev && counts_dev, "qselb_collect: null pointer");
+  MFISH_REQUIRE(n > 0 && cap >= QSEG && cap % QSEG == 0, "qselb_collect: bad sizes");
+  cudaStream_t st = as_stream(stream);
+  QWs* ws = reinterpret_cast<QWs*>(ws_dev);
+  ProfScope prof("masked_quantile_collect", st);
+  const int blocks = (int)std::min<int64_t>((n / 4 + 255) / 256 + 1, (int64_t)num_sms() * 8);
+  qsel_bracket_kernel<<<1, 32, 0, st>>>(ws, pair_dev);
+  MFISH_CUDA(cudaMemsetAsync(cand_dev, 0x7f, (size_t)cap * sizeof(float), st));
+  qsel_set_cap_kernel<<<1, 1, 0, st>>>(ws, (unsigned long long)cap);
+  qsel_range_kernel<false><<<blocks, 256, 0, st>>>(vol_dev, mask_dev, n, ws, cand_dev, nullptr);
+  qsel_export_counts_kernel<<<1, 1, 0, st>>>(ws, counts_dev);
+  count_launch(4);
+  return check_launch("qselb_collect");
+}
+
+extern "C" int mfish_qselb_ranks(void* ws_dev, double q, const long long* counts_dev, float* out_dev,
+                                 double* info_dev, void* stream) {
+  MFISH_REQUIRE(ws_dev && counts_dev && out_dev && info_dev, "qselb_ranks: null pointer");
+  cudaStream_t st = as_stream(stream);
+  QWs* ws = reinterpret_cast<QWs*>(ws_dev);
+  qsel_init_kernel<<<1, 256, 0, st>>>(ws, q, QMODE_RANKS);
+  qsel_ranks_kernel<<<1, 32, 0, st>>>(ws, out_dev, info_dev, counts_dev);
+  count_launch(2);
+  return check_launch("qselb_ranks");
+}
+
+extern "C" int mfish_qselb_cand_hist(const float* cand_dev, int64_t cap, int pass, void* ws_dev, void* stream) {
+  MFISH_REQUIRE(cand_dev && ws_dev && cap > 0, "qselb_cand_hist: bad arguments");
+  MFISH_REQUIRE(pass >= 0 && pass <= 2, "qselb_cand_hist: pass must be 0, 1 or 2");
+  cudaStream_t st = as_stream(stream);
+  QWs* ws = reinterpret_cast<QWs*>(ws_dev);
+  const int cblocks = (int)std::min<int64_t>((cap / 4 + 255) / 256 + 1, (int64_t)num_sms() * 4);
+  if (pass == 0)
+    qsel_hist_kernel<0><<<cblocks, 256, 0, st>>>(cand_dev, nullptr, cap, ws, 0, &ws->ctl.cap);
+  else if (pass == 1)
+    qsel_hist_kernel<1><<<cblocks, 256, 0, st>>>(cand_dev, nullptr, cap, ws, 0, &ws->ctl.cap);
+  else
+    qsel_hist_kernel<2><<<cblocks, 256, 0, st>>>(cand_dev, nullptr, cap, ws, 0, &ws->ctl.cap);
+  count_launch(1);
+  return check_launch("qselb_cand_hist");
 }
 
 extern "C" int mfish_masked_quantile_f32(const float* vol_dev, const uint8_t* mask_dev, int64_t n, double q,

@@ -667,26 +667,62 @@ def masked_percentile(vol: Volume, mask: torch.Tensor, q_percent: float) -> floa
 
 
 def masked_quantile_distributed(vol: torch.Tensor, mask: torch.Tensor, q: float, reduce_hist):
-    """Masked radix select over a volume that is split across ranks: ``reduce_hist(int32 tensor)``
-    sums the 2x2048-bin histogram over the ranks between the hist and scan step of each pass.
+    """Masked select of the two order statistics around quantile ``q`` over a volume that is split across
+    ranks; ``reduce_hist(tensor)`` sums an integer tensor over the ranks in place.  ONE pass over the slab:
+    a 1/64 sample (its 2x2048-bin histograms all-reduced) brackets the wanted ranks, the full pass counts the
+    masked voxels below the bracket and collects those inside it, and the exact ranks are selected among the
+    candidates of all ranks (their histograms all-reduced).  A missed bracket (checked identically on every
+    rank) falls back to the three-pass radix select with 64-bit bins.
     Returns (value[k], value[k+1], gamma, n_masked) of the RAW values."""
     dev = vol.device
+    lib = L.lib()
+    st = _stream()
+    ws = WS.get("qws", (L.QUANTILE_WS_BYTES,), torch.uint8, dev)
+    out = torch.empty(2, dtype=torch.float32, device=dev)
+    pair = torch.empty(2, dtype=torch.float32, device=dev)
+    info = torch.zeros(3, dtype=torch.float64, device=dev)
+    scratch = torch.empty(3, dtype=torch.float64, device=dev)
+    counts = torch.empty(4, dtype=torch.int64, device=dev)
+    hist = ws[:2 * 2048 * 4].view(torch.int32)
+    n = vol.numel()
+    L.check(lib.mfish_qselb_begin(ws.data_ptr(), float(q), st))
+    for p in range(3):
+        L.check(lib.mfish_qselb_sample_hist(vol.data_ptr(), mask.data_ptr(), n, p, ws.data_ptr(), st))
+        reduce_hist(hist)
+        L.check(lib.mfish_qsel_scan(p, ws.data_ptr(), pair.data_ptr(), scratch.data_ptr(), st))
+    cap = (max(1 << 20, n // 64) + 63) // 64 * 64
+    cand = WS.get("qcand", (cap,), torch.float32, dev)
+    L.check(lib.mfish_qselb_collect(vol.data_ptr(), mask.data_ptr(), n, ws.data_ptr(), pair.data_ptr(),
+                                    cand.data_ptr(), cap, counts.data_ptr(), st))
+    reduce_hist(counts)
+    L.check(lib.mfish_qselb_ranks(ws.data_ptr(), float(q), counts.data_ptr(), out.data_ptr(), info.data_ptr(), st))
+    for p in range(3):
+        L.check(lib.mfish_qselb_cand_hist(cand.data_ptr(), cap, p, ws.data_ptr(), st))
+        reduce_hist(hist)
+        L.check(lib.mfish_qsel_scan(p, ws.data_ptr(), out.data_ptr(), info.data_ptr(), st))
+    gamma, nm, status = info.tolist()
+    if status != 0.0:
+        return masked_quantile_distributed_3pass(vol, mask, q, reduce_hist)
+    v0, v1 = out.tolist()
+    return v0, v1, gamma, nm
+
+
+def masked_quantile_distributed_3pass(vol: torch.Tensor, mask: torch.Tensor, q: float, reduce_hist):
+    """The three-pass radix select over a split volume: the 2x2048 32-bit bins of every rank are widened to 64
+    bits before ``reduce_hist`` sums them (a mosaic of 2^32 voxels or more would wrap a 32-bit bin)."""
+    dev = vol.device
+    lib = L.lib()
+    st = _stream()
     ws = WS.get("qws", (L.QUANTILE_WS_BYTES,), torch.uint8, dev)
     out = torch.empty(2, dtype=torch.float32, device=dev)
     info = torch.empty(2, dtype=torch.float64, device=dev)
     hist = ws[:2 * 2048 * 4].view(torch.int32)
-    n_local = torch.tensor([float(vol.numel())], dtype=torch.float64, device=dev)
-    reduce_hist(n_local)
-    if float(n_local.item()) >= 2.0 ** 32:
-        # the bins are uint32: a mosaic with >= 2^32 voxels could wrap one (sign + exponent + 2 mantissa bits
-        # decide the first pass's bin) without anything noticing
-        raise OverflowError("distributed masked quantile: the mosaic has 2^32 voxels or more, a 32-bit histogram "
-                            "bin could overflow")
-    L.check(L.lib().mfish_qsel_begin(ws.data_ptr(), float(q), _stream()))
+    L.check(lib.mfish_qsel_begin(ws.data_ptr(), float(q), st))
     for p in range(3):
-        L.check(L.lib().mfish_qsel_hist(vol.data_ptr(), mask.data_ptr(), vol.numel(), p, ws.data_ptr(), _stream()))
-        reduce_hist(hist)
-        L.check(L.lib().mfish_qsel_scan(p, ws.data_ptr(), out.data_ptr(), info.data_ptr(), _stream()))
+        L.check(lib.mfish_qsel_hist(vol.data_ptr(), mask.data_ptr(), vol.numel(), p, ws.data_ptr(), st))
+        h64 = hist.to(torch.int64) & 0xFFFFFFFF
+        reduce_hist(h64)
+        L.check(lib.mfish_qsel_scan_u64(p, ws.data_ptr(), h64.data_ptr(), out.data_ptr(), info.data_ptr(), st))
     v0, v1 = out.tolist()
     gamma, n = info.tolist()
     return v0, v1, gamma, n

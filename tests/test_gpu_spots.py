@@ -293,6 +293,41 @@ def test_masked_percentile_bracketed_path_exact(kind, q):
     assert got == np.percentile(oracle.normalize_image(a)[mask], q)
 
 
+@pytest.mark.parametrize("kind", ["float", "uint8_ties", "two_values", "sparse_mask"])
+@pytest.mark.parametrize("q", [0.25, 0.9])
+@pytest.mark.parametrize("three_pass", [False, True])
+def test_masked_quantile_distributed_steps(kind, q, three_pass):
+    """the split-volume select (one pass per slab + all-reduced histograms / counters) on one rank: the
+    reduce callback is the identity, the result must be the two order statistics numpy's 'linear' method
+    interpolates between -- on the bracketed path, on its verified fallback (heavy ties overflow the
+    candidate buffer), and through the 64-bit three-pass select directly"""
+    from muscle_fish_b200 import device as D, taps as T
+    rng = np.random.default_rng(21)
+    shape = (200, 192, 40)
+    if kind == "float":
+        a = (rng.standard_normal(shape) * 10 + 160).astype(np.float32)
+        mask = rng.random(shape) < 0.5
+    elif kind == "uint8_ties":
+        a = rng.integers(0, 7, size=shape).astype(np.float32)
+        mask = rng.random(shape) < 0.7
+    elif kind == "two_values":
+        a = np.where(rng.random(shape) < 0.25, 3.0, 900.0).astype(np.float32)
+        mask = np.ones(shape, bool)
+    else:
+        a = (rng.random(shape) * 1e4).astype(np.float32)
+        mask = rng.random(shape) < 0.004
+    vol = D.ingest(a, want_minmax=False)
+    m = D.ingest(mask, as_mask=True)
+    calls = []
+    fn = D.masked_quantile_distributed_3pass if three_pass else D.masked_quantile_distributed
+    v0, v1, gamma, n = fn(vol.data, m, q, lambda t: calls.append(tuple(t.shape)))
+    srt = np.sort(a[mask])
+    _, k, g = T.percentile_virtual_index(len(srt), q * 100)
+    assert n == len(srt) and abs(gamma - g) < 1e-12
+    assert v0 == srt[k] and v1 == srt[min(k + 1, len(srt) - 1)]
+    assert len(calls) >= 3
+
+
 def test_blur_at_points_matches_dense_blur():
     from muscle_fish_b200 import device as D
     rng = np.random.default_rng(16)

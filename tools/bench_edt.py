@@ -1,6 +1,6 @@
 """EDT only, on the C2 nucleus mask: per-kernel CUDA-event times (mfish_profile_*), for the
-anisotropic and the isotropic transform.  Environment switches (MFISH_EDT_ZHULL=0, MFISH_EDT_XRING=0)
-select the round-1 kernels; with --check the result is compared against theirs bit for bit
+anisotropic and the isotropic transform.  The environment switch MFISH_EDT_V2=0
+selects the linked-hull kernels of round 1; the result is compared against theirs bit for bit
 (isotropic squares) / to 1e-6 (anisotropic)."""
 import os
 import subprocess
@@ -53,7 +53,7 @@ if __name__ == "__main__":
         sys.exit(0)
     import torch
     os.makedirs("gpurun_out", exist_ok=True)
-    base_env = dict(os.environ, MFISH_EDT_ZHULL="0", MFISH_EDT_XRING="0")
+    base_env = dict(os.environ, MFISH_EDT_V2="0")
     subprocess.run([sys.executable, __file__, "--child", "round1", "/tmp/edt_old.pt"], env=base_env, check=True)
     new = run("new")
     old = torch.load("/tmp/edt_old.pt")
