@@ -149,6 +149,13 @@ int mfish_log3d_peaks_f32(const float* in_dev, float* out_dev, float* tmp1_dev, 
                           const float* norm_minmax_dev, float threshold, void* cand_ws_dev, int64_t cand_cap,
                           int64_t* out_idx_dev, float* out_val_dev, uint32_t* count_dev, int64_t capacity,
                           void* stream);
+/* The same on the planes [out_z0, out_z1) of a z-extended slab (z-slab mosaics), taken as a cube of their own:
+ * LoG as mfish_log3d_range_f32, peak indices relative to that cube, zero padding at its two faces.       */
+int mfish_log3d_peaks_range_f32(const float* in_dev, float* out_dev, float* tmp1_dev, float* tmp2_dev,
+                                float* tmp3_dev, int64_t nz, int64_t nx, int64_t ny, double sigma,
+                                const float* norm_minmax_dev, int64_t out_z0, int64_t out_z1, float threshold,
+                                void* cand_ws_dev, int64_t cand_cap, int64_t* out_idx_dev, float* out_val_dev,
+                                uint32_t* count_dev, int64_t capacity, void* stream);
 
 /* ---- spot detection --------------------------------------------------- *
  * skimage.feature.peak_local_max(cube, threshold_abs=t, footprint=ones(3^4))
@@ -223,7 +230,8 @@ int mfish_qsel_scan_u64(int pass, void* ws_dev, const unsigned long long* hist64
  *   mfish_qselb_collect(...)   pair_dev = the bracketing values; one pass over the slab counts the masked
  *                  voxels, those below the bracket, and appends those inside it to cand_dev (cap floats,
  *                  cap % 64 == 0); counts_dev = int64 {n_masked, n_below, n_cand, overflow}
- *                  -> all-reduce counts_dev (sum)
+ *                  -> all-reduce counts_dev (sum); minmax_dev (optional float[2]): {min, max} over ALL
+ *                  voxels of the slab from the same pass (su.normalize_image's bounds: all-reduce min / max)
  *   mfish_qselb_ranks(ws, q, counts_dev, out, info)   global ranks relative to the candidates;
  *                  info_dev = {gamma, n_masked, status}; status 1: bracket missed / a buffer overflowed,
  *                  run the three-pass select instead
@@ -234,7 +242,7 @@ int mfish_qselb_sample_hist(const float* vol_dev, const uint8_t* mask_dev, int64
                             void* stream);
 int mfish_qselb_collect(const float* vol_dev, const uint8_t* mask_dev, int64_t n, void* ws_dev,
                         const float* pair_dev, float* cand_dev, int64_t cap, long long* counts_dev,
-                        void* stream);
+                        float* minmax_dev, void* stream);
 int mfish_qselb_ranks(void* ws_dev, double q, const long long* counts_dev, float* out_dev, double* info_dev,
                       void* stream);
 int mfish_qselb_cand_hist(const float* cand_dev, int64_t cap, int pass, void* ws_dev, void* stream);

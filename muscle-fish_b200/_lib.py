@@ -49,6 +49,8 @@ SIGNATURES = {
     "mfish_log3d_f32": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _d, _p, _p]),
     "mfish_log3d_range_f32": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _d, _p, _i64, _i64, _p]),
     "mfish_log3d_peaks_f32": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _d, _p, _f, _p, _i64, _p, _p, _p, _i64, _p]),
+    "mfish_log3d_peaks_range_f32": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _d, _p, _i64, _i64, _f, _p, _i64, _p,
+                                         _p, _p, _i64, _p]),
     "mfish_nms_compact_f32": (_i, [_p, _i64, _i64, _i64, _i64, _f, _p, _p, _p, _i64, _p]),
     "mfish_rank_prune": (_i, [_p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i, _p, _p, _p, _p]),
     "mfish_overlap_pairs": (_i, [_p, _i64, _i64, _i64, _i64, _i64, _p, _p, _p, _i64, _p]),
@@ -61,7 +63,7 @@ SIGNATURES = {
     "mfish_qsel_scan_u64": (_i, [_i, _p, _p, _p, _p, _p]),
     "mfish_qselb_begin": (_i, [_p, _d, _p]),
     "mfish_qselb_sample_hist": (_i, [_p, _p, _i64, _i, _p, _p]),
-    "mfish_qselb_collect": (_i, [_p, _p, _i64, _p, _p, _p, _i64, _p, _p]),
+    "mfish_qselb_collect": (_i, [_p, _p, _i64, _p, _p, _p, _i64, _p, _p, _p]),
     "mfish_qselb_ranks": (_i, [_p, _d, _p, _p, _p, _p]),
     "mfish_qselb_cand_hist": (_i, [_p, _i64, _i, _p, _p]),
     "mfish_blur_at_points": (_i, [_p, _i64, _i64, _i64, _p, _i64, _p, _i, _p, _i, _p, _i, _i, _p, _p, _p]),

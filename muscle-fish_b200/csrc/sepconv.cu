@@ -1413,8 +1413,8 @@ static int log3d_impl(const float* in_dev, float* out_dev, float* tmp1_dev, floa
   PassDesc px{tmp2_dev + off, tmp3_dev + off, out_dev + off, nullptr, out_z1 - out_z0, nx, ny, MFISH_AXIS_X, g.data(),
               d.data(), radius, MFISH_BOUNDARY_REFLECT, MFISH_CONV_LAST, (float)(-(sigma * sigma)), nullptr, st};
   if (cand != nullptr) {
-    if (radius > 16 || !whole) {
-      set_error("log3d: fused candidate emission supports radius <= 16 on whole volumes");
+    if (radius > 16) {
+      set_error("log3d: fused candidate emission supports radius <= 16");
       return MFISH_ERR_UNSUPPORTED;
     }
     px.cand_thr = cand_thr;
@@ -1443,23 +1443,37 @@ int nms_verify_candidates(const float* cube, int64_t nz, int64_t nx, int64_t ny,
 // append); a second, tiny kernel checks the full 3x3x3 neighbourhood of those candidates only.  Saves the
 // stand-alone NMS pass over the volume.  cand_ws_dev: (cand_cap + 1) uint32 of scratch.  *count_dev =
 // 0xFFFFFFFF reports a candidate overflow: run mfish_nms_compact_f32 on out_dev instead.
+// The planes [out_z0, out_z1) of a z-extended slab are treated as a cube of their own: LoG as
+// mfish_log3d_range_f32, candidates and peak indices relative to that cube ((x ny + y)(out_z1 - out_z0) + z -
+// out_z0), zero padding at its two faces -- a z-slab keeps the peaks of its own planes, which lie inside.
+extern "C" int mfish_log3d_peaks_range_f32(const float* in_dev, float* out_dev, float* tmp1_dev, float* tmp2_dev,
+                                           float* tmp3_dev, int64_t nz, int64_t nx, int64_t ny, double sigma,
+                                           const float* norm_minmax_dev, int64_t out_z0, int64_t out_z1,
+                                           float threshold, void* cand_ws_dev, int64_t cand_cap, int64_t* out_idx_dev,
+                                           float* out_val_dev, uint32_t* count_dev, int64_t capacity, void* stream) {
+  MFISH_REQUIRE(cand_ws_dev && out_idx_dev && out_val_dev && count_dev, "log3d_peaks: null pointer");
+  MFISH_REQUIRE(cand_cap > 0 && cand_cap < (1ll << 31) && capacity > 0, "log3d_peaks: bad capacity");
+  MFISH_REQUIRE(threshold >= 0.f, "log3d_peaks: threshold must be >= 0");
+  MFISH_REQUIRE(out_z0 >= 0 && out_z0 < out_z1 && out_z1 <= nz, "log3d_peaks: bad plane range");
+  cudaStream_t st = as_stream(stream);
+  uint32_t* cand_count = reinterpret_cast<uint32_t*>(cand_ws_dev);
+  uint32_t* cand = cand_count + 1;
+  MFISH_CUDA(cudaMemsetAsync(cand_count, 0, sizeof(uint32_t), st));
+  int rc = log3d_impl(in_dev, out_dev, tmp1_dev, tmp2_dev, tmp3_dev, nz, nx, ny, sigma, norm_minmax_dev, out_z0,
+                      out_z1, threshold, cand, cand_count, (uint32_t)cand_cap, stream);
+  if (rc != MFISH_OK) return rc;
+  return nms_verify_candidates(out_dev + out_z0 * nx * ny, out_z1 - out_z0, nx, ny, threshold, cand, cand_count,
+                               (uint32_t)cand_cap, out_idx_dev, out_val_dev, count_dev, capacity, st);
+}
+
 extern "C" int mfish_log3d_peaks_f32(const float* in_dev, float* out_dev, float* tmp1_dev, float* tmp2_dev,
                                      float* tmp3_dev, int64_t nz, int64_t nx, int64_t ny, double sigma,
                                      const float* norm_minmax_dev, float threshold, void* cand_ws_dev,
                                      int64_t cand_cap, int64_t* out_idx_dev, float* out_val_dev, uint32_t* count_dev,
                                      int64_t capacity, void* stream) {
-  MFISH_REQUIRE(cand_ws_dev && out_idx_dev && out_val_dev && count_dev, "log3d_peaks: null pointer");
-  MFISH_REQUIRE(cand_cap > 0 && cand_cap < (1ll << 31) && capacity > 0, "log3d_peaks: bad capacity");
-  MFISH_REQUIRE(threshold >= 0.f, "log3d_peaks: threshold must be >= 0");
-  cudaStream_t st = as_stream(stream);
-  uint32_t* cand_count = reinterpret_cast<uint32_t*>(cand_ws_dev);
-  uint32_t* cand = cand_count + 1;
-  MFISH_CUDA(cudaMemsetAsync(cand_count, 0, sizeof(uint32_t), st));
-  int rc = log3d_impl(in_dev, out_dev, tmp1_dev, tmp2_dev, tmp3_dev, nz, nx, ny, sigma, norm_minmax_dev, 0, nz,
-                      threshold, cand, cand_count, (uint32_t)cand_cap, stream);
-  if (rc != MFISH_OK) return rc;
-  return nms_verify_candidates(out_dev, nz, nx, ny, threshold, cand, cand_count, (uint32_t)cand_cap, out_idx_dev,
-                               out_val_dev, count_dev, capacity, st);
+  return mfish_log3d_peaks_range_f32(in_dev, out_dev, tmp1_dev, tmp2_dev, tmp3_dev, nz, nx, ny, sigma,
+                                     norm_minmax_dev, 0, nz, threshold, cand_ws_dev, cand_cap, out_idx_dev,
+                                     out_val_dev, count_dev, capacity, stream);
 }
 
 extern "C" int mfish_log3d_f32(const float* in_dev, float* out_dev, float* tmp1_dev, float* tmp2_dev,

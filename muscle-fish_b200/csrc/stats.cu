@@ -709,7 +709,7 @@ extern "C" int mfish_qselb_sample_hist(const float* vol_dev, const uint8_t* mask
 
 extern "C" int mfish_qselb_collect(const float* vol_dev, const uint8_t* mask_dev, int64_t n, void* ws_dev,
                                    const float* pair_dev, float* cand_dev, int64_t cap, long long* counts_dev,
-                                   void* stream) {
+                                   float* minmax_dev, void* stream) {
   MFISH_REQUIRE(vol_dev && mask_dev && ws_dev && pair_dev && cand_dev && counts_dev, "qselb_collect: null pointer");
   MFISH_REQUIRE(n > 0 && cap >= QSEG && cap % QSEG == 0, "qselb_collect: bad sizes");
   cudaStream_t st = as_stream(stream);
@@ -719,7 +719,15 @@ extern "C" int mfish_qselb_collect(const float* vol_dev, const uint8_t* mask_dev
   qsel_bracket_kernel<<<1, 32, 0, st>>>(ws, pair_dev);
   MFISH_CUDA(cudaMemsetAsync(cand_dev, 0x7f, (size_t)cap * sizeof(float), st));
   qsel_set_cap_kernel<<<1, 1, 0, st>>>(ws, (unsigned long long)cap);
-  qsel_range_kernel<false><<<blocks, 256, 0, st>>>(vol_dev, mask_dev, n, ws, cand_dev, nullptr);
+  if (minmax_dev) {  // the slab's own {min, max} over ALL voxels from the same pass
+    uint32_t* mm = reinterpret_cast<uint32_t*>(minmax_dev);
+    qsel_mm_init_kernel<<<1, 1, 0, st>>>(mm);
+    qsel_range_kernel<true><<<blocks, 256, 0, st>>>(vol_dev, mask_dev, n, ws, cand_dev, mm);
+    qsel_mm_finalize_kernel<<<1, 1, 0, st>>>(mm);
+    count_launch(2);
+  } else {
+    qsel_range_kernel<false><<<blocks, 256, 0, st>>>(vol_dev, mask_dev, n, ws, cand_dev, nullptr);
+  }
   qsel_export_counts_kernel<<<1, 1, 0, st>>>(ws, counts_dev);
   count_launch(4);
   return check_launch("qselb_collect");

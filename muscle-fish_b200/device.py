@@ -387,18 +387,21 @@ def detect_peaks(cube: torch.Tensor, threshold: float, capacity: int | None = No
 
 
 def log_peaks_async(vol: Volume, sigma: float, threshold: float, out: torch.Tensor | None = None,
-                    capacity: int | None = None):
+                    capacity: int | None = None, z_range=None):
     """One scale of blob_log in a single library call: LoG volume + thresholded 26-neighbour NMS +
     compaction, the candidate test fused into the last LoG pass.  Returns ``(log_volume, finish)``;
-    ``finish()`` waits for the count and returns (raster_idx, value) like ``detect_peaks``."""
+    ``finish()`` waits for the count and returns (raster_idx, value) like ``detect_peaks``.
+    ``z_range=(a, b)`` (z-extended slabs): only the planes [a, b) are produced and searched, as a cube of
+    their own -- raster indices are relative to ``log_volume[a:b]``."""
     if float(threshold) < 0:
         raise ValueError("negative thresholds are not supported (reference zero-pads the scale axis)")
     d = vol.data
     shp, dev = d.shape, d.device
     nz, nx, ny = shp
+    za, zb = (0, nz) if z_range is None else (int(z_range[0]), int(z_range[1]))
     if d.numel() >= (1 << 32):  # candidate offsets are 32-bit: fall back to the two-call form
-        log = log_volume(vol, sigma, out)
-        return log, detect_peaks_async(log, threshold, capacity)
+        log = log_volume(vol, sigma, out, z_range=z_range)
+        return log, detect_peaks_async(log[za:zb], threshold, capacity)
     if out is None:
         out = torch.empty(shp, dtype=torch.float32, device=dev)
     t1 = WS.get("log1", shp, torch.float32, dev)
@@ -411,16 +414,16 @@ def log_peaks_async(vol: Volume, sigma: float, threshold: float, out: torch.Tens
     count = torch.zeros(1, dtype=torch.int32, device=dev)
     idx = WS.get("pk_idx", (cap,), torch.int64, dev)
     val = WS.get("pk_val", (cap,), torch.float32, dev)
-    L.check(L.lib().mfish_log3d_peaks_f32(d.data_ptr(), out.data_ptr(), t1.data_ptr(), t2.data_ptr(), t3.data_ptr(),
-                                          nz, nx, ny, float(sigma),
-                                          vol.minmax.data_ptr() if vol.minmax is not None else None, thr,
-                                          cand_ws.data_ptr(), cand_cap, idx.data_ptr(), val.data_ptr(),
-                                          count.data_ptr(), cap, _stream()))
+    L.check(L.lib().mfish_log3d_peaks_range_f32(d.data_ptr(), out.data_ptr(), t1.data_ptr(), t2.data_ptr(),
+                                                t3.data_ptr(), nz, nx, ny, float(sigma),
+                                                vol.minmax.data_ptr() if vol.minmax is not None else None, za, zb,
+                                                thr, cand_ws.data_ptr(), cand_cap, idx.data_ptr(), val.data_ptr(),
+                                                count.data_ptr(), cap, _stream()))
 
     def finish():
         n = int(count.item()) & 0xFFFFFFFF
         if n == 0xFFFFFFFF or n > cap:  # candidate overflow / result overflow: stand-alone kernel
-            return detect_peaks(out, threshold, None if n == 0xFFFFFFFF else int(n * 1.25) + 1024)
+            return detect_peaks(out[za:zb], threshold, None if n == 0xFFFFFFFF else int(n * 1.25) + 1024)
         return idx[:n], val[:n]
 
     return out, finish
@@ -666,13 +669,14 @@ def masked_percentile(vol: Volume, mask: torch.Tensor, q_percent: float) -> floa
     return masked_percentile_async(vol, mask, q_percent)()
 
 
-def masked_quantile_distributed(vol: torch.Tensor, mask: torch.Tensor, q: float, reduce_hist):
+def masked_quantile_distributed(vol: torch.Tensor, mask: torch.Tensor, q: float, reduce_hist, minmax_out=None):
     """Masked select of the two order statistics around quantile ``q`` over a volume that is split across
     ranks; ``reduce_hist(tensor)`` sums an integer tensor over the ranks in place.  ONE pass over the slab:
     a 1/64 sample (its 2x2048-bin histograms all-reduced) brackets the wanted ranks, the full pass counts the
     masked voxels below the bracket and collects those inside it, and the exact ranks are selected among the
     candidates of all ranks (their histograms all-reduced).  A missed bracket (checked identically on every
-    rank) falls back to the three-pass radix select with 64-bit bins.
+    rank) falls back to the three-pass radix select with 64-bit bins.  ``minmax_out`` (float32[2] on the device):
+    the slab's own {min, max} over ALL voxels, reduced by the same pass.
     Returns (value[k], value[k+1], gamma, n_masked) of the RAW values."""
     dev = vol.device
     lib = L.lib()
@@ -693,7 +697,8 @@ def masked_quantile_distributed(vol: torch.Tensor, mask: torch.Tensor, q: float,
     cap = (max(1 << 20, n // 64) + 63) // 64 * 64
     cand = WS.get("qcand", (cap,), torch.float32, dev)
     L.check(lib.mfish_qselb_collect(vol.data_ptr(), mask.data_ptr(), n, ws.data_ptr(), pair.data_ptr(),
-                                    cand.data_ptr(), cap, counts.data_ptr(), st))
+                                    cand.data_ptr(), cap, counts.data_ptr(),
+                                    minmax_out.data_ptr() if minmax_out is not None else None, st))
     reduce_hist(counts)
     L.check(lib.mfish_qselb_ranks(ws.data_ptr(), float(q), counts.data_ptr(), out.data_ptr(), info.data_ptr(), st))
     for p in range(3):

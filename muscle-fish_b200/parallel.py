@@ -208,7 +208,8 @@ def run_batch(n_stacks: int, loader, shape_xyz, img_dtype=torch.uint16, sigma=2.
 
 
 class SlabLayout:
-    """z-slab ownership (filters, NMS) and x-slab ownership (EDT z pass) of a [nz][nx][ny] mosaic."""
+    """z-slab ownership (filters, NMS, row scan), y-slab ownership (EDT envelope passes; or x-slab ownership for
+    the z pass alone) of a [nz][nx][ny] mosaic."""
 
     def __init__(self, nz, nx, ny, rank=None, world=None):
         self.nz, self.nx, self.ny = int(nz), int(nx), int(ny)
@@ -216,6 +217,10 @@ class SlabLayout:
         self.world = dist.get_world_size() if world is None else world
         self.zb = split_bounds(self.nz, self.world)
         self.xb = split_bounds(self.nx, self.world)
+        self.yb = split_bounds(self.ny, self.world)
+
+    y0 = property(lambda self: self.yb[self.rank][0])
+    y1 = property(lambda self: self.yb[self.rank][1])
 
     @property
     def z0(self):
@@ -353,6 +358,30 @@ def repartition_x_to_y(t: torch.Tensor, lay: "XSlabLayout", group=None) -> torch
     return out
 
 
+def repartition_z_to_y(t: torch.Tensor, lay: SlabLayout, group=None) -> torch.Tensor:
+    """[nz_local][nx][ny] (z-slab) -> [nz][nx][ny_local] (y-slab): the all-to-all between the EDT's row scan and
+    its two envelope passes when the mosaic is cut along z (2 bytes per voxel on the wire instead of the 4 of the
+    in-plane squares; a peer's block arrives where it belongs, nothing to unpack)."""
+    P, r = lay.world, lay.rank
+    if P == 1:
+        return t
+    out = _buf("z2y_out", (lay.nz, lay.nx, lay.y1 - lay.y0), t.dtype, t.device)
+    ops = []
+    for s in range(P):
+        if s == r:
+            continue
+        yb, ye = lay.yb[s]
+        snd = _buf(f"z2y_send{s}", (t.shape[0], lay.nx, ye - yb), t.dtype, t.device)
+        snd.copy_(t[:, :, yb:ye])
+        ops.append(dist.P2POp(dist.isend, _wire(snd), s, group))
+        ops.append(dist.P2POp(dist.irecv, _wire(out[lay.zb[s][0]:lay.zb[s][1]]), s, group))
+    out[lay.z0:lay.z1] = t[:, :, lay.y0:lay.y1]
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return out
+
+
 def repartition_z_to_x(t: torch.Tensor, lay: SlabLayout, group=None) -> torch.Tensor:
     """[nz_local][nx][ny] (z-slab) -> [nz][nx_local][ny] (x-slab): the all-to-all before the EDT z pass."""
     P, r = lay.world, lay.rank
@@ -414,6 +443,8 @@ class DeviceOps:
         D._require_cuda()
         self.D = D
 
+    fused_range_peaks = True
+
     def minmax(self, slab):
         return self.D.minmax(slab)
 
@@ -443,15 +474,21 @@ class DeviceOps:
         return self.D.blur_at_points_dev(self.D.Volume(ext, mm), zxy.to(torch.int32).contiguous(), sigma_xyz,
                                          "nearest")
 
-    # masked radix select in three passes; `reduce` all-reduces the histogram between hist and scan
+    # masked select of the two order statistics around quantile q; `reduce` all-reduces (sum) the integer
+    # tensors it is handed (sample / candidate histograms, counters)
     def masked_quantile(self, vol, mask, q, reduce):
         return self.D.masked_quantile_distributed(vol, mask, q, reduce)
 
-    def log_peaks(self, ext, mm, sigma, thr):
-        """LoG + thresholded NMS of a whole (extended) slab in one library call
-        -> (raster (x*ny + y)*nz + z int64 [n], value float32 [n]), unordered"""
+    def masked_quantile_minmax(self, vol, mask, q, reduce):
+        """the same, and the slab's own {min, max} over all voxels from the same pass -> (v0, v1, gamma, n, mm)"""
+        mm = torch.empty(2, dtype=torch.float32, device=vol.device)
+        return self.D.masked_quantile_distributed(vol, mask, q, reduce, minmax_out=mm) + (mm,)
+
+    def log_peaks(self, ext, mm, sigma, thr, z_range=None):
+        """LoG + thresholded NMS of an (extended) slab in one library call, on its planes ``z_range`` only if
+        given -> (raster (x*ny + y)*nzs + z int64 [n] over those nzs planes, value float32 [n]), unordered"""
         out = _buf("log_ext", ext.shape, torch.float32, ext.device)
-        _, finish = self.D.log_peaks_async(self.D.Volume(ext, mm), sigma, thr, out=out)
+        _, finish = self.D.log_peaks_async(self.D.Volume(ext, mm), sigma, thr, out=out, z_range=z_range)
         return finish()
 
     def edt_rowscan(self, mask):
@@ -490,11 +527,14 @@ class _ZDecomp:
         # rule and are not used); reflect applies only at the global faces
         a = radius if lo else 0
         b = ext.shape[0] - (radius if hi else 0)
-        with _phase("log"):
-            log_ext = ops.log(ext, mm, sigma, z_range=(a, b))
         nzs = b - a
+        with _phase("log"):
+            if getattr(ops, "fused_range_peaks", False):  # candidate test inside the last LoG pass
+                ras_l, val = ops.log_peaks(ext, mm, sigma, t_spot, z_range=(a, b))
+            else:
+                log_ext = ops.log(ext, mm, sigma, z_range=(a, b))
+                ras_l, val = ops.peaks(log_ext[a:b], t_spot)
         with _phase("peaks"):
-            ras_l, val = ops.peaks(log_ext[a:b], t_spot)
             # local raster ((x*ny + y)*nzs + zs) -> global raster ((x*ny + y)*nz + zg); keep own planes
             zs = ras_l % nzs
             xy = ras_l // nzs
@@ -555,9 +595,16 @@ def slab_find_spots_snrfilter(img_slab: torch.Tensor, mask_slab: torch.Tensor, l
         dec = _XDecomp(lay) if isinstance(lay, XSlabLayout) else _ZDecomp(lay)
     dev = img_slab.device
     nz, nx, ny = lay.nz, lay.nx, lay.ny
-    # 1. global min / max
+    def reduce_hist(h):
+        dist.all_reduce(h, op=dist.ReduceOp.SUM, group=group)
+    # 1. global min / max -- and, where the ops offer it, the P25 baseline's order statistics (step 6) from the
+    #    same single pass over the raw slab (the percentile is selected on raw values and mapped afterwards)
+    quant = None
     with _phase("minmax"):
-        mm = ops.minmax(img_slab).clone()
+        if hasattr(ops, "masked_quantile_minmax"):
+            *quant, mm = ops.masked_quantile_minmax(img_slab, mask_slab, 0.25, reduce_hist)
+        else:
+            mm = ops.minmax(img_slab).clone()
         lo_hi = mm.to(torch.float32)
         lo_t, hi_t = lo_hi[0:1].clone(), lo_hi[1:2].clone()
         dist.all_reduce(lo_t, op=dist.ReduceOp.MIN, group=group)
@@ -609,10 +656,8 @@ def slab_find_spots_snrfilter(img_slab: torch.Tensor, mask_slab: torch.Tensor, l
             both[1, ownz] = ops.blur_at_points(ext, mm, dec.ext_pts(zo, xo, yo), (3, 3, 0.3))
         dist.all_reduce(both, op=dist.ReduceOp.SUM, group=group)
     # 6. P25 baseline over the (global) mask
-    def reduce_hist(h):
-        dist.all_reduce(h, op=dist.ReduceOp.SUM, group=group)
     with _phase("quantile"):
-        v0, v1, gamma, n = ops.masked_quantile(img_slab, mask_slab, 0.25, reduce_hist)
+        v0, v1, gamma, n = quant if quant is not None else ops.masked_quantile(img_slab, mask_slab, 0.25, reduce_hist)
     if n == 0:
         raise IndexError("percentile of an empty selection (mask selects no voxel)")
     a01 = T.interp01(np.array([v0, v1], dtype=np.float64), lo_v, hi_v)
@@ -670,6 +715,20 @@ def slab_edt(notnuc_slab: torch.Tensor, lay: SlabLayout, sampling_xyz=(1.0, 1.0,
     return repartition_x_to_z(dx, lay, group) if back_to_z else dx
 
 
+def slab_edt_rows(notnuc_slab: torch.Tensor, lay: SlabLayout, sampling_xyz=(1.0, 1.0, 1.0), ops=None, group=None):
+    """The same transform with the cut moved in front of BOTH envelope passes: row scan on the z-slab, one
+    all-to-all of the uint16 row distances into y-slabs (half the bytes of ``slab_edt``'s 4-byte in-plane squares),
+    x and z passes there.  Returns the distance map in y-slab layout ``[nz][nx][ny_local]``
+    (``yslab_spot_distances`` looks spots up in it)."""
+    ops = ops or DeviceOps()
+    with _phase("edt_rowscan"):
+        dy = ops.edt_rowscan(notnuc_slab)
+    with _phase("edt_all_to_all"):
+        dyy = repartition_z_to_y(dy, lay, group)
+    with _phase("edt_xz"):
+        return ops.edt_xz(dyy, sampling_xyz, lay.ny)
+
+
 def slab_spot_distances(dist_xslab: torch.Tensor, spots_xyz: np.ndarray, lay: SlabLayout, ops=None, group=None):
     """EDT value at each spot (the interpn gather of nocodazole/fish_analysis_noco.py:297-298) from the
     x-slab partitioned distance map; every rank gets the full vector."""
@@ -703,8 +762,9 @@ def xslab_edt(notnuc_slab: torch.Tensor, lay: XSlabLayout, sampling_xyz=(1.0, 1.
         return ops.edt_xz(dyy, sampling_xyz, lay.ny)
 
 
-def xslab_spot_distances(dist_yslab: torch.Tensor, spots_xyz: np.ndarray, lay: XSlabLayout, ops=None, group=None):
-    """EDT value at each spot from the y-slab partitioned distance map; every rank gets the full vector."""
+def yslab_spot_distances(dist_yslab: torch.Tensor, spots_xyz: np.ndarray, lay, ops=None, group=None):
+    """EDT value at each spot from the y-slab partitioned distance map (``lay``: either layout; both carry the
+    y bounds); every rank gets the full vector."""
     ops = ops or DeviceOps()
     dev = dist_yslab.device
     s = torch.as_tensor(np.ascontiguousarray(np.asarray(spots_xyz)[:, :3]).astype(np.int64)).to(dev)
@@ -720,19 +780,25 @@ def xslab_spot_distances(dist_yslab: torch.Tensor, spots_xyz: np.ndarray, lay: X
     return out.cpu().numpy()
 
 
+xslab_spot_distances = yslab_spot_distances
+
+
 def slab_analyze(img_slab: torch.Tensor, mask_slab: torch.Tensor, notnuc_slab: torch.Tensor, lay,
                  sigma=2.0, t_spot=0.025, sampling_xyz=(1.0, 1.0, 1.0), snr=None, ops=None, group=None,
-                 edt_group=None, full_table=True):
+                 edt_group=None, full_table=True, edt_wire="rows"):
     """The whole path on a slab-decomposed mosaic (``lay``: ``SlabLayout`` = z-slabs, ``XSlabLayout`` = x-slabs):
     ``slab_find_spots_snrfilter`` + the distance transform + the per-spot distances.  The distance transform
     does not depend on the spots and its chain has no host round trip: given ``edt_group`` (a second
     communicator over the same ranks, ``dist.new_group()``) on CUDA tensors it is queued first on a side
     stream, so its all-to-all and kernels run beside the spot chain's halo exchange, small collectives and
-    host round trips.  Returns the spot dict plus ``spot_dist`` (float64 per kept spot) and ``dist_slab`` (the
-    distance map: x-slab partitioned for z-slab input, y-slab partitioned for x-slab input)."""
+    host round trips.  ``edt_wire`` (z-slabs): "rows" = uint16 row distances cross the cut, both envelope passes
+    run on y-slabs (``slab_edt_rows``); "squares" = the 4-byte in-plane squares cross it, z pass on x-slabs
+    (``slab_edt``).  Returns the spot dict plus ``spot_dist`` (float64 per kept spot) and ``dist_slab`` (the
+    distance map: y-slab partitioned, or x-slab partitioned for z-slabs with ``edt_wire="squares"``)."""
     xs = isinstance(lay, XSlabLayout)
-    edt_fn = xslab_edt if xs else slab_edt
-    dist_fn = xslab_spot_distances if xs else slab_spot_distances
+    squares = (not xs) and edt_wire == "squares"
+    edt_fn = xslab_edt if xs else (slab_edt if squares else slab_edt_rows)
+    dist_fn = slab_spot_distances if squares else yslab_spot_distances
     if edt_group is not None and img_slab.is_cuda:
         from . import device as D
         cur = torch.cuda.current_stream()
@@ -750,6 +816,6 @@ def slab_analyze(img_slab: torch.Tensor, mask_slab: torch.Tensor, notnuc_slab: t
         dmap = edt_fn(notnuc_slab, lay, sampling_xyz, ops=ops, group=group)
     res["spot_dist"] = dist_fn(dmap, res["spots"], lay, ops=ops, group=group)
     res["dist_slab"] = dmap
-    if not xs:
+    if squares:
         res["dist_xslab"] = dmap
     return res

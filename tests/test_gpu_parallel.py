@@ -47,6 +47,9 @@ def _job(rank, world, port, outdir):
                               edt_group=dist.new_group())
         torch.cuda.synchronize()
         assert np.array_equal(both["spots"], res["spots"]) and np.array_equal(both["spot_dist"], sd)
+        zy = both["dist_slab"].cpu().numpy()  # z-slabs, uint16 rows on the wire: y-slab partitioned map
+        sq = P.slab_analyze(img, fib, notnuc, lay, sigma=2.0, t_spot=0.025, sampling_xyz=ANISO, edt_wire="squares")
+        assert np.array_equal(sq["spot_dist"], sd)
         # x-slab decomposition of the same stack: same global result
         xlay = P.XSlabLayout(SHAPE[2], SHAPE[0], SHAPE[1])
         xs = slice(xlay.x0, xlay.x1)
@@ -59,7 +62,7 @@ def _job(rank, world, port, outdir):
         dy_ = xres["dist_slab"].cpu().numpy()
         np.save(os.path.join(outdir, f"r{rank}.npy"),
                 np.array([res["spots"], res["intensity"], res["baseline"], sd, dz, (lay.z0, lay.z1), dy_,
-                          (xlay.y0, xlay.y1)], dtype=object), allow_pickle=True)
+                          (xlay.y0, xlay.y1), zy], dtype=object), allow_pickle=True)
     finally:
         dist.destroy_process_group()
 
@@ -76,12 +79,13 @@ def _check(world):
                                                       pair_order="sorted")
     grass = oracle.distance_transform_edt(np.logical_not(st["nuc_mask"]), sampling=ANISO)
     assert len(ref_spots) > 50
-    for spots, inten, baseline, sd, dz, (z0, z1), dy_, (y0, y1) in res:
+    for spots, inten, baseline, sd, dz, (z0, z1), dy_, (y0, y1), zy in res:
         assert match_fraction(spots, ref_spots) >= 0.999
         np.testing.assert_allclose(np.sort(inten), np.sort([r[4] for r in ref_data[1:]]), rtol=1e-6)
         np.testing.assert_allclose(sd, oracle.edt_gather(grass, spots, ANISO), rtol=1e-6)
         np.testing.assert_allclose(dz, grass.transpose(2, 0, 1)[z0:z1], rtol=1e-6)
         np.testing.assert_allclose(dy_, grass.transpose(2, 0, 1)[:, :, y0:y1], rtol=1e-6)
+        np.testing.assert_allclose(zy, grass.transpose(2, 0, 1)[:, :, y0:y1], rtol=1e-6)
 
 
 def test_slab_drivers_world1():

@@ -328,6 +328,25 @@ def test_masked_quantile_distributed_steps(kind, q, three_pass):
     assert len(calls) >= 3
 
 
+@pytest.mark.parametrize("z_range", [(3, 25), (0, 20), (8, 28), (0, 28)])
+def test_log_peaks_on_a_plane_range_equals_two_calls(z_range):
+    """z-extended slabs: LoG + fused candidate test on the planes [a, b) only == ranged LoG, then the
+    stand-alone NMS on that sub-cube (same peaks, same values; indices relative to the sub-cube)"""
+    import torch
+    from muscle_fish_b200 import device as D, synth
+    st = synth.make_stack(shape=(96, 80, 28), n_spots=150, n_nuclei=2, seed=5)
+    vol = D.ingest(st["img"])
+    a, b = z_range
+    log = D.log_volume(vol, 2.0, z_range=z_range)
+    r0, v0 = D.detect_peaks(log[a:b].contiguous(), 0.025)
+    log2, finish = D.log_peaks_async(vol, 2.0, 0.025, z_range=z_range)
+    r1, v1 = finish()
+    assert torch.equal(log2[a:b], log[a:b])
+    o0, o1 = torch.argsort(r0), torch.argsort(r1)
+    assert r0.numel() > 20
+    assert torch.equal(r0[o0], r1[o1]) and torch.equal(v0[o0], v1[o1])
+
+
 def test_blur_at_points_matches_dense_blur():
     from muscle_fish_b200 import device as D
     rng = np.random.default_rng(16)

@@ -225,10 +225,15 @@ def _spots_job(rank, world, seed):
     # the combined driver (CPU tensors: no side stream) returns the same thing
     both = P.slab_analyze(img[lay.z0:lay.z1].clone(), fib[lay.z0:lay.z1].clone(), notnuc[lay.z0:lay.z1].clone(), lay,
                           sigma=2.0, t_spot=0.025, sampling_xyz=ANISO, ops=ops, edt_group=dist.new_group())
-    assert np.array_equal(both["spots"], res["spots"]) and np.array_equal(both["spot_dist"], sd)
-    assert torch.equal(both["dist_xslab"], dmap)
+    assert np.array_equal(both["spots"], res["spots"])
+    np.testing.assert_allclose(both["spot_dist"], sd, rtol=1e-6)  # (the oracle ops take two scipy routes)
+    assert torch.equal(both["dist_slab"], P.slab_edt_rows(notnuc[lay.z0:lay.z1].clone(), lay, ANISO, ops=ops))
+    sq = P.slab_analyze(img[lay.z0:lay.z1].clone(), fib[lay.z0:lay.z1].clone(), notnuc[lay.z0:lay.z1].clone(), lay,
+                        sigma=2.0, t_spot=0.025, sampling_xyz=ANISO, ops=ops, edt_wire="squares")
+    assert np.array_equal(sq["spot_dist"], sd) and torch.equal(sq["dist_xslab"], dmap)
+    ymap = both["dist_slab"].numpy()
     return [res["spots"], res["spots_masked"], res["intensity"], res["baseline"], res["snr"], sd, dz.numpy(),
-            (lay.z0, lay.z1)]
+            (lay.z0, lay.z1), ymap, (lay.y0, lay.y1)]
 
 
 def test_slab_pipeline_world2_equals_unsplit_oracle():
@@ -239,7 +244,7 @@ def test_slab_pipeline_world2_equals_unsplit_oracle():
                                                       pair_order="sorted")
     grass = oracle.distance_transform_edt(np.logical_not(st["nuc_mask"]), sampling=ANISO)
     for r in range(2):
-        spots, masked, inten, baseline, snr, sd, dz, (z0, z1) = res[r]
+        spots, masked, inten, baseline, snr, sd, dz, (z0, z1), ymap, (y0, y1) = res[r]
         assert len(ref_spots) > 10
         assert match_fraction(spots, ref_spots) >= 0.999
         assert len(masked) == len(ref_data) - 1
@@ -247,6 +252,7 @@ def test_slab_pipeline_world2_equals_unsplit_oracle():
         np.testing.assert_allclose(np.sort(inten), np.sort(ref_int), rtol=1e-6)
         np.testing.assert_allclose(sd, oracle.edt_gather(grass, spots, ANISO), rtol=1e-6)
         np.testing.assert_allclose(dz, grass.transpose(2, 0, 1)[z0:z1], rtol=1e-6)
+        np.testing.assert_allclose(ymap, grass.transpose(2, 0, 1)[:, :, y0:y1], rtol=1e-6)
     np.testing.assert_array_equal(res[0][0], res[1][0])  # every rank holds the same global result
 
 
