@@ -423,7 +423,13 @@ def bench_slab(ctx, args):
             lay = P.XSlabLayout(Z, X, Y)
             st = synth.make_stack_device(shape, ns, nn, seed, x_range=(lay.x0, lay.x1))
         notnuc = (st["nuc_mask"] == 0).to(torch.uint8)
-        return lay, st["img"], st["fiber_mask"], notnuc
+        img = st["img"]
+        if kind == "z":  # the resident slab sits where the halo exchange extends it (no per-step copy of it)
+            home = P.slab_input_buffer(lay, SIGMA, img.dtype, img.device)
+            if home is not None:
+                home.copy_(img)
+                img = home
+        return lay, img, st["fiber_mask"], notnuc
 
     def cleanup():
         P.clear_buffers()
@@ -468,7 +474,9 @@ def bench_slab(ctx, args):
     nvox = float(X) * Y * Z
     steps = max(1, min(args.steps, args.slab_steps))
     out = {"matches_n1": matches, "mosaic": [X, Y, Z], "n_gpus": world, "unit": UNIT, "steps": steps,
-           "scaling": "strong", "nvlink_peer_copy_reference_gbs": 770.0}
+           "scaling": "strong", "nvlink_peer_copy_reference_gbs": 770.0,
+           "exchange": "peer memory (mfish_copy2d into symmetric buffers)" if P._PEER_STATE["ok"] is not False and
+           os.environ.get("MFISH_P2P", "1") != "0" else "NCCL send/recv"}
     radius = 8
     for kind in ("z", "x"):
         lay, img, fib, notnuc = slabs(kind, shape, ns, nn, seed)
@@ -481,13 +489,15 @@ def bench_slab(ctx, args):
         dt, res = ctx.timed(step, steps, 2)
         ms = dt / steps * 1e3
         # one more step with per-phase wall clocks (synchronising: the two chains then run one after the other)
+        # (an untimed one first: without the second communicator the EDT's exchange makes new connections)
+        P.slab_analyze(img, fib, notnuc, lay, sigma=SIGMA, t_spot=T_SPOT, sampling_xyz=SAMPLING, full_table=False)
         P.PHASES = {}
         P.slab_analyze(img, fib, notnuc, lay, sigma=SIGMA, t_spot=T_SPOT, sampling_xyz=SAMPLING, full_table=False)
         phases = {k: round(val * 1e3, 3) for k, val in P.PHASES.items()}
         P.PHASES = None
         if kind == "z":
             halo_bytes = 2 * (radius + 1) * X * Y * 4  # received by an interior rank
-            a2a_bytes = (Z / world) * X * Y * 4 * (world - 1) / world  # sent by every rank (int32 f2)
+            a2a_bytes = (Z / world) * X * Y * 2 * (world - 1) / world  # sent by every rank (uint16 row distances)
         else:
             halo_bytes = 2 * 12 * Z * Y * 4
             a2a_bytes = Z * (X / world) * Y * 2 * (world - 1) / world  # uint16 row distances

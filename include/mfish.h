@@ -369,6 +369,18 @@ int mfish_onehot_gaussian_f32(const int32_t* labels_dev, int64_t nz, int64_t nx,
                               int64_t total_elems, const double* sigma_zxy_host, float* out_dev,
                               float* tmp_dev, void* stream);
 
+/* ---- block moves between slabs (NVLink peer memory) ------------------------ *
+ * nrows rows of row_bytes from src (rows src_pitch apart) to dst (rows dst_pitch apart); all four and both
+ * base addresses multiples of 16.  dst may be a buffer of a PEER GPU mapped into this process (symmetric
+ * memory): the kernel then packs and transfers in one go -- the halo exchange of the filters and the
+ * all-to-all in front of the EDT's envelope passes of a slab-decomposed mosaic (BASELINE configs[3]).        */
+int mfish_copy2d(void* dst_dev, int64_t dst_pitch, const void* src_dev, int64_t src_pitch, int64_t row_bytes,
+                 int64_t nrows, void* stream);
+/* the same for n2 x n1 rows with two pitches each (rows pitch1 apart, groups of n1 rows pitch2 apart): a
+ * [nz][rows][ny] block whose rows are a sub-range of both volumes.                                           */
+int mfish_copy3d(void* dst_dev, int64_t dst_pitch1, int64_t dst_pitch2, const void* src_dev, int64_t src_pitch1,
+                 int64_t src_pitch2, int64_t row_bytes, int64_t n1, int64_t n2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

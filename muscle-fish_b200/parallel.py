@@ -68,6 +68,72 @@ def _buf(tag, shape, dtype, device):
 
 def clear_buffers():
     _BUFS.clear()
+    _PEER_BUFS.clear()
+
+
+# ------------------------------------------------------------------------ NVLink peer memory
+# On CUDA tensors the block moves between slabs (halo planes / rows, the all-to-all in front of the EDT's
+# envelope passes) do not go through send/recv pairs: every rank holds a SYMMETRIC buffer (torch symmetric
+# memory: same shape on every rank, mapped into every peer), and a sender writes its block straight into the
+# receiver's buffer with one pack-and-transfer kernel (``mfish_copy2d``: 16-byte loads from local HBM, 16-byte
+# stores through NVSwitch), bracketed by two device-side barriers of the buffer's handle.  No staging copies,
+# nothing to unpack, measured ~2x the NCCL send/recv rate on these block shapes (tools/probe_symm.py).
+# MFISH_P2P=0, CPU tensors (the gloo tests) or a failed rendezvous fall back to grouped isend / irecv.
+_PEER_BUFS = {}
+_PEER_STATE = {"ok": None}
+
+
+def _peer_ok(t: torch.Tensor) -> bool:
+    import os
+    return t.is_cuda and _PEER_STATE["ok"] is not False and os.environ.get("MFISH_P2P", "1") != "0"
+
+
+def _peer_buf(tag, shape, dtype, device, group):
+    """(local tensor, handle, [view of every rank's buffer]) of the symmetric buffer `tag`; the first use of a
+    (tag, shape) is collective.  None when symmetric memory is unavailable."""
+    k = (tag, tuple(shape), dtype, str(device), id(group))
+    ent = _PEER_BUFS.get(k)
+    if ent is None:
+        try:
+            import torch.distributed._symmetric_memory as symm
+            buf = symm.empty(tuple(shape), dtype=dtype, device=device)
+            hdl = symm.rendezvous(buf, group if group is not None else dist.group.WORLD)
+            peers = [hdl.get_buffer(r, tuple(shape), dtype) for r in range(hdl.world_size)]
+            _PEER_STATE["ok"] = True
+        except Exception as e:  # noqa: BLE001  (systemic: every rank fails the same way)
+            if _PEER_STATE["ok"]:
+                raise
+            import warnings
+            warnings.warn(f"symmetric memory unavailable ({e!r}): slab exchanges use NCCL send/recv")
+            _PEER_STATE["ok"] = False
+            return None
+        ent = _PEER_BUFS[k] = (buf, hdl, peers)
+    return ent
+
+
+def _block_copy(dst: torch.Tensor, src: torch.Tensor):
+    """dst[...] = src[...] for 3-D views with a contiguous last axis; dst may live on a peer GPU.  One
+    ``mfish_copy2d`` / ``mfish_copy3d`` launch (16-byte words), torch's copy for anything unaligned."""
+    assert dst.shape == src.shape and dst.dtype == src.dtype and dst.dim() == 3
+    n2, n1, w = src.shape
+    if n2 == 0 or n1 == 0 or w == 0:
+        return
+    es = src.element_size()
+    rb = w * es
+    ok = src.stride(2) == 1 and dst.stride(2) == 1 and rb % 16 == 0 and src.data_ptr() % 16 == 0 \
+        and dst.data_ptr() % 16 == 0 and all((v.stride(0) * es) % 16 == 0 and (v.stride(1) * es) % 16 == 0
+                                             for v in (src, dst))
+    if not ok:
+        dst.copy_(src)
+        return
+    from . import _lib as L
+    from . import device as D
+    lib, st = L.lib(), D._stream()
+    sp1, sp2, dp1, dp2 = src.stride(1) * es, src.stride(0) * es, dst.stride(1) * es, dst.stride(0) * es
+    if sp1 == rb and dp1 == rb:  # contiguous n1*w runs, n2 of them
+        L.check(lib.mfish_copy2d(dst.data_ptr(), dp2, src.data_ptr(), sp2, rb * n1, n2, st))
+    else:
+        L.check(lib.mfish_copy3d(dst.data_ptr(), dp1, dp2, src.data_ptr(), sp1, sp2, rb, n1, n2, st))
 
 
 # ------------------------------------------------------------------------------ partitioning
@@ -275,6 +341,22 @@ def exchange_halo(slab: torch.Tensor, halo: int, lay: SlabLayout, group=None):
     lo = halo if r > 0 else 0
     hi = halo if r < P - 1 else 0
     nzl = slab.shape[0]
+    if _peer_ok(slab):
+        nz_max = max(e - b for b, e in lay.zb)
+        pm = _peer_buf("halo_ext", (2 * halo + nz_max,) + tuple(slab.shape[1:]), slab.dtype, slab.device, group)
+        if pm is not None:
+            buf, hdl, peers = pm
+            hdl.barrier(channel=0)  # every rank is done with the previous step's extended slab
+            if slab.data_ptr() != buf[lo:lo + nzl].data_ptr():  # (slab_input_buffer: the slab already lives there)
+                _block_copy(buf[lo:lo + nzl], slab)
+            if r > 0:  # my lowest planes are the upper halo of the rank below
+                b_, e_ = lay.zb[r - 1]
+                lo_n = halo if r - 1 > 0 else 0
+                _block_copy(peers[r - 1][lo_n + (e_ - b_):lo_n + (e_ - b_) + halo], slab[:halo])
+            if r < P - 1:  # my highest planes are the lower halo of the rank above
+                _block_copy(peers[r + 1][:halo], slab[nzl - halo:])
+            hdl.barrier(channel=1)  # every block has landed
+            return buf[:lo + nzl + hi], lo, hi
     ext = _buf("halo_ext", (lo + nzl + hi,) + tuple(slab.shape[1:]), slab.dtype, slab.device)
     ext[lo:lo + nzl] = slab
     ops = []
@@ -292,6 +374,25 @@ def exchange_halo(slab: torch.Tensor, halo: int, lay: SlabLayout, group=None):
     return ext, lo, hi
 
 
+def slab_input_buffer(lay: SlabLayout, sigma: float, dtype=torch.float32, device=None, group=None):
+    """The rank's own z-slab ``[nz_local][nx][ny]`` as a view INSIDE the extended buffer the halo exchange of
+    ``slab_find_spots_snrfilter(sigma)`` works in: a caller that puts its slab there (H2D copy, generator) saves the
+    pipeline the copy of the slab into the extended buffer every step.  None when peer memory is not in use
+    (then any tensor is as good as another)."""
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+    halo = T.gaussian_radius(sigma) + 1
+    r, P = lay.rank, lay.world
+    probe = torch.empty(0, device=device)
+    if P == 1 or not _peer_ok(probe):
+        return None
+    nz_max = max(e - b for b, e in lay.zb)
+    pm = _peer_buf("halo_ext", (2 * halo + nz_max, lay.nx, lay.ny), dtype, device, group)
+    if pm is None:
+        return None
+    lo = halo if r > 0 else 0
+    return pm[0][lo:lo + (lay.z1 - lay.z0)]
+
+
 def exchange_halo_x(slab: torch.Tensor, halo: int, lay: "XSlabLayout", group=None):
     """x-slab [nz][nx_local][ny]: append up to `halo` x-rows of each x-neighbour.  Returns (ext, lo, hi)."""
     r, P = lay.rank, lay.world
@@ -302,6 +403,30 @@ def exchange_halo_x(slab: torch.Tensor, halo: int, lay: "XSlabLayout", group=Non
     lo = halo if r > 0 else 0
     hi = halo if r < P - 1 else 0
     nz, nxl, ny = slab.shape
+    widths = [e - b for b, e in lay.xb]
+    if _peer_ok(slab):
+        # one flat symmetric allocation; every rank's extended slab is a contiguous [nz][lo + nxl + hi][ny]
+        # view of its own buffer, and a neighbour addresses it in THAT rank's shape
+        pm = _peer_buf("halo_ext_x", (nz * (2 * halo + max(widths)) * ny,), slab.dtype, slab.device, group)
+        if pm is not None:
+            _, hdl, _ = pm
+
+            def ext_of(q):
+                lo_q = halo if q > 0 else 0
+                hi_q = halo if q < P - 1 else 0
+                return hdl.get_buffer(q, (nz, lo_q + widths[q] + hi_q, ny), slab.dtype), lo_q
+
+            mine, _ = ext_of(r)
+            hdl.barrier(channel=0)
+            _block_copy(mine[:, lo:lo + nxl], slab)
+            if r > 0:
+                below, lo_b = ext_of(r - 1)
+                _block_copy(below[:, lo_b + widths[r - 1]:], slab[:, :halo])
+            if r < P - 1:
+                above, _ = ext_of(r + 1)
+                _block_copy(above[:, :halo], slab[:, nxl - halo:])
+            hdl.barrier(channel=1)
+            return mine, lo, hi
     ext = _buf("halo_ext_x", (nz, lo + nxl + hi, ny), slab.dtype, slab.device)
     ext[:, lo:lo + nxl] = slab
     ops, keep = [], []
@@ -336,6 +461,17 @@ def repartition_x_to_y(t: torch.Tensor, lay: "XSlabLayout", group=None) -> torch
     if P == 1:
         return t
     nz = lay.nz
+    if _peer_ok(t) and len({e - b for b, e in lay.yb}) == 1:
+        pm = _peer_buf("x2y_out", (nz, lay.nx, lay.y1 - lay.y0), t.dtype, t.device, group)
+        if pm is not None:
+            buf, hdl, peers = pm
+            hdl.barrier(channel=0)
+            for k in range(P):
+                s_ = (r + k) % P  # own block first, then the peers in ring order
+                yb, ye = lay.yb[s_]
+                _block_copy(peers[s_][:, lay.x0:lay.x1] if s_ != r else buf[:, lay.x0:lay.x1], t[:, :, yb:ye])
+            hdl.barrier(channel=1)
+            return buf
     out = _buf("x2y_out", (nz, lay.nx, lay.y1 - lay.y0), t.dtype, t.device)
     ops, recvs = [], {}
     for s in range(P):
@@ -365,6 +501,17 @@ def repartition_z_to_y(t: torch.Tensor, lay: SlabLayout, group=None) -> torch.Te
     P, r = lay.world, lay.rank
     if P == 1:
         return t
+    if _peer_ok(t) and len({e - b for b, e in lay.yb}) == 1:
+        pm = _peer_buf("z2y_out", (lay.nz, lay.nx, lay.y1 - lay.y0), t.dtype, t.device, group)
+        if pm is not None:
+            buf, hdl, peers = pm
+            hdl.barrier(channel=0)
+            for k in range(P):
+                s_ = (r + k) % P
+                yb, ye = lay.yb[s_]
+                _block_copy(peers[s_][lay.z0:lay.z1] if s_ != r else buf[lay.z0:lay.z1], t[:, :, yb:ye])
+            hdl.barrier(channel=1)
+            return buf
     out = _buf("z2y_out", (lay.nz, lay.nx, lay.y1 - lay.y0), t.dtype, t.device)
     ops = []
     for s in range(P):
