@@ -311,9 +311,25 @@ def bench_e2e(ctx, args, img, fiber, nuc, shape, nvox):
     warm = max(1, min(args.warmup, 3))
     dt, res = ctx.timed(fused, steps, warm)
     h2d = int(h_img.numel() * 4 + h_fib.numel() + h_nuc.numel())
+    # the ceiling the host side sets: the same three pinned buffers copied to the device and nothing else, every
+    # rank at once (with N ranks on one host they share its memory system and PCIe root complexes)
+    d_img = torch.empty(shape, dtype=torch.float32, device="cuda")
+    d_fib = torch.empty(shape, dtype=torch.uint8, device="cuda")
+    d_nuc = torch.empty(shape, dtype=torch.uint8, device="cuda")
+
+    def copies_only():
+        d_nuc.copy_(h_nuc, non_blocking=True)
+        d_img.copy_(h_img, non_blocking=True)
+        d_fib.copy_(h_fib, non_blocking=True)
+        torch.cuda.synchronize()
+
+    dtc, _ = ctx.timed(copies_only, 3, 1)
+    del d_img, d_fib, d_nuc
+    h2d_only_ms = dtc / 3 * 1e3
     e2e = {"value": ctx.world * nvox * steps / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h_bytes(res), "steps": steps, "ms_per_step": dt / steps * 1e3,
            "pcie_floor_ms": h2d / 55e9 * 1e3,
+           "h2d_only_ms_all_ranks_at_once": h2d_only_ms, "h2d_only_gbs_per_gpu": h2d / h2d_only_ms / 1e6,
            "api": "muscle_fish.find_spots_snrfilter_with_distances (= find_spots_snrfilter + the EDT/interpn pair of "
                   "nocodazole/fish_analysis_noco.py:218-221,297-298 in one call): pinned host float32 (x,y,z) image "
                   "+ uint8 masks in, host float64 spots / table / distances out"}
