@@ -61,6 +61,7 @@ def host_to_device(arr) -> torch.Tensor:
     return t.to("cuda", non_blocking=t.is_pinned())
 
 
+STAGED_UPLOADS = os.environ.get("MFISH_STAGED_UPLOADS", "1") != "0"
 _COPY_STREAMS = {}
 _SIDE_STREAMS = {}
 _LIST_STREAMS = {}
@@ -85,10 +86,106 @@ def _list_stream():
     return st
 
 
-def host_to_device_many(arrs):
+# ---- pageable host arrays: narrowed on the host by worker threads, staged through pinned memory
+# The reference's callers hand over pageable float64 images (fix_bleaching's output) and int64 0/1 masks
+# (np.where(..., 1, 0)): general_pipeline/fish_analysis.py:196-199.  Copying those as they are moves 8 bytes per
+# voxel per array through the driver's own synchronous staging (~11 GB/s).  The device converts an image to
+# float32 and a mask to "voxel != 0" on ingest anyway, so the same conversion is done on the host instead --
+# numpy ufuncs on chunks in a few threads (they release the GIL) writing into a ring of pinned buffers -- and
+# 4 (image) or 1 (mask) bytes per voxel cross PCIe asynchronously while later chunks are being converted.
+_STAGE_MIN_BYTES = 64 << 20
+_STAGE_CHUNK_ELEMS = 8 << 20
+_STAGE = {}
+
+
+def _is_pinned(a: np.ndarray) -> bool:
+    """is this numpy array backed by page-locked memory (then the plain asynchronous copy is the fast path)?"""
+    try:
+        if not a.flags.c_contiguous:
+            return False
+        b = a if a.dtype != np.bool_ else a.view(np.uint8)
+        if not b.flags.writeable:
+            return False
+        return torch.from_numpy(b).is_pinned()
+    except Exception:  # noqa: BLE001
+        return False
+
+
+def _stage_resources():
+    ent = _STAGE.get("pool")
+    if ent is None:
+        from concurrent.futures import ThreadPoolExecutor
+        try:
+            ncpu = len(os.sched_getaffinity(0))
+        except AttributeError:
+            ncpu = os.cpu_count() or 1
+        nthreads = max(1, min(8, ncpu // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
+        depth = nthreads + 2
+        ring = [torch.empty(_STAGE_CHUNK_ELEMS * 4, dtype=torch.uint8).pin_memory() for _ in range(depth)]
+        ent = _STAGE["pool"] = (ThreadPoolExecutor(nthreads), ring, [None] * depth)
+    return ent
+
+
+def _upload_staged(a: np.ndarray, kind: str, cs, cur):
+    """pageable (x, y, z) array -> (device tensor, ready event): masks arrive as uint8 0/1, float64 / int64 images
+    as float32, other images in their own dtype"""
+    import threading
+    pool, ring, events = _stage_resources()
+    depth = len(ring)
+    if kind == "mask":
+        out_np = np.dtype(np.uint8)
+    elif a.dtype in (np.dtype(np.float64), np.dtype(np.int64)):
+        out_np = np.dtype(np.float32)
+    else:
+        out_np = a.dtype  # 8 / 16 / 32-bit images travel as they are
+    out_t = torch.from_numpy(np.empty(0, out_np)).dtype
+    esz = out_np.itemsize
+    n0 = a.shape[0]
+    per_row = int(np.prod(a.shape[1:]))
+    rows = max(1, _STAGE_CHUNK_ELEMS // per_row)
+    if per_row > _STAGE_CHUNK_ELEMS:  # one leading-axis row does not fit a ring buffer: the plain path
+        return None
+    chunks = [(r0, min(n0, r0 + rows)) for r0 in range(0, n0, rows)]
+    dst = torch.empty(a.shape, dtype=out_t, device="cuda")
+    released = [threading.Event() for _ in chunks]  # chunk c's DMA has been queued (its slot's event recorded)
+
+    def convert(c):
+        r0, r1 = chunks[c]
+        slot = c % depth
+        if c >= depth:
+            released[c - depth].wait()
+        ev = events[slot]
+        if ev is not None:
+            ev.synchronize()  # the previous DMA out of this pinned buffer has finished
+        view = ring[slot][:(r1 - r0) * per_row * esz].numpy().view(out_np).reshape((r1 - r0,) + a.shape[1:])
+        if kind == "mask":
+            np.not_equal(a[r0:r1], 0, out=view.view(np.bool_))
+        else:
+            np.copyto(view, a[r0:r1], casting="unsafe")
+        return slot
+
+    futs = [pool.submit(convert, c) for c in range(len(chunks))]
+    cs.wait_stream(cur)
+    for c, f in enumerate(futs):
+        slot = f.result()
+        r0, r1 = chunks[c]
+        src = ring[slot][:(r1 - r0) * per_row * esz].view(out_t).view((r1 - r0,) + tuple(a.shape[1:]))
+        with torch.cuda.stream(cs):
+            dst[r0:r1].copy_(src, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(cs)
+        events[slot] = ev
+        released[c].set()
+    return dst, ev
+
+
+def host_to_device_many(arrs, kinds=None):
     """Queue the H2D copies of several host arrays back to back on a side stream and return
     [(device tensor, ready event)], so that work on the first array overlaps the later copies
-    (PCIe is the slow link of the host-buffer path).  Device / non-array inputs pass through."""
+    (PCIe is the slow link of the host-buffer path).  Device / non-array inputs pass through.
+    ``kinds`` (per array: "image" / "mask" / None) tells what the array is FOR: large pageable arrays of a known
+    kind are narrowed on the host (float32 / 0-1 uint8: exactly what ``ingest`` makes of them) while they are
+    staged through pinned memory."""
     _require_cuda()
     dev = torch.cuda.current_device()
     cur = torch.cuda.current_stream()
@@ -97,7 +194,8 @@ def host_to_device_many(arrs):
         cs = _COPY_STREAMS[dev] = torch.cuda.Stream()
     out = []
     started = False
-    for arr in arrs:
+    kinds = list(kinds) if kinds is not None else [None] * len(arrs)
+    for arr, kind in zip(arrs, kinds):
         if arr is None:
             out.append((None, None))
             continue
@@ -105,6 +203,13 @@ def host_to_device_many(arrs):
             src = arr if arr.is_cuda else arr.contiguous()
         else:
             a = np.asarray(arr)
+            if (kind in ("image", "mask") and a.ndim == 3 and a.nbytes >= _STAGE_MIN_BYTES and a.dtype in _DTYPES
+                    and STAGED_UPLOADS and not _is_pinned(a)):
+                staged = _upload_staged(a, kind, cs, cur)
+                if staged is not None:
+                    started = True
+                    out.append(staged)
+                    continue
             if a.dtype == np.bool_:
                 a = a.view(np.uint8)
             if a.dtype not in _DTYPES:
@@ -1052,7 +1157,8 @@ def analyze_host(img_fish, fiber_mask, region_nuc, sigma=2.0, t_spot=0.025, samp
     ``region_nuc`` is the nucleus mask itself (the NOT is taken on ingest, nocodazole/fish_analysis_noco.py:218).
     Returns the dict of ``analyze_stack``."""
     t = timer or _NoTimer()
-    (tn, en), (ti, ei), (tf, ef) = host_to_device_many([region_nuc, img_fish, fiber_mask])
+    (tn, en), (ti, ei), (tf, ef) = host_to_device_many([region_nuc, img_fish, fiber_mask],
+                                                       kinds=("mask", "image", "mask"))
     main = torch.cuda.current_stream()
     side = _side_stream()
     side.wait_stream(main)

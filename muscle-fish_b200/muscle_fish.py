@@ -38,9 +38,9 @@ class _Lazy:
 def _prep(img_fish, mask, z_first):
     vol = D.HANDOFF.lookup(img_fish, z_first)  # an array this package returned: already on the device
     if vol is not None:
-        (tm, em), = D.host_to_device_many([mask])
+        (tm, em), = D.host_to_device_many([mask], kinds=("mask",))
     else:
-        (ti, ei), (tm, em) = D.host_to_device_many([img_fish, mask])
+        (ti, ei), (tm, em) = D.host_to_device_many([img_fish, mask], kinds=("image", "mask"))
         vol = D.ingest(ti, z_first=z_first, ready=ei)
     m = _Lazy(tm, em, z_first, vol.data.shape) if mask is not None else None
     return vol, m

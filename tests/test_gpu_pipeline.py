@@ -156,3 +156,42 @@ def test_run_batch_equals_stack_by_stack():
         def bad(i, *a):
             raise RuntimeError("boom")
         P.run_batch(3, bad, shape, torch.uint16, rank=0, world=1)
+
+
+def test_staged_uploads_of_pageable_arrays(monkeypatch):
+    """Large pageable arrays are narrowed on the host (float64 / int64 image -> float32, any mask -> 0/1 uint8:
+    what ingest makes of them on the device) while they are staged through a ring of pinned buffers.  Forced on
+    for small arrays and small chunks here, so that the ring wraps several times: same device data as the
+    conversion done directly, same spots / table / distances as the plain path."""
+    import torch
+    from muscle_fish_b200 import device as D, muscle_fish as mf, synth
+    monkeypatch.setattr(D, "_STAGE_MIN_BYTES", 0)
+    monkeypatch.setattr(D, "_STAGE_CHUNK_ELEMS", 1 << 16)
+    D._STAGE.clear()
+    try:
+        rng = np.random.default_rng(4)
+        img = rng.random((90, 70, 31)) * 4000.0
+        m64 = (rng.random((90, 70, 31)) < 0.4).astype(np.int64) * 5
+        u16 = (img * 10).astype(np.uint16)
+        fimg = np.asfortranarray(img)  # not C-contiguous
+        (t_img, e1), (t_m, e2), (t_u, e3), (t_f, e4) = D.host_to_device_many(
+            [img, m64, u16, fimg], kinds=("image", "mask", "image", "image"))
+        for e in (e1, e2, e3, e4):
+            assert e is not None
+            torch.cuda.current_stream().wait_event(e)
+        assert t_img.dtype == torch.float32 and torch.equal(t_img.cpu(), torch.from_numpy(img.astype(np.float32)))
+        assert t_m.dtype == torch.uint8 and torch.equal(t_m.cpu(), torch.from_numpy((m64 != 0).astype(np.uint8)))
+        assert t_u.dtype == torch.uint16 and np.array_equal(t_u.cpu().numpy(), u16)
+        assert torch.equal(t_f.cpu(), torch.from_numpy(img.astype(np.float32)))
+        st = synth.make_config("small")
+        args = (st["img"].astype(np.float64), st["nuc_mask"].astype(np.int64), ANISO)
+        kw = dict(sigma=2.0, t_spot=0.025, mask=st["fiber_mask"].astype(np.int64))
+        a = mf.find_spots_snrfilter_with_distances(*args, **kw)
+        monkeypatch.setattr(D, "STAGED_UPLOADS", False)
+        b = mf.find_spots_snrfilter_with_distances(*args, **kw)
+        np.testing.assert_array_equal(a[0], b[0])
+        assert a[1] == b[1]
+        np.testing.assert_array_equal(a[2], b[2])
+        assert len(a[0]) > 20
+    finally:
+        D._STAGE.clear()
