@@ -8,6 +8,8 @@
 
 #include <stdlib.h>
 
+#include <memory>
+
 #include "common.cuh"
 
 namespace mfish {
@@ -785,7 +787,9 @@ static int quantile_fast_impl(const float* vol_dev, const uint8_t* mask_dev, int
   MFISH_REQUIRE(vol_dev && mask_dev && ws_dev && out_dev && info_dev, "masked_quantile: null pointer");
   MFISH_REQUIRE(n > 0 && q >= 0.0 && q <= 1.0, "masked_quantile: bad arguments");
   cudaStream_t st = as_stream(stream);
-  ProfScope prof(minmax_dev ? "masked_quantile_minmax" : "masked_quantile_bracketed", st);
+  // three timing scopes: the sample's select (1/64 of the volume, three times), THE full pass (5 B/voxel: the
+  // kernel the roofline is about), the select among the collected candidates
+  std::unique_ptr<ProfScope> prof(new ProfScope("masked_quantile_sample", st));
   uint32_t* mm = reinterpret_cast<uint32_t*>(minmax_dev);
   QWs* ws = reinterpret_cast<QWs*>(ws_dev);
   const int64_t cap = (std::max<int64_t>(1 << 20, n / 64) + QSEG - 1) / QSEG * QSEG;
@@ -812,8 +816,10 @@ static int quantile_fast_impl(const float* vol_dev, const uint8_t* mask_dev, int
   qsel_scan_kernel<2><<<1, QSCAN_THREADS, 0, st>>>(ws, pair, dummy);
   qsel_bracket_kernel<<<1, 32, 0, st>>>(ws, pair);
   // 2. the one full pass
-  MFISH_CUDA(cudaMemsetAsync(cand, 0x7f, (size_t)cap * sizeof(float), st));  // 3.39e38: sorts above any voxel
+  cudaMemsetAsync(cand, 0x7f, (size_t)cap * sizeof(float), st);  // 3.39e38: sorts above any voxel
   qsel_set_cap_kernel<<<1, 1, 0, st>>>(ws, (unsigned long long)cap);  // (a pageable H2D copy would stall the stream)
+  prof.reset();
+  prof.reset(new ProfScope(minmax_dev ? "masked_quantile_minmax" : "masked_quantile_bracketed", st));
   if (mm) {
     qsel_mm_init_kernel<<<1, 1, 0, st>>>(mm);
     qsel_range_kernel<true><<<blocks, 256, 0, st>>>(vol_dev, mask_dev, n, ws, cand, mm);
@@ -823,6 +829,8 @@ static int quantile_fast_impl(const float* vol_dev, const uint8_t* mask_dev, int
     qsel_range_kernel<false><<<blocks, 256, 0, st>>>(vol_dev, mask_dev, n, ws, cand, nullptr);
   }
   // 3. exact ranks inside the candidates
+  prof.reset();
+  prof.reset(new ProfScope("masked_quantile_select", st));
   qsel_init_kernel<<<1, 256, 0, st>>>(ws, q, QMODE_RANKS);
   qsel_ranks_kernel<<<1, 32, 0, st>>>(ws, out_dev, info_dev);
   const int cblocks = (int)std::min<int64_t>((cap / 4 + 255) / 256 + 1, (int64_t)num_sms() * 4);
@@ -833,6 +841,7 @@ static int quantile_fast_impl(const float* vol_dev, const uint8_t* mask_dev, int
   qsel_hist_kernel<2><<<cblocks, 256, 0, st>>>(cand, nullptr, cap, ws, 0, &ws->ctl.cap);
   qsel_scan_kernel<2><<<1, QSCAN_THREADS, 0, st>>>(ws, out_dev, info_dev);
   count_launch(17);
+  prof.reset();
   int rc = check_launch("masked_quantile_fast");
   cudaFreeAsync(cand, st);
   cudaFreeAsync(pair, st);

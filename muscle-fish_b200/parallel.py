@@ -961,8 +961,15 @@ def slab_analyze(img_slab: torch.Tensor, mask_slab: torch.Tensor, notnuc_slab: t
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             dmap = edt_fn(notnuc_slab, lay, sampling_xyz, ops=ops, group=edt_group)
-        res = slab_find_spots_snrfilter(img_slab, mask_slab, lay, sigma=sigma, t_spot=t_spot, snr=snr, ops=ops,
-                                        group=group, full_table=full_table)
+        # The spot chain runs on the HIGH-priority stream: its LoG passes are dispatched ahead of the distance
+        # transform's remaining blocks, so the chain reaches its latency-bound end (peak lists, small collectives,
+        # host round trips) early and that end -- not the LoG -- is what overlaps the transform's heavy kernels.
+        spot = D._list_stream()
+        spot.wait_stream(cur)
+        with torch.cuda.stream(spot):
+            res = slab_find_spots_snrfilter(img_slab, mask_slab, lay, sigma=sigma, t_spot=t_spot, snr=snr, ops=ops,
+                                            group=group, full_table=full_table)
+        cur.wait_stream(spot)
         cur.wait_stream(side)
         dmap.record_stream(cur)
     else:

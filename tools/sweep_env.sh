@@ -1,7 +1,7 @@
 # sweep one environment variable over values on the C2 bench: tools/sweep_env.sh VAR v1 v2 ...
 V=$1; shift
 for val in "$@"; do
-  env $V=$val python bench.py --steps 10 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/sw.json 2> gpurun_out/sw.err; echo "$V=$val rc=$?"
+  env $V=$val python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-batch --e2e-steps 1 > gpurun_out/sw.json 2> gpurun_out/sw.err; echo "$V=$val rc=$?"
   python - <<PY
 import json
 d=json.load(open('gpurun_out/sw.json'))
