@@ -97,3 +97,34 @@ def test_slab_drivers_world2_nccl():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (one process per GPU)")
     _check(2)
+
+
+@pytest.mark.parametrize("dtype", ["uint16", "float32", "uint8"])
+def test_block_copy_kernels_match_torch_slicing(dtype):
+    """mfish_copy2d / mfish_copy3d (the pack-and-transfer kernel of the slab exchanges) on local buffers: every
+    block shape the re-partitions and halo exchanges produce, plus an unaligned one (torch's copy takes it)."""
+    import torch
+    import muscle_fish_b200  # noqa: F401
+    from muscle_fish_b200 import parallel as P
+    dt = getattr(torch, dtype)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    src = torch.randint(0, 200, (12, 40, 96), device="cuda", generator=g).to(dt)
+    cases = [
+        (slice(None), slice(None), slice(32, 64)),   # last-axis block of every row (z/x -> y re-partition)
+        (slice(None), slice(8, 24), slice(None)),    # middle-axis rows (x halo)
+        (slice(3, 9), slice(None), slice(None)),     # leading planes (z halo)
+        (slice(2, 11), slice(8, 24), slice(16, 80)),  # all three at once
+        (slice(None), slice(None), slice(1, 50)),    # unaligned start: falls back to torch
+    ]
+    for sl in cases:
+        blk = src[sl]
+        # into a contiguous destination, and into a sub-block of a larger one
+        dst = torch.zeros(blk.shape, dtype=dt, device="cuda")
+        P._block_copy(dst, blk)
+        assert torch.equal(dst, blk)
+        big = torch.zeros((16, 48, 128), dtype=dt, device="cuda")
+        view = big[2:2 + blk.shape[0], 4:4 + blk.shape[1], 16:16 + blk.shape[2]]
+        P._block_copy(view, blk)
+        assert torch.equal(view, blk)
+        big[2:2 + blk.shape[0], 4:4 + blk.shape[1], 16:16 + blk.shape[2]] = 0
+        assert not big.any(), "nothing outside the destination block was written"
