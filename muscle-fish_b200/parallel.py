@@ -961,10 +961,11 @@ def slab_analyze(img_slab: torch.Tensor, mask_slab: torch.Tensor, notnuc_slab: t
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             dmap = edt_fn(notnuc_slab, lay, sampling_xyz, ops=ops, group=edt_group)
-        # The spot chain runs on the HIGH-priority stream: its LoG passes are dispatched ahead of the distance
-        # transform's remaining blocks, so the chain reaches its latency-bound end (peak lists, small collectives,
-        # host round trips) early and that end -- not the LoG -- is what overlaps the transform's heavy kernels.
-        spot = D._list_stream()
+        # MFISH_SLAB_PRIO=1 runs the spot chain on the high-priority stream (its LoG passes dispatched ahead of the
+        # transform's blocks).  Measured (tools/slab_modes.py): 1 ms faster at 2 GPUs, 3-4 ms SLOWER at 8 (as slow
+        # as running the chains one after the other) -- off by default.
+        import os
+        spot = D._list_stream() if os.environ.get("MFISH_SLAB_PRIO", "0") == "1" else cur
         spot.wait_stream(cur)
         with torch.cuda.stream(spot):
             res = slab_find_spots_snrfilter(img_slab, mask_slab, lay, sigma=sigma, t_spot=t_spot, snr=snr, ops=ops,
