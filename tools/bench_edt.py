@@ -17,6 +17,8 @@ def run(tag, save=None):
     shape, ns, nn, seed = synth.CONFIGS[wl]
     if os.environ.get("EDT_NZ"):
         shape = (shape[0], shape[1], int(os.environ["EDT_NZ"]))
+    if os.environ.get("EDT_SHAPE"):  # "x,y,z"
+        shape = tuple(int(v) for v in os.environ["EDT_SHAPE"].split(","))
     st = synth.make_stack_device(shape, 100, nn, seed)
     notnuc = (st["nuc_mask"] == 0).to(torch.uint8)
     del st
