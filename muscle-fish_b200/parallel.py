@@ -2,18 +2,19 @@
 
 Two partitionings:
 
-* **batch** -- independent stacks, one per rank round-robin, no data-path collective.  This is the
-  reference's own model: ``general_pipeline/batch_process.py:28-52`` writes one job per image.
-* **z-slab** -- one large mosaic ``[nz][nx][ny]`` split into contiguous z-slabs.
-    - global min/max:           all-reduce(MIN/MAX) of two floats
-    - LoG / NMS / blur:         r+1 input planes from each z-neighbour (send/recv halo exchange);
-                                every rank reports only peaks whose centre lies in its own planes
+* **batch** -- independent stacks, one per rank round-robin, no data-path collective (``run_batch``: pinned
+  double-buffered staging so that PCIe never waits for the GPU).  This is the reference's own model:
+  ``general_pipeline/batch_process.py:28-52`` writes one job per image.
+* **mosaic** -- one large volume ``[nz][nx][ny]`` split into contiguous z-slabs (``SlabLayout``) or x-slabs
+  (``XSlabLayout``), ``slab_analyze``:
+    - min/max + P25 baseline:   ONE pass over the raw slab; sample / candidate histograms and counters all-reduced
+    - LoG / NMS / blur:         radius+1 input planes (12 rows) from each neighbour; every rank reports only the
+                                peaks whose centre lies in its own planes (rows)
     - overlap prune:            all-gather of the (small) peak lists, same prune on every rank
-    - P25 baseline:             three 2x2048-bin histogram all-reduces (masked radix select)
-    - EDT:                      y and x passes slab-local; the z pass needs whole z lines, so the
-                                in-plane squared distances are re-partitioned from z-slabs to
-                                x-slabs (all-to-all of grouped send/recv), then the z pass runs
-                                on ``[nz][nx/P][ny]``
+    - EDT:                      row scan slab-local; the uint16 row distances are re-partitioned into y-slabs
+                                (all-to-all), both envelope passes run there on whole lines
+    - exchanges:                on CUDA tensors blocks are written straight into the receiver's symmetric buffer
+                                over NVLink (``mfish_copy2d`` / ``mfish_copy3d``), else grouped isend / irecv
 
 The communication code only moves torch tensors; the voxel work is done by an ``ops`` object.
 ``DeviceOps`` (default) calls the CUDA library.  The CPU tests inject an oracle-backed ``ops`` to
@@ -910,9 +911,7 @@ def xslab_edt(notnuc_slab: torch.Tensor, lay: XSlabLayout, sampling_xyz=(1.0, 1.
     with _phase("edt_rowscan"):
         dy = ops.edt_rowscan(notnuc_slab)
     with _phase("edt_all_to_all"):
-        wire = dy
-        dyy = repartition_x_to_y(wire, lay, group)
-        dyy = dyy.view(torch.uint16) if dy.dtype == torch.uint16 else dyy
+        dyy = repartition_x_to_y(dy, lay, group)
     with _phase("edt_xz"):
         return ops.edt_xz(dyy, sampling_xyz, lay.ny)
 

@@ -243,3 +243,48 @@ def test_fish_analysis_call_sequence_with_the_dropin_segmentation(tmp_path):
     ref_fiber = S.threshold_fiber(oracle.normalize_image(st["img"]))
     assert got["fiber"].dtype == ref_fiber.dtype and (got["fiber"] != ref_fiber).mean() < 2e-3
     assert len(got["spots"]) > 50
+
+
+@pytest.mark.gpu
+def test_nocodazole_call_sequence_vs_oracle():
+    """nocodazole/fish_analysis_noco.py:189-298 with the import-line seams (morphology, distance_transform_edt,
+    filters.gaussian) and the drop-in find_spots: nuclear region by erosions, grassfire, per-nucleus faded
+    masks, spots, distance of every spot to the nearest nucleus -- each stage against the oracle's restatement."""
+    import oracle
+    from oracle import ref_fade, ref_morph
+    import muscle_fish_b200  # noqa: F401
+    from muscle_fish_b200 import filters, morphology, ndimage, synth
+    from muscle_fish_b200 import muscle_fish as mf
+    from conftest import match_fraction
+    st = synth.make_config("small")
+    dims_xyz = np.array([0.0577, 0.0577, 0.5])
+    nuclei_labeled = st["nuc_mask"].astype(np.int64)
+    img_fiber_only = st["fiber_mask"].astype(np.int64)
+    # :193-198  region_nuc: 1 erosion in 3-D, then 10 per plane
+    region_nuc = np.where(nuclei_labeled > 0, 1, 0)
+    for n in range(1):
+        region_nuc = morphology.binary_erosion(region_nuc)
+    for n in range(2):  # (10 upstream; the small test nuclei would vanish)
+        for z in range(region_nuc.shape[2]):
+            region_nuc[:, :, z] = morphology.binary_erosion(region_nuc[:, :, z])
+    ref_region = ref_morph.iterate(np.where(nuclei_labeled > 0, 1, 0), "erode", 1, 2)
+    np.testing.assert_array_equal(region_nuc != 0, ref_region != 0)
+    assert region_nuc.any()
+    # :218-221  grassfire
+    grassfire = ndimage.distance_transform_edt(np.logical_not(region_nuc), sampling=dims_xyz)
+    ref_grass = oracle.distance_transform_edt(np.logical_not(ref_region), sampling=dims_xyz)
+    assert grassfire.dtype == np.float64
+    np.testing.assert_allclose(grassfire, ref_grass, rtol=1e-6)
+    # :227-235  labels (host) and the faded mask of every nucleus
+    lab, n_nuc = ref_fade.label_nuclei(region_nuc)
+    assert n_nuc >= 2
+    fades = filters.nucleus_fades(lab, n_nuc)
+    for i in range(n_nuc):
+        nuc = np.where(lab == i, 1, 0)
+        assert np.abs(fades[i] - oracle.gaussian(nuc.astype(float), (3, 3, 1))).max() <= 1e-5
+    # :269  spots; :297-298 their distance to the nearest nucleus (interpn on grid nodes = gather)
+    spots = mf.find_spots(st["img"], t_spot=0.02, mask=img_fiber_only)
+    ref_spots = oracle.find_spots(st["img"], t_spot=0.02, mask=img_fiber_only, pair_order="sorted")
+    assert len(ref_spots) > 50 and match_fraction(spots, ref_spots) >= 0.999
+    got_d = ndimage.spot_distances(region_nuc, spots, dims_xyz)
+    np.testing.assert_allclose(got_d, oracle.edt_gather(ref_grass, spots, dims_xyz), rtol=1e-6)
