@@ -640,11 +640,13 @@ class DeviceOps:
         mm = torch.empty(2, dtype=torch.float32, device=vol.device)
         return self.D.masked_quantile_distributed(vol, mask, q, reduce, minmax_out=mm) + (mm,)
 
-    def log_peaks(self, ext, mm, sigma, thr, z_range=None):
+    def log_peaks(self, ext, mm, sigma, thr, z_range=None, between=None):
         """LoG + thresholded NMS of an (extended) slab in one library call, on its planes ``z_range`` only if
         given -> (raster (x*ny + y)*nzs + z int64 [n] over those nzs planes, value float32 [n]), unordered"""
         out = _buf("log_ext", ext.shape, torch.float32, ext.device)
         _, finish = self.D.log_peaks_async(self.D.Volume(ext, mm), sigma, thr, out=out, z_range=z_range)
+        if between is not None:
+            between()  # every heavy kernel of the spot chain is queued; the host has not waited for any yet
         return finish()
 
     def edt_rowscan(self, mask):
@@ -671,7 +673,7 @@ class _ZDecomp:
     def __init__(self, lay: SlabLayout):
         self.lay = lay
 
-    def detect(self, ops, img_slab, mm, sigma, t_spot, radius, group):
+    def detect(self, ops, img_slab, mm, sigma, t_spot, radius, group, after_log=None):
         """halo exchange + LoG + NMS; -> (extended slab, GLOBAL raster of the own peaks, their values)"""
         lay = self.lay
         nz = lay.nz
@@ -686,9 +688,11 @@ class _ZDecomp:
         nzs = b - a
         with _phase("log"):
             if getattr(ops, "fused_range_peaks", False):  # candidate test inside the last LoG pass
-                ras_l, val = ops.log_peaks(ext, mm, sigma, t_spot, z_range=(a, b))
+                ras_l, val = ops.log_peaks(ext, mm, sigma, t_spot, z_range=(a, b), between=after_log)
             else:
                 log_ext = ops.log(ext, mm, sigma, z_range=(a, b))
+                if after_log is not None:
+                    after_log()
                 ras_l, val = ops.peaks(log_ext[a:b], t_spot)
         with _phase("peaks"):
             # local raster ((x*ny + y)*nzs + zs) -> global raster ((x*ny + y)*nz + zg); keep own planes
@@ -714,7 +718,7 @@ class _XDecomp:
     def __init__(self, lay: XSlabLayout):
         self.lay = lay
 
-    def detect(self, ops, img_slab, mm, sigma, t_spot, radius, group):
+    def detect(self, ops, img_slab, mm, sigma, t_spot, radius, group, after_log=None):
         lay = self.lay
         nz, ny = lay.nz, lay.ny
         # radius rows for the x filter pass + 1 row of LoG for the NMS; the blur at the spots (sigma 3) reaches 12
@@ -722,7 +726,13 @@ class _XDecomp:
             ext, lo, hi = exchange_halo_x(img_slab, max(radius + 1, 12), lay, group)
         self.lo = lo
         with _phase("log"):
-            ras_l, val = ops.log_peaks(ext, mm, sigma, t_spot)  # raster (x_e*ny + y)*nz + z over the extended slab
+            if getattr(ops, "fused_range_peaks", False):
+                ras_l, val = ops.log_peaks(ext, mm, sigma, t_spot, between=after_log)
+            else:
+                if after_log is not None:
+                    after_log()
+                ras_l, val = ops.log_peaks(ext, mm, sigma, t_spot)
+            # raster (x_e*ny + y)*nz + z over the extended slab
         with _phase("peaks"):
             xe = ras_l // (ny * nz)
             own = (xe >= lo) & (xe < lo + img_slab.shape[1])
@@ -739,13 +749,15 @@ class _XDecomp:
 
 
 def slab_find_spots_snrfilter(img_slab: torch.Tensor, mask_slab: torch.Tensor, lay, sigma=2.0,
-                              t_spot=0.025, snr=None, ops=None, group=None, full_table=True):
+                              t_spot=0.025, snr=None, ops=None, group=None, full_table=True, after_log=None):
     """``find_spots_snrfilter`` (modules/muscle_fish.py:281-402) on a slab-decomposed mosaic: ``lay`` a
     ``SlabLayout`` (z-slabs ``[nz_local][nx][ny]``) or an ``XSlabLayout`` (x-slabs ``[nz][nx_local][ny]``);
     ``img_slab`` float32 / ``mask_slab`` uint8.  Every rank returns the same global result:
     dict(spots (N,4) float64 [x,y,z,sigma], spots_masked, intensity, baseline, snr).
     ``full_table=False`` skips the host copy of the per-spot table of ALL mask-passing spots
-    (``spots_masked`` / ``intensity``, the reference's ``spot_data``) and returns only the kept spots."""
+    (``spots_masked`` / ``intensity``, the reference's ``spot_data``) and returns only the kept spots.
+    ``after_log()`` is called once the chain's heavy kernels (min/max + P25 pass, LoG) are queued and before the
+    host first waits for the peak count: the place to queue other heavy work behind them."""
     with _phase("setup"):
         ops = ops or DeviceOps()
         dec = _XDecomp(lay) if isinstance(lay, XSlabLayout) else _ZDecomp(lay)
@@ -769,7 +781,7 @@ def slab_find_spots_snrfilter(img_slab: torch.Tensor, mask_slab: torch.Tensor, l
         lo_v, hi_v = float(lo_t.item()), float(hi_t.item())
     # 2./3. halo of raw input, LoG and NMS on the extended slab; every rank keeps the peaks it owns
     radius = T.gaussian_radius(sigma)
-    ext, ras_g, val = dec.detect(ops, img_slab, mm, sigma, t_spot, radius, group)
+    ext, ras_g, val = dec.detect(ops, img_slab, mm, sigma, t_spot, radius, group, after_log=after_log)
     # 4. all-gather the peak lists (padded to the longest), prune identically everywhere
     with _phase("gather_peaks"):
         n_loc = torch.tensor([ras_g.numel()], dtype=torch.int64, device=dev)
@@ -955,11 +967,38 @@ def slab_analyze(img_slab: torch.Tensor, mask_slab: torch.Tensor, notnuc_slab: t
     dist_fn = slab_spot_distances if squares else yslab_spot_distances
     if edt_group is not None and img_slab.is_cuda:
         from . import device as D
+        import os
         cur = torch.cuda.current_stream()
         side = D._side_stream()
         side.wait_stream(cur)
-        with torch.cuda.stream(side):
-            dmap = edt_fn(notnuc_slab, lay, sampling_xyz, ops=ops, group=edt_group)
+        gated = (not squares) and os.environ.get("MFISH_SLAB_GATE", "0") == "1"
+        if gated:
+            # MFISH_SLAB_GATE=1 (experiment, off): the transform's light front (row scan + re-partition) beside the
+            # spot chain's heavy front, its envelope passes queued BEHIND the LoG so that they run while the spot
+            # chain's end waits on its round trips.  Measured (tools/slab_modes.py) no better than one chain after
+            # the other (2 GPUs 38.9 vs 38.3 ms side by side; 8 GPUs x-slabs 32.2 vs 26.6): the small kernels and
+            # collectives of the chain's end queue behind the envelope passes' blocks.
+            ops_ = ops or DeviceOps()
+            with torch.cuda.stream(side):
+                with _phase("edt_rowscan"):
+                    dy = ops_.edt_rowscan(notnuc_slab)
+                with _phase("edt_all_to_all"):
+                    dyy = (repartition_x_to_y if xs else repartition_z_to_y)(dy, lay, edt_group)
+            late = {}
+
+            def after_log():
+                if "dmap" in late:
+                    return
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream())
+                side.wait_event(ev)
+                with torch.cuda.stream(side):
+                    with _phase("edt_xz"):
+                        late["dmap"] = ops_.edt_xz(dyy, sampling_xyz, lay.ny)
+        else:
+            after_log = None
+            with torch.cuda.stream(side):
+                dmap = edt_fn(notnuc_slab, lay, sampling_xyz, ops=ops, group=edt_group)
         # MFISH_SLAB_PRIO=1 runs the spot chain on the high-priority stream (its LoG passes dispatched ahead of the
         # transform's blocks).  Measured (tools/slab_modes.py): 1 ms faster at 2 GPUs, 3-4 ms SLOWER at 8 (as slow
         # as running the chains one after the other) -- off by default.
@@ -968,7 +1007,10 @@ def slab_analyze(img_slab: torch.Tensor, mask_slab: torch.Tensor, notnuc_slab: t
         spot.wait_stream(cur)
         with torch.cuda.stream(spot):
             res = slab_find_spots_snrfilter(img_slab, mask_slab, lay, sigma=sigma, t_spot=t_spot, snr=snr, ops=ops,
-                                            group=group, full_table=full_table)
+                                            group=group, full_table=full_table, after_log=after_log)
+        if gated:
+            after_log()  # (a chain that returned before its LoG)
+            dmap = late["dmap"]
         cur.wait_stream(spot)
         cur.wait_stream(side)
         dmap.record_stream(cur)

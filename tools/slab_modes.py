@@ -1,5 +1,6 @@
 """Mosaic (configs[3]) under torchrun: the two chains of parallel.slab_analyze one after the other, side by side,
-and side by side with the spot chain on the high-priority stream -- both decompositions.  One JSON line."""
+side by side with the spot chain on the high-priority stream, and with the transform's envelope passes gated behind
+the LoG -- both decompositions.  One JSON line."""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, torch.distributed as dist
@@ -27,8 +28,9 @@ for kind in ("z", "x"):
         home = P.slab_input_buffer(lay, 2.0, img.dtype, img.device)
         if home is not None:
             home.copy_(img); img = home
-    for mode in ("serial", "overlap", "overlap_prio"):
+    for mode in ("serial", "overlap", "overlap_prio", "gated"):
         os.environ["MFISH_SLAB_PRIO"] = "1" if mode == "overlap_prio" else "0"
+        os.environ["MFISH_SLAB_GATE"] = "1" if mode == "gated" else "0"
         def step():
             return P.slab_analyze(img, fib, notnuc, lay, sigma=2.0, t_spot=0.025, sampling_xyz=SAMPLING,
                                   edt_group=None if mode == "serial" else edt_group, full_table=False)
