@@ -18,9 +18,10 @@ NOT-nucleus mask and the per-spot distance gather.
                general_pipeline/fish_analysis.py:196-199 actually passes (pageable float64 + int64 masks).
 * ``batch``  : BASELINE configs[2] -- 64 stacks of config-1 geometry through parallel.run_batch, every
                N-th stack per rank, double-buffered pinned staging (host buffers in, host results out).
-* ``slab``   : (N > 1) BASELINE configs[3] -- one mosaic 16384x2048x200 split into z-slabs
-               (parallel.slab_analyze: NCCL halo exchange, all-to-all before the EDT's z pass), strong
-               scaling, plus a check of a quarter mosaic against a single-GPU run of the same data.
+* ``slab``   : (N > 1) BASELINE configs[3] -- one mosaic 16384x2048x200 split into z-slabs, and into x-slabs
+               beside them (parallel.slab_analyze: halo exchange and the all-to-all before the EDT's envelope
+               passes over NVLink peer memory, NCCL for the small collectives), strong scaling, per-phase
+               times, plus a check of a quarter mosaic against a single-GPU run of the same data.
 * N > 1      : one process per GPU (torchrun); ``value`` / ``e2e`` run independent stacks per rank, no
                data-path collective (the reference's batch_process.py model) -> "scaling": "weak".
 * ``--impl reference``: the reference's CPU arithmetic (oracle: scipy.ndimage float64) on the
