@@ -999,11 +999,15 @@ def slab_analyze(img_slab: torch.Tensor, mask_slab: torch.Tensor, notnuc_slab: t
             after_log = None
             with torch.cuda.stream(side):
                 dmap = edt_fn(notnuc_slab, lay, sampling_xyz, ops=ops, group=edt_group)
-        # MFISH_SLAB_PRIO=1 runs the spot chain on the high-priority stream (its LoG passes dispatched ahead of the
-        # transform's blocks).  Measured (tools/slab_modes.py): 1 ms faster at 2 GPUs, 3-4 ms SLOWER at 8 (as slow
-        # as running the chains one after the other) -- off by default.
+        # The spot chain on the high-priority stream (its LoG passes dispatched ahead of the transform's blocks, its
+        # latency-bound end overlapping the envelope passes).  Measured (tools/slab_modes.py, median ms, z- / x-slabs,
+        # without -> with): 2 GPUs 38.3 -> 35.8 / 39.5 -> 36.7; 4 GPUs 48.8 -> 49.4 / 45.1 -> 40.9; 8 GPUs
+        # 35.6 -> 36.8 / 26.6 -> 30.4 (the overlap is lost: as slow as one chain after the other).  Hence: on up to
+        # 4 ranks, off beyond; MFISH_SLAB_PRIO=0/1 overrides.
         import os
-        spot = D._list_stream() if os.environ.get("MFISH_SLAB_PRIO", "0") == "1" else cur
+        prio = os.environ.get("MFISH_SLAB_PRIO", "auto")
+        use_prio = prio == "1" or (prio not in ("0", "1") and lay.world <= 4)
+        spot = D._list_stream() if use_prio else cur
         spot.wait_stream(cur)
         with torch.cuda.stream(spot):
             res = slab_find_spots_snrfilter(img_slab, mask_slab, lay, sigma=sigma, t_spot=t_spot, snr=snr, ops=ops,
