@@ -381,6 +381,20 @@ int mfish_copy2d(void* dst_dev, int64_t dst_pitch, const void* src_dev, int64_t 
 int mfish_copy3d(void* dst_dev, int64_t dst_pitch1, int64_t dst_pitch2, const void* src_dev, int64_t src_pitch1,
                  int64_t src_pitch2, int64_t row_bytes, int64_t n1, int64_t n2, void* stream);
 
+/* ---- connected components (segmentation clean-up and labelling) ------------ *
+ * skimage.morphology.label / remove_small_objects / remove_small_holes as modules/muscle_fish.py:182-184,
+ * 266-272 and nocodazole/fish_analysis_noco.py:227 call them.  mask_dev: C-ordered (na, nb, nc) uint8 volume
+ * (nonzero = foreground; na = 1 for 2-D), laid out in the order the CALLER's array is -- a voxel's linear index
+ * is then the raster index scipy / skimage scan in.  parent_dev (int32, same size) receives, for every
+ * foreground voxel, the smallest linear index of its component (-1 for background): the component's label is the
+ * rank of that index among the roots.  connectivity_full: 26- (8-) neighbourhood, else the 6- (4-) one.      */
+int mfish_ccl_roots_u8(const uint8_t* mask_dev, int64_t na, int64_t nb, int64_t nc, int connectivity_full,
+                       int32_t* parent_dev, void* stream);
+/* np.bincount(labels.ravel(), minlength=nvalues) of an int32 label volume (values outside [0, nvalues) ignored):
+ * the component sizes remove_small_objects / remove_small_holes and threshold_fiber's "largest object" need.   */
+int mfish_label_sizes_i32(const int32_t* labels_dev, int64_t n, int32_t nvalues, unsigned long long* sizes_dev,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -84,6 +84,8 @@ SIGNATURES = {
     "mfish_split_moments_f32": (_i, [_p, _i64, _f, _p, _p]),
     "mfish_binarize_f32": (_i, [_p, _i64, _f, _p, _p, _p]),
     "mfish_compartments_u8": (_i, [_p, _p, _i64, _i64, _i64, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
+    "mfish_ccl_roots_u8": (_i, [_p, _i64, _i64, _i64, _i, _p, _p]),
+    "mfish_label_sizes_i32": (_i, [_p, _i64, C.c_int32, _p, _p]),
     "mfish_copy2d": (_i, [_p, _i64, _p, _i64, _i64, _i64, _p]),
     "mfish_copy3d": (_i, [_p, _i64, _i64, _p, _i64, _i64, _i64, _i64, _i64, _p]),
     "mfish_label_bbox_i32": (_i, [_p, _i64, _i64, _i64, C.c_int32, C.c_int32, _p, _p]),

@@ -8,6 +8,8 @@ rna_decay/fish_analysis_actd.py:165-183; reference paths relative to the upstrea
 * ``iterate(image, op, n3d, n2d)``  the whole loop nest (n3d 3-D steps, then n2d steps on every z plane)
   in one call: n steps with the cross are one step with the L1 ball of radius n, so the 50 sweeps of the
   reference are one capped city-block distance transform on the device.
+* ``label`` / ``remove_small_objects`` / ``remove_small_holes``  connected components on the device, with
+  skimage's numbering (components in raster order of their first voxel).
 * ``compartments(nuclei_binary, fiber_mask)``  region_nuc / region_peri / region_cyt exactly as
   fish_analysis.py:169-186 defines them, from one upload of the two masks.
 
@@ -79,3 +81,20 @@ def compartments(nuclei_binary, fiber_mask, erode=(1, 10), dilate=(4, 40), dtype
     shape = np.asarray(nuclei_binary).shape
     return {"nuc": _mask_to_host(r_nuc, shape, dtype), "cyt": _mask_to_host(r_cyt, shape, dtype),
             "peri": _mask_to_host(r_peri, shape, dtype)}
+
+
+# ``morphology.label`` / ``remove_small_objects`` / ``remove_small_holes`` (modules/muscle_fish.py:182-184, 266-272,
+# nocodazole/fish_analysis_noco.py:227): connected components on the device (csrc/ccl.cu), same numbering as skimage
+def label(image, connectivity=None, return_num=False):
+    from . import segmentation
+    return segmentation.label(image, connectivity=connectivity, return_num=return_num)
+
+
+def remove_small_objects(ar, min_size=64, connectivity=1):
+    from . import segmentation
+    return segmentation.remove_small_objects(ar, min_size, connectivity)
+
+
+def remove_small_holes(ar, area_threshold=64, connectivity=1):
+    from . import segmentation
+    return segmentation.remove_small_holes(ar, area_threshold, connectivity)

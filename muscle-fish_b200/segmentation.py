@@ -6,8 +6,10 @@ the upstream repository root):
                                                          labelling, nuclei outside the fibre dropped
 
 The voxel work -- normalisation, the two large-radius blurs (81 / 161 taps per axis), the 256-bin histogram,
-the iterated means of Li's method, the binarisation -- runs on the GPU.  Connected-component labelling and
-the small-object / small-hole clean-up stay on the host (scipy.ndimage.label), as SURVEY 8f-2 plans.
+the iterated means of Li's method, the binarisation, and (round 2) the connected-component labelling with the
+small-object / small-hole clean-up built on it -- runs on the GPU: ``label`` = ``skimage.morphology.label`` /
+``scipy.ndimage.label`` with the same numbering (components in raster order of their first voxel), union-find
+kernels in ``csrc/ccl.cu``.
 
 skimage version notes (the reference pins none; API usage implies 0.14-0.17): ``threshold_li`` is the
 iterative form those releases ship up to 0.15 (tolerance = half a 256th of the range, start at the mean);
@@ -16,7 +18,9 @@ iterative form those releases ship up to 0.15 (tolerance = half a 256th of the r
 from __future__ import annotations
 
 import numpy as np
+import torch
 
+from . import _lib as L
 from . import device as D
 
 
@@ -67,30 +71,81 @@ def threshold_li(vol_zxy):
     return threshold + immin
 
 
-def _label_full(mask):
-    from scipy import ndimage as ndi
-    return ndi.label(mask, structure=np.ones((3,) * mask.ndim, dtype=bool))  # skimage label: connectivity = ndim
+def label_device(mask: torch.Tensor, full: bool = True):
+    """Connected components of a C-ordered 2-D / 3-D uint8 / bool device mask, in the order the mask is laid out:
+    ``(labels int32, n)`` with the numbering of ``scipy.ndimage.label`` / ``skimage.morphology.label`` (components
+    ranked by their first voxel in raster order).  ``full``: 8- / 26-neighbourhood (skimage's default for
+    ``label``), else 4- / 6-neighbourhood (``connectivity=1``: what remove_small_objects / _holes use on bools)."""
+    m = mask.contiguous()
+    if m.dtype == torch.bool:
+        m = m.view(torch.uint8)
+    if m.dim() not in (2, 3) or m.dtype != torch.uint8:
+        raise ValueError("label_device: 2-D or 3-D uint8 / bool mask expected")
+    dims = (1,) + tuple(m.shape) if m.dim() == 2 else tuple(m.shape)
+    n = m.numel()
+    parent = torch.empty(n, dtype=torch.int32, device=m.device)
+    if n == 0:
+        return parent.view(m.shape), 0
+    L.check(L.lib().mfish_ccl_roots_u8(m.data_ptr(), dims[0], dims[1], dims[2], 1 if full else 0, parent.data_ptr(),
+                                       D._stream()))
+    # every foreground voxel now holds its component's smallest raster index; rank the roots, gather the rank
+    roots = torch.nonzero(parent == torch.arange(n, dtype=torch.int32, device=m.device)).view(-1)
+    ncomp = int(roots.numel())
+    rank = torch.zeros(n + 1, dtype=torch.int32, device=m.device)  # slot n: the background's "root"
+    rank[roots] = torch.arange(1, ncomp + 1, dtype=torch.int32, device=m.device)
+    labels = rank[torch.where(parent >= 0, parent, n).long()]
+    return labels.view(m.shape), ncomp
 
 
-def _remove_small_objects(ar, min_size):
-    """skimage.morphology.remove_small_objects(bool array, min_size, connectivity=1)"""
-    from scipy import ndimage as ndi
-    lab, _ = ndi.label(ar)  # cross: connectivity 1
-    sizes = np.bincount(lab.ravel())
-    too_small = sizes < min_size
-    too_small[0] = False
-    out = ar.copy()
-    out[too_small[lab]] = False
-    return out
+def label_sizes(labels: torch.Tensor, ncomp: int) -> torch.Tensor:
+    """voxel count per label 0 .. ncomp (np.bincount(labels.ravel())), int64 on the device"""
+    lab = labels.contiguous()
+    sizes = torch.empty(ncomp + 1, dtype=torch.int64, device=lab.device)
+    L.check(L.lib().mfish_label_sizes_i32(lab.data_ptr(), lab.numel(), ncomp + 1, sizes.data_ptr(), D._stream()))
+    return sizes
 
 
-def _remove_small_holes(ar, area_threshold):
-    return np.logical_not(_remove_small_objects(np.logical_not(ar), area_threshold))
+def remove_small_objects_device(mask: torch.Tensor, min_size: int) -> torch.Tensor:
+    """skimage.morphology.remove_small_objects(bool array, min_size) (connectivity 1) -> bool device mask"""
+    lab, n = label_device(mask, full=False)
+    keep = label_sizes(lab, n) >= int(min_size)
+    keep[0] = False
+    return keep[lab.long()]
 
 
-def _host_mask(m_zxy, z_first):
-    t = m_zxy if z_first else m_zxy.permute(1, 2, 0).contiguous()
-    return t.cpu().numpy()
+def remove_small_holes_device(mask: torch.Tensor, area_threshold: int) -> torch.Tensor:
+    """skimage.morphology.remove_small_holes(bool array, area_threshold) (connectivity 1)"""
+    m = mask if mask.dtype == torch.bool else mask != 0
+    return ~remove_small_objects_device(~m, area_threshold)
+
+
+def remove_small_objects(ar, min_size=64, connectivity=1):
+    """``skimage.morphology.remove_small_objects`` for a host BOOL array (modules/muscle_fish.py:182)."""
+    a = np.asarray(ar)
+    if a.dtype != np.bool_ or connectivity != 1:
+        raise NotImplementedError("remove_small_objects: bool arrays with connectivity 1 (what the reference passes)")
+    return remove_small_objects_device(D.host_to_device(np.ascontiguousarray(a)), min_size).cpu().numpy()
+
+
+def remove_small_holes(ar, area_threshold=64, connectivity=1):
+    """``skimage.morphology.remove_small_holes`` for a host BOOL array (modules/muscle_fish.py:183)."""
+    a = np.asarray(ar)
+    if a.dtype != np.bool_ or connectivity != 1:
+        raise NotImplementedError("remove_small_holes: bool arrays with connectivity 1 (what the reference passes)")
+    return remove_small_holes_device(D.host_to_device(np.ascontiguousarray(a)), area_threshold).cpu().numpy()
+
+
+def label(image, connectivity=None, return_num=False):
+    """``skimage.morphology.label`` for a host array (the import-line seam of
+    nocodazole/fish_analysis_noco.py:227: ``morphology.label(region_nuc, return_num=True)``): labels in the
+    array's own raster order, int64 like skimage's."""
+    a = np.asarray(image)
+    if connectivity not in (None, 1, a.ndim):
+        raise NotImplementedError("label: connectivity 1 or the full neighbourhood")
+    m = D.host_to_device(np.ascontiguousarray(a != 0))
+    lab, n = label_device(m, full=connectivity != 1 or a.ndim == 1)
+    out = lab.cpu().numpy().astype(np.int64)
+    return (out, n) if return_num else out
 
 
 def threshold_fiber(img_fish, t_fiber=None, z_first=False, verbose=False):
@@ -114,16 +169,17 @@ def threshold_fiber(img_fish, t_fiber=None, z_first=False, verbose=False):
         bin_d = bin_d[-1:].expand_as(bin_d).contiguous()
         if verbose:
             print('OVERRIDE: using final frame mask for entire z-stack.')
-    bin_fiber = _host_mask(bin_d, False)  # (x, y, z), as the reference labels it
-    fiber_labeled, n_labels = _label_full(bin_fiber)
-    sizes = np.bincount(fiber_labeled.ravel())
-    sizes[0] = 0
+    bin_xyz = bin_d.permute(1, 2, 0).contiguous()  # (x, y, z), as the reference labels it
+    fiber_labeled, n_labels = label_device(bin_xyz, full=True)
     if n_labels == 0:
         raise ValueError("max() arg is an empty sequence")  # what max(label_sizes, ...) raises upstream
-    mask = np.where(fiber_labeled == int(np.argmax(sizes)), 1, 0)
+    sizes = label_sizes(fiber_labeled, n_labels)
+    sizes[0] = 0
+    biggest = int(torch.argmax(sizes).item())  # the first of equally large ones, as np.argmax / max() upstream
+    mask_d = (fiber_labeled == biggest).to(torch.uint8)
     if z_first:
-        mask = mask.transpose(2, 0, 1)
-    return mask
+        mask_d = mask_d.permute(2, 0, 1).contiguous()
+    return mask_d.cpu().numpy().astype(np.int64)  # np.where(..., 1, 0)
 
 
 def threshold_nuclei(img_dapi, t_dapi=None, fiber_mask=None, labeled=True, multiplier=0.75, z_first=False,
@@ -142,17 +198,23 @@ def threshold_nuclei(img_dapi, t_dapi=None, fiber_mask=None, labeled=True, multi
     if verbose:
         print('DAPI threshold = ' + str(thresh))
     # the NORMALISED, unblurred image is what gets binarised (modules/muscle_fish.py:181)
-    bin_dapi = _host_mask(D.binarize(vol.data, thresh, vol.minmax), z_first).astype(bool)
-    bin_dapi = _remove_small_objects(bin_dapi, 2048)
-    bin_dapi = _remove_small_holes(bin_dapi, 2048)
-    nuclei_labeled, n_nuc = _label_full(bin_dapi)
+    bin_d = D.binarize(vol.data, thresh, vol.minmax)  # [z][x][y]
+    bin_dapi = (bin_d if z_first else bin_d.permute(1, 2, 0).contiguous()) != 0  # the caller's own axis order
+    bin_dapi = remove_small_objects_device(bin_dapi, 2048)
+    bin_dapi = remove_small_holes_device(bin_dapi, 2048)
+    nuclei_labeled, n_nuc = label_device(bin_dapi, full=True)
     if fiber_mask is not None:
         if verbose:
             print('Removing nuclei that are not connected to main fiber segment...')
-        inside = np.bincount(nuclei_labeled[np.asarray(fiber_mask).astype(bool)].ravel(), minlength=n_nuc + 1)
+        (fm, ev), = D.host_to_device_many([fiber_mask], kinds=("mask",))
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+        if tuple(fm.shape) != tuple(nuclei_labeled.shape):
+            raise ValueError("operands could not be broadcast together: fiber_mask and image shapes differ")
+        inside = torch.bincount(nuclei_labeled[fm != 0].view(-1), minlength=n_nuc + 1)
         drop = inside == 0
         drop[0] = False
-        nuclei_labeled[drop[nuclei_labeled]] = 0
+        nuclei_labeled = torch.where(drop[nuclei_labeled.long()], torch.zeros_like(nuclei_labeled), nuclei_labeled)
     if labeled:
-        return nuclei_labeled
-    return np.where(nuclei_labeled > 0, 1, 0)
+        return nuclei_labeled.cpu().numpy().astype(np.int64)
+    return (nuclei_labeled > 0).cpu().numpy().astype(np.int64)

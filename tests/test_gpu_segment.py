@@ -91,3 +91,61 @@ def test_threshold_fiber_and_nuclei_vs_oracle(z_first, capsys):
         last_ref = S.threshold_fiber(img, t_fiber='last')
         last_got = sg.threshold_fiber(img, t_fiber='last')
         assert (last_got != last_ref).mean() < 2e-3
+
+
+def _blobs(shape, p, seed):
+    """random mask with structure at several scales: noise voxels, blobs, holes"""
+    from scipy import ndimage as ndi
+    rng = np.random.default_rng(seed)
+    m = ndi.gaussian_filter(rng.random(shape), 1.5) > (0.5 + 0.02 * (1 - 2 * p))
+    m |= rng.random(shape) < 0.02 * p
+    m &= ~(rng.random(shape) < 0.01)
+    return m
+
+
+@pytest.mark.parametrize("shape", [(40, 33, 17), (9, 64, 5), (1, 50, 60), (70, 45), (3, 3, 3), (128, 96, 24)])
+@pytest.mark.parametrize("full", [True, False])
+@pytest.mark.parametrize("p", [0.2, 0.8])
+def test_label_matches_scipy_numbering(shape, full, p):
+    """csrc/ccl.cu: same components AND the same label numbers as scipy.ndimage.label / skimage.morphology.label
+    (components ranked by their first voxel in raster order), both neighbourhoods, 2-D and 3-D"""
+    import torch
+    from scipy import ndimage as ndi
+    from muscle_fish_b200 import segmentation as sg
+    m = _blobs(shape, p, seed=len(shape) * 7 + shape[0])
+    structure = np.ones((3,) * m.ndim, bool) if full else None
+    ref, n_ref = ndi.label(m, structure=structure)
+    lab, n = sg.label_device(torch.from_numpy(m).cuda(), full=full)
+    assert n == n_ref and n >= 1
+    np.testing.assert_array_equal(lab.cpu().numpy(), ref)
+    got, n2 = sg.label(m, connectivity=None if full else 1, return_num=True)
+    assert n2 == n_ref and got.dtype == np.int64
+    np.testing.assert_array_equal(got, ref)
+
+
+def test_label_edge_cases():
+    import torch
+    from muscle_fish_b200 import segmentation as sg, morphology
+    z = torch.zeros((5, 6, 7), dtype=torch.uint8, device="cuda")
+    lab, n = sg.label_device(z)
+    assert n == 0 and not lab.any()
+    o = torch.ones((5, 6, 7), dtype=torch.uint8, device="cuda")
+    lab, n = sg.label_device(o, full=False)
+    assert n == 1 and bool((lab == 1).all())
+    # a long snake: many union steps along one chain
+    s = np.zeros((64, 64), bool)
+    s[::2, :] = True
+    s[1::4, -1] = True
+    s[3::4, 0] = True
+    out, n = morphology.label(s, connectivity=1, return_num=True)
+    assert n == 1 and np.array_equal(out != 0, s)
+
+
+@pytest.mark.parametrize("min_size", [4, 40])
+def test_remove_small_objects_and_holes_vs_oracle(min_size):
+    """skimage.morphology.remove_small_objects / remove_small_holes on bool arrays (connectivity 1), as
+    modules/muscle_fish.py:182-183 call them"""
+    from muscle_fish_b200 import morphology
+    m = _blobs((48, 40, 12), 0.5, seed=9)
+    np.testing.assert_array_equal(morphology.remove_small_objects(m, min_size), S.remove_small_objects(m, min_size))
+    np.testing.assert_array_equal(morphology.remove_small_holes(m, min_size), S.remove_small_holes(m, min_size))
