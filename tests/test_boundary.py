@@ -275,9 +275,12 @@ def test_nocodazole_call_sequence_vs_oracle():
     ref_grass = oracle.distance_transform_edt(np.logical_not(ref_region), sampling=dims_xyz)
     assert grassfire.dtype == np.float64
     np.testing.assert_allclose(grassfire, ref_grass, rtol=1e-6)
-    # :227-235  labels (host) and the faded mask of every nucleus
-    lab, n_nuc = ref_fade.label_nuclei(region_nuc)
-    assert n_nuc >= 2
+    # :227-235  labels (morphology.label on the device, skimage's numbering) and the faded mask of every nucleus
+    region_nuc_labeled, n_nuc = morphology.label(region_nuc, return_num=True)
+    lab = region_nuc_labeled - 1  # shift so bg = -1 and nuclei = [0:n_nuc]
+    ref_lab, ref_n = ref_fade.label_nuclei(region_nuc)
+    assert n_nuc == ref_n >= 2
+    np.testing.assert_array_equal(lab, ref_lab)
     fades = filters.nucleus_fades(lab, n_nuc)
     for i in range(n_nuc):
         nuc = np.where(lab == i, 1, 0)
