@@ -350,6 +350,17 @@ class Handoff:
 
 
 HANDOFF = Handoff()
+# the same for MASKS this package returned (threshold_fiber's result is the `mask=` of every later call of
+# general_pipeline/fish_analysis.py:152-199): the payload is the uint8 device mask [nz][nx][ny]
+MASK_HANDOFF = Handoff()
+
+
+def ingest_mask(src, z_first=False, negate=False, ready=None):
+    """``ingest(src, as_mask=True)``, skipping the upload for a mask array this package returned itself"""
+    m = MASK_HANDOFF.lookup(src, z_first)
+    if m is not None:
+        return (m == 0).to(torch.uint8) if negate else m
+    return ingest(src, z_first=z_first, as_mask=True, negate=negate, ready=ready)
 
 
 def minmax(vol: torch.Tensor) -> torch.Tensor:
@@ -1157,7 +1168,8 @@ def analyze_host(img_fish, fiber_mask, region_nuc, sigma=2.0, t_spot=0.025, samp
     ``region_nuc`` is the nucleus mask itself (the NOT is taken on ingest, nocodazole/fish_analysis_noco.py:218).
     Returns the dict of ``analyze_stack``."""
     t = timer or _NoTimer()
-    (tn, en), (ti, ei), (tf, ef) = host_to_device_many([region_nuc, img_fish, fiber_mask],
+    fiber_dev = MASK_HANDOFF.lookup(fiber_mask, z_first)  # a mask this package returned: already on the device
+    (tn, en), (ti, ei), (tf, ef) = host_to_device_many([region_nuc, img_fish, None if fiber_dev is not None else fiber_mask],
                                                        kinds=("mask", "image", "mask"))
     main = torch.cuda.current_stream()
     side = _side_stream()
@@ -1177,7 +1189,7 @@ def analyze_host(img_fish, fiber_mask, region_nuc, sigma=2.0, t_spot=0.025, samp
     # handling (high-priority stream) queues behind PCIe
     fiber_arrived = torch.cuda.Event()
     with torch.cuda.stream(side):
-        fiber = ingest(tf, z_first=z_first, as_mask=True, ready=ef)
+        fiber = fiber_dev if fiber_dev is not None else ingest(tf, z_first=z_first, as_mask=True, ready=ef)
         if tuple(fiber.shape) != tuple(vol.data.shape):
             raise IndexError("mask and image shapes differ")
         fiber_arrived.record(side)

@@ -27,7 +27,7 @@ def _mask_to_device(image):
     """host 2-D [nx][ny] or 3-D (x,y,z) array -> uint8 device mask [nz][nx][ny] (nonzero = set)"""
     a = np.asarray(image)
     if a.ndim == 3:
-        return D.ingest(a, as_mask=True), a.shape
+        return D.ingest_mask(image if isinstance(image, np.ndarray) else a), a.shape
     if a.ndim == 2:
         import torch
         t = D.host_to_device(a)

@@ -23,8 +23,10 @@ class _Lazy:
     """A mask whose host->device copy is already queued; converted on first use, so that the
     filters on the image overlap the mask's trip over PCIe."""
 
-    def __init__(self, tensor, event, z_first, shape):
-        self.tensor, self.event, self.z_first, self.shape, self._m = tensor, event, z_first, shape, None
+    def __init__(self, tensor, event, z_first, shape, ready=None):
+        self.tensor, self.event, self.z_first, self.shape, self._m = tensor, event, z_first, shape, ready
+        if ready is not None and tuple(ready.shape) != tuple(shape):
+            raise IndexError("mask and image shapes differ: %r vs %r" % (tuple(ready.shape), tuple(shape)))
 
     def get(self):
         if self._m is None:
@@ -37,12 +39,14 @@ class _Lazy:
 
 def _prep(img_fish, mask, z_first):
     vol = D.HANDOFF.lookup(img_fish, z_first)  # an array this package returned: already on the device
+    mdev = D.MASK_HANDOFF.lookup(mask, z_first)  # the same for a mask (threshold_fiber's result)
+    up_mask = None if mdev is not None else mask
     if vol is not None:
-        (tm, em), = D.host_to_device_many([mask], kinds=("mask",))
+        (tm, em), = D.host_to_device_many([up_mask], kinds=("mask",))
     else:
-        (ti, ei), (tm, em) = D.host_to_device_many([img_fish, mask], kinds=("image", "mask"))
+        (ti, ei), (tm, em) = D.host_to_device_many([img_fish, up_mask], kinds=("image", "mask"))
         vol = D.ingest(ti, z_first=z_first, ready=ei)
-    m = _Lazy(tm, em, z_first, vol.data.shape) if mask is not None else None
+    m = _Lazy(tm, em, z_first, vol.data.shape, ready=mdev) if mask is not None else None
     return vol, m
 
 
@@ -162,7 +166,7 @@ def fix_bleaching(img, second_half=True, mask=None, z_first=False, draw=False, i
 
     img = np.asarray(img)
     vol = D.HANDOFF.lookup(img, z_first) or D.ingest(img, z_first=z_first, want_minmax=False)
-    m = D.ingest(mask, z_first=z_first, as_mask=True) if mask is not None else None
+    m = D.ingest_mask(mask, z_first=z_first) if mask is not None else None
     nz = vol.data.shape[0]
     start_frame = nz // 2 if second_half else 0
     sums, cnts = D.plane_means(vol.data, m)

@@ -176,10 +176,12 @@ def threshold_fiber(img_fish, t_fiber=None, z_first=False, verbose=False):
     sizes = label_sizes(fiber_labeled, n_labels)
     sizes[0] = 0
     biggest = int(torch.argmax(sizes).item())  # the first of equally large ones, as np.argmax / max() upstream
-    mask_d = (fiber_labeled == biggest).to(torch.uint8)
-    if z_first:
-        mask_d = mask_d.permute(2, 0, 1).contiguous()
-    return mask_d.cpu().numpy().astype(np.int64)  # np.where(..., 1, 0)
+    mask_d = (fiber_labeled == biggest).to(torch.uint8)  # (x, y, z)
+    mask_zxy = mask_d.permute(2, 0, 1).contiguous()
+    out = (mask_zxy if z_first else mask_d).cpu().numpy().astype(np.int64)  # np.where(..., 1, 0)
+    # the fibre mask is the `mask=` of every later call (general_pipeline/fish_analysis.py:152-199): keep its
+    # device twin, so those calls find it resident instead of uploading 8 bytes per voxel again
+    return D.MASK_HANDOFF.register(out, mask_zxy, z_first)
 
 
 def threshold_nuclei(img_dapi, t_dapi=None, fiber_mask=None, labeled=True, multiplier=0.75, z_first=False,
@@ -206,9 +208,13 @@ def threshold_nuclei(img_dapi, t_dapi=None, fiber_mask=None, labeled=True, multi
     if fiber_mask is not None:
         if verbose:
             print('Removing nuclei that are not connected to main fiber segment...')
-        (fm, ev), = D.host_to_device_many([fiber_mask], kinds=("mask",))
-        if ev is not None:
-            torch.cuda.current_stream().wait_event(ev)
+        fm = D.MASK_HANDOFF.lookup(fiber_mask, z_first)
+        if fm is not None:
+            fm = fm if z_first else fm.permute(1, 2, 0)  # [z][x][y] -> the caller's axis order
+        else:
+            (fm, ev), = D.host_to_device_many([fiber_mask], kinds=("mask",))
+            if ev is not None:
+                torch.cuda.current_stream().wait_event(ev)
         if tuple(fm.shape) != tuple(nuclei_labeled.shape):
             raise ValueError("operands could not be broadcast together: fiber_mask and image shapes differ")
         inside = torch.bincount(nuclei_labeled[fm != 0].view(-1), minlength=n_nuc + 1)
