@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmfish_sm100.so")
+# (MFISH_LIB: an alternative build of the library, for A/B timing of kernel variants -- tools/)
+LIB_PATH = os.environ.get("MFISH_LIB") or os.path.join(_HERE, "libmfish_sm100.so")
 
 # constants mirrored from include/mfish.h
 ABI_VERSION = 5
