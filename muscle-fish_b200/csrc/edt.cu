@@ -313,7 +313,10 @@ struct Hull<false> {
 // SQ : EDT_OUT_DIST only -- 0 distances, 1 distances + int32 squares, 2 int32 squares only
 // IdxT: element offsets inside a line bundle (uint32 when the volume has < 2^32 elements)
 template <typename TIn, typename LinkT, int OUT, int SQ, bool INT, typename IdxT, int ENV_BATCH>
-__global__ void __launch_bounds__(ENV_THREADS) edt_envelope_kernel(const EnvArgs<TIn, LinkT> a) {
+// (min-blocks 1 on the long-line instances lifts ptxas' own cap of 40 registers -- 48, no spills: x pass 1.45 ->
+// 1.38 ms; the short-line instances are faster under the cap, 0 = unspecified)
+__global__ void __launch_bounds__(ENV_THREADS, ENV_BATCH == ENV_BATCH_LONG ? 1 : 0)
+    edt_envelope_kernel(const EnvArgs<TIn, LinkT> a) {
   using H = Hull<INT>;
   using GT = typename H::G;
   using BT = typename H::B;
