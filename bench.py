@@ -505,6 +505,8 @@ def bench_slab(ctx, args):
         torch.cuda.reset_peak_memory_stats()
         dt, res = ctx.timed(step, steps, 2)
         ms = dt / steps * 1e3
+        # single steps as well: side by side, the two chains' cross-rank waits make a step vary by several ms
+        singles = [ctx.timed(step, 1, 0)[0] * 1e3 for _ in range(6)]
         # one more step with per-phase wall clocks (synchronising: the two chains then run one after the other)
         # (an untimed one first: without the second communicator the EDT's exchange makes new connections)
         P.slab_analyze(img, fib, notnuc, lay, sigma=SIGMA, t_spot=T_SPOT, sampling_xyz=SAMPLING, full_table=False)
@@ -523,6 +525,7 @@ def bench_slab(ctx, args):
             "workload": f"configs[3]: mosaic {X}x{Y}x{Z} in {world} {kind}-slabs, parallel.slab_analyze (spot path + "
                         "EDT + per-spot distances), device-resident slabs",
             "ms_per_step": ms, "value": nvox / ms / 1e6, "found_spots": int(len(res["spots"])),
+            "ms_single_steps": [round(v, 2) for v in singles], "ms_median_single": float(np.median(singles)),
             "phases_ms_serialised": phases,
             "halo_bytes_in_per_rank": int(halo_bytes), "halo_gbs": gbs(halo_bytes, "halo"),
             "all_to_all_bytes_out_per_rank": int(a2a_bytes), "all_to_all_gbs": gbs(a2a_bytes, "edt_all_to_all"),
@@ -641,7 +644,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--slab-steps", type=int, default=5)
+    ap.add_argument("--slab-steps", type=int, default=10)
     ap.add_argument("--batch-stacks", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-batch", action="store_true")
