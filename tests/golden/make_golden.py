@@ -1,4 +1,4 @@
-"""Generate tests/golden/golden_small.npz.
+"""Generate tests/golden/golden_small.npz (default), golden_morph.npz (`morph`), golden_label.npz (`label`).
 
 The reference's own modules cannot be imported in this image (matplotlib / scikit-image /
 czifile are absent), and it ships no test vectors.  The fixtures are therefore produced by the
@@ -69,8 +69,45 @@ def main_morph():
     print("wrote", path, {k: (v.shape, int(v.sum())) for k, v in out.items()}, os.path.getsize(path), "bytes")
 
 
+def main_label():
+    """tests/golden/golden_label.npz: connected components (both neighbourhoods), the small-object / small-hole
+    clean-up and the per-nucleus faded masks of modules/muscle_fish.py:182-184 and
+    nocodazole/fish_analysis_noco.py:227-235 by the real scipy.ndimage label / gaussian_filter."""
+    rng = np.random.default_rng(97)
+    shape = (48, 40, 12)
+    m = ndi.gaussian_filter(rng.random(shape), 1.5) > 0.5
+    m |= rng.random(shape) < 0.01
+    m &= ~(rng.random(shape) < 0.01)
+    lab26, n26 = ndi.label(m, structure=np.ones((3, 3, 3), bool))
+    lab6, n6 = ndi.label(m)
+    out = {"mask": m.astype(np.uint8), "label_full": lab26.astype(np.int32), "n_full": np.array(n26),
+           "label_cross": lab6.astype(np.int32), "n_cross": np.array(n6)}
+    sizes = np.bincount(lab6.ravel())
+    small = sizes < 30
+    small[0] = False
+    out["no_small_objects_30"] = (m & ~small[lab6]).astype(np.uint8)
+    inv = ~m
+    labh, _ = ndi.label(inv)
+    hs = np.bincount(labh.ravel())
+    smallh = hs < 30
+    smallh[0] = False
+    out["no_small_holes_30"] = (~(inv & ~smallh[labh])).astype(np.uint8)
+    st = synth.make_stack(shape=(72, 64, 20), n_spots=10, n_nuclei=3, seed=98, nuc_semi=(14.0, 9.0, 5.0))
+    nuc_lab, n = ndi.label(st["nuc_mask"] > 0, structure=np.ones((3, 3, 3), bool))
+    out["nuc_labeled"] = (nuc_lab - 1).astype(np.int32)  # bg = -1, nuclei 0..n-1 (fish_analysis_noco.py:229)
+    for i in range(n):
+        out[f"fade_{i}"] = ndi.gaussian_filter((nuc_lab - 1 == i).astype(float), (3, 3, 1), mode="nearest",
+                                               truncate=4.0).astype(np.float32)
+    out["n_nuc"] = np.array(n)
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_label.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, {k: getattr(v, "shape", None) for k, v in out.items()}, os.path.getsize(path), "bytes")
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "morph":
+    if len(sys.argv) > 1 and sys.argv[1] == "label":
+        main_label()
+    elif len(sys.argv) > 1 and sys.argv[1] == "morph":
         main_morph()
     else:
         main()

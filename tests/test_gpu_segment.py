@@ -149,3 +149,23 @@ def test_remove_small_objects_and_holes_vs_oracle(min_size):
     m = _blobs((48, 40, 12), 0.5, seed=9)
     np.testing.assert_array_equal(morphology.remove_small_objects(m, min_size), S.remove_small_objects(m, min_size))
     np.testing.assert_array_equal(morphology.remove_small_holes(m, min_size), S.remove_small_holes(m, min_size))
+
+
+def test_label_cleanup_and_fades_vs_golden():
+    """the committed fixture of the real scipy routines (tests/golden/golden_label.npz)"""
+    import os
+    from muscle_fish_b200 import filters, morphology
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_label.npz"))
+    m = g["mask"].astype(bool)
+    lab, n = morphology.label(m, return_num=True)
+    assert n == int(g["n_full"])
+    np.testing.assert_array_equal(lab, g["label_full"])
+    lab1, n1 = morphology.label(m, connectivity=1, return_num=True)
+    assert n1 == int(g["n_cross"])
+    np.testing.assert_array_equal(lab1, g["label_cross"])
+    np.testing.assert_array_equal(morphology.remove_small_objects(m, 30), g["no_small_objects_30"].astype(bool))
+    np.testing.assert_array_equal(morphology.remove_small_holes(m, 30), g["no_small_holes_30"].astype(bool))
+    nuc_lab = g["nuc_labeled"]
+    fades = filters.nucleus_fades(nuc_lab, int(g["n_nuc"]))
+    for i in range(int(g["n_nuc"])):
+        assert np.abs(fades[i] - g[f"fade_{i}"]).max() <= 1e-5

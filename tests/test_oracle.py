@@ -238,3 +238,23 @@ def test_compartment_oracle_matches_golden_and_the_closed_form():
     m = nuc.astype(bool)
     for op, n3, n2 in [("dilate", 4, 7), ("erode", 1, 3), ("dilate", 0, 5), ("erode", 2, 0)]:
         np.testing.assert_array_equal(M.iterate(m, op, n3, n2), closed(m, op, n3, n2))
+
+
+def test_oracle_label_and_fade_reproduce_golden():
+    """tests/golden/golden_label.npz (real scipy label / gaussian_filter): the oracle's restatements of skimage's
+    label / remove_small_objects / remove_small_holes (ref_segment) and of the per-nucleus loop (ref_fade)."""
+    import os
+    from oracle import ref_fade, ref_segment as S
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_label.npz"))
+    m = g["mask"].astype(bool)
+    lab, n = S.label(m)
+    assert n == int(g["n_full"])
+    np.testing.assert_array_equal(lab, g["label_full"])
+    np.testing.assert_array_equal(S.remove_small_objects(m, 30), g["no_small_objects_30"].astype(bool))
+    np.testing.assert_array_equal(S.remove_small_holes(m, 30), g["no_small_holes_30"].astype(bool))
+    nuc_lab = g["nuc_labeled"]
+    lab2, n2 = ref_fade.label_nuclei(nuc_lab >= 0)
+    assert n2 == int(g["n_nuc"])
+    np.testing.assert_array_equal(lab2, nuc_lab)
+    for i in range(n2):
+        np.testing.assert_allclose(ref_fade.nucleus_fade(nuc_lab, i), g[f"fade_{i}"], rtol=0, atol=1e-7)
