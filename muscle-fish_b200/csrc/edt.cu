@@ -18,6 +18,7 @@
 //                           integer < 2^53.  A backward sweep walks the hull and evaluates.
 // Algorithmic bytes per voxel: pass 1 R1+W2, pass 2 R2+W2(link)+W4, pass 3 R4+W2(link)+W4.
 #include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -270,6 +271,9 @@ constexpr int ENV_THREADS = 128;
 // 12 -- measured 1.76 -> 1.67 ms on C2, while 16 costs 1.90 ms and the x pass is indifferent)
 constexpr int ENV_BATCH_LONG = 8;
 constexpr int ENV_BATCH_SHORT = 4;
+#ifndef ENV_BANDED_MIN_BLOCKS
+#define ENV_BANDED_MIN_BLOCKS 10
+#endif
 
 // Arithmetic of the hull tests.  With G(u) = F(u)/w2 + u^2, site b is hidden by (a, q) iff
 //     (Gb - Ga) (q - b)  >=  (Gq - Gb) (b - a).
@@ -312,25 +316,45 @@ struct Hull<false> {
 // OUT: EDT_OUT_I32 (squared, int32) / EDT_OUT_F32 (squared, float) / EDT_OUT_DIST (sqrt, float)
 // SQ : EDT_OUT_DIST only -- 0 distances, 1 distances + int32 squares, 2 int32 squares only
 // IdxT: element offsets inside a line bundle (uint32 when the volume has < 2^32 elements)
-template <typename TIn, typename LinkT, int OUT, int SQ, bool INT, typename IdxT, int ENV_BATCH>
+// BANDS: 1 = one thread per line.  2 = two threads per line (all-integer instances only): the line is cut in the
+//        middle, the thread of the upper band works in MIRRORED coordinates (t' = L-1-u, negative memory stride), so
+//        both threads scan from their outer end towards the cut and both hull stacks end with their top next to it.
+//        With G(u) = F(u) + u^2 the hull is the lower convex hull of the points (u, G(u)) (adding the linear term of
+//        the mirrored frame does not change it), so the two chains are joined by their lower common tangent: entries
+//        are dropped from the two tops -- the only direction the in-place links allow, and the one the tangent
+//        needs -- until neither top is hidden by its neighbour below and the other chain's top.  Both threads
+//        run that (short) walk redundantly, then each fills from the tangent's crossing point outwards along its
+//        own chain.  Twice the threads: the x pass of a 2048 x 2048 x 100 stack no longer runs as a single partial wave.
+template <typename TIn, typename LinkT, int OUT, int SQ, bool INT, typename IdxT, int ENV_BATCH, int BANDS>
 // (min-blocks 1 on the long-line instances lifts ptxas' own cap of 40 registers -- 48, no spills: x pass 1.45 ->
 // 1.38 ms; the short-line instances are faster under the cap, 0 = unspecified)
-__global__ void __launch_bounds__(ENV_THREADS, ENV_BATCH == ENV_BATCH_LONG ? 1 : 0)
+__global__ void __launch_bounds__(ENV_THREADS, BANDS == 2 ? ENV_BANDED_MIN_BLOCKS : (ENV_BATCH == ENV_BATCH_LONG ? 1 : 0))
     edt_envelope_kernel(const EnvArgs<TIn, LinkT> a) {
+  static_assert(BANDS == 1 || (BANDS == 2 && INT), "banded lines: all-integer instances only");
   using H = Hull<INT>;
   using GT = typename H::G;
   using BT = typename H::B;
   using WT = typename H::W;
   using R = EdtRaw<TIn>;
-  const int64_t i = (int64_t)blockIdx.x * ENV_THREADS + threadIdx.x;
-  if (i >= a.inner) return;
-  const int64_t base = (int64_t)blockIdx.y * a.outer_stride + i;
+  // pointer walks along a line: unsigned element steps (one thread per line) / signed ones (the mirrored band)
+  using StepT = typename std::conditional<BANDS == 1, IdxT, int64_t>::type;
+  constexpr int LINES = ENV_THREADS / BANDS;  // lines per block
+  const int band = BANDS == 1 ? 0 : (int)threadIdx.x / LINES;  // warp-uniform
+  const int64_t i = (int64_t)blockIdx.x * LINES + (BANDS == 1 ? (int)threadIdx.x : (int)threadIdx.x % LINES);
+  if (BANDS == 1 && i >= a.inner) return;
+  const bool valid = i < a.inner;  // BANDS == 2: every thread reaches the barrier below
+  const int Lfull = a.L;
+  // this thread's share of the line, in its own frame: L sites, element 0 at `base`, step `stp`
+  const int L = BANDS == 1 ? Lfull : (!valid ? 0 : (band == 0 ? Lfull / 2 : Lfull - Lfull / 2));
+  const int64_t line0 = (int64_t)blockIdx.y * a.outer_stride + (valid ? i : 0);
+  const int64_t base = line0 + (band ? (int64_t)(Lfull - 1) * a.stride : 0);
+  const StepT stp = (StepT)(band ? -a.stride : a.stride);
   const TIn* __restrict__ in = a.in + base;
   // hull links and payloads are addressed as parameter base + one IdxT element index (a single
-  // IMAD.WIDE per access when the volume has < 2^32 elements), not through 64-bit pointer arithmetic
+  // IMAD.WIDE per access when the volume has < 2^32 elements), not through 64-bit pointer arithmetic;
+  // the mirrored band's negative step wraps modulo 2^32 there, the sums stay true element offsets
   const IdxT bi = (IdxT)base;
-  const IdxT st = (IdxT)a.stride;
-  const int L = a.L;
+  const IdxT st = (IdxT)stp;
   const double sG = a.sG;
 
   // ---- forward sweep: build the hull as an in-place linked stack (link[q] = entry below q).
@@ -344,9 +368,9 @@ __global__ void __launch_bounds__(ENV_THREADS, ENV_BATCH == ENV_BATCH_LONG ? 1 :
   {
     uint32_t nb[ENV_BATCH];
 #pragma unroll
-    for (int u = 0; u < ENV_BATCH; ++u) nb[u] = u < L ? R::fetch(in + (IdxT)u * st) : R::kFetchNone;
+    for (int u = 0; u < ENV_BATCH; ++u) nb[u] = u < L ? R::fetch(in + (StepT)u * stp) : R::kFetchNone;
     IdxT lidx = bi;
-    const TIn* __restrict__ pnext = in + (IdxT)ENV_BATCH * st;
+    const TIn* __restrict__ pnext = in + (StepT)ENV_BATCH * stp;
     double qd = 0.0;
     // one hull step for site q with payload rq (skipped for "no site")
     auto step = [&](uint32_t rq, int q) {
@@ -384,8 +408,8 @@ __global__ void __launch_bounds__(ENV_THREADS, ENV_BATCH == ENV_BATCH_LONG ? 1 :
 #pragma unroll
       for (int u = 0; u < ENV_BATCH; ++u) s_raw[u][threadIdx.x] = nb[u];
 #pragma unroll
-      for (int u = 0; u < ENV_BATCH; ++u) nb[u] = R::fetch(pnext + (IdxT)u * st);
-      pnext += (IdxT)ENV_BATCH * st;
+      for (int u = 0; u < ENV_BATCH; ++u) nb[u] = R::fetch(pnext + (StepT)u * stp);
+      pnext += (StepT)ENV_BATCH * stp;
 #pragma unroll 4
       for (int u = 0; u < ENV_BATCH; ++u) step(R::decode(s_raw[u][threadIdx.x]), q0 + u);
     }
@@ -395,8 +419,8 @@ __global__ void __launch_bounds__(ENV_THREADS, ENV_BATCH == ENV_BATCH_LONG ? 1 :
       for (int u = 0; u < ENV_BATCH; ++u) s_raw[u][threadIdx.x] = nb[u];
 #pragma unroll
       for (int u = 0; u < ENV_BATCH; ++u)
-        nb[u] = (q0 + ENV_BATCH + u < L) ? R::fetch(pnext + (IdxT)u * st) : R::kFetchNone;
-      pnext += (IdxT)ENV_BATCH * st;
+        nb[u] = (q0 + ENV_BATCH + u < L) ? R::fetch(pnext + (StepT)u * stp) : R::kFetchNone;
+      pnext += (StepT)ENV_BATCH * stp;
       const int qe = min(L, q0 + ENV_BATCH);
 #pragma unroll 1
       for (int q = q0; q < qe; ++q) step(R::decode(s_raw[q - q0][threadIdx.x]), q);
@@ -406,13 +430,90 @@ __global__ void __launch_bounds__(ENV_THREADS, ENV_BATCH == ENV_BATCH_LONG ? 1 :
   // ---- backward sweep over the hull.  Parabola u at p (divided by w2) is G(u) - 2 p u + p^2:
   //   D(p) = (Gprev - Gcur) + 2 p (cur - prev) = -A + p * 2B   prev at least as good  <=>  D(p) <= 0
   //   val(p) = F(cur) + w2 (p - cur)^2
-  // output pointers walk backwards with p (element L-1 first)
-  float* __restrict__ out_f = reinterpret_cast<float*>(a.out) + base + (IdxT)(L - 1) * st;
-  int32_t* __restrict__ out_i = reinterpret_cast<int32_t*>(a.out) + base + (IdxT)(L - 1) * st;
-  int32_t* __restrict__ out_sq = a.out_sq + base + (IdxT)(L - 1) * st;
+  // output pointers walk backwards with p (element pstart first; L-1 when the thread owns the whole line)
+  int pstart = L - 1;
+  if constexpr (BANDS == 2) {
+    // ---- join the two chains of the line (see BANDS above).  Everything below is in the line's own frame
+    // (u = 0..Lfull-1, G(u) = F(u) + u^2); the upper band's entries are stored mirrored (u = Lfull-1 - t').
+    __shared__ int s_top[4][ENV_THREADS];
+    s_top[0][threadIdx.x] = t0;
+    s_top[1][threadIdx.x] = t1;
+    s_top[2][threadIdx.x] = (int)G0;
+    s_top[3][threadIdx.x] = (int)(G0 - A);  // G of t1 (unused when t1 is absent)
+    __syncthreads();
+    const int other = (int)threadIdx.x ^ LINES;
+    const int o0 = s_top[0][other];
+    if (t0 == EDT_NO_SITE) {
+      if (o0 != EDT_NO_SITE || !valid) return;  // the other band's thread fills the whole line
+      // no site on the line at all: each thread writes its own band (the no-site loop below)
+    } else if (o0 == EDT_NO_SITE) {
+      pstart = Lfull - 1;  // the whole line from this band's chain
+    } else {
+      const int o1 = s_top[1][other], oG0 = s_top[2][other], oG1 = s_top[3][other];
+      const int top = Lfull - 1;
+      // l / lb: top of the lower band's chain and the entry below it; r / rb: the same for the upper band
+      int l = band ? o0 : t0, lb = band ? o1 : t1;
+      int rm = band ? t0 : o0, rbm = band ? t1 : o1;  // mirrored indices of the upper band
+      int r = top - rm, rb = rbm == EDT_NO_SITE ? EDT_NO_SITE : top - rbm;
+      // G in the line's frame: the lower band's is stored as it is; the upper band's G' = F + t'^2
+      int32_t Gl = band ? oG0 : (int32_t)G0, Glb = band ? oG1 : (int32_t)(G0 - A);
+      const int32_t Grm = band ? (int32_t)G0 : oG0, Grbm = band ? (int32_t)(G0 - A) : oG1;
+      int32_t Gr = Grm - rm * rm + r * r, Grb = rb == EDT_NO_SITE ? 0 : Grbm - rbm * rbm + rb * rb;
+      const IdxT l0 = (IdxT)line0, sa = (IdxT)a.stride;
+      for (;;) {
+        bool moved = false;
+        // l is hidden by (lb, r)
+        while (lb != EDT_NO_SITE && (long long)(Gl - Glb) * (r - l) >= (long long)(Gr - Gl) * (l - lb)) {
+          l = lb;
+          Gl = Glb;
+          lb = (int)a.link[l0 + (IdxT)l * sa];
+          if (lb != EDT_NO_SITE) Glb = (int32_t)(R::load(a.in + (l0 + (IdxT)lb * sa)) + (uint32_t)(lb * lb));
+          moved = true;
+        }
+        // r is hidden by (l, rb)
+        while (rb != EDT_NO_SITE && (long long)(Gr - Gl) * (rb - r) >= (long long)(Grb - Gr) * (r - l)) {
+          r = rb;
+          Gr = Grb;
+          const int t = (int)a.link[l0 + (IdxT)r * sa];  // mirrored index of the entry below
+          rb = t == EDT_NO_SITE ? EDT_NO_SITE : top - t;
+          if (rb != EDT_NO_SITE) Grb = (int32_t)(R::load(a.in + (l0 + (IdxT)rb * sa)) + (uint32_t)(rb * rb));
+          moved = true;
+        }
+        if (!moved) break;
+      }
+      // l is at least as good as r at p  <=>  2 p (r - l) <= Gr - Gl: the lower band's thread fills p <= m,
+      // the upper band's thread p > m (ties go to l; the value is the same)
+      const int num = Gr - Gl, den = 2 * (r - l);
+      int m = num >= 0 ? num / den : -((den - 1 - num) / den);
+      m = max(-1, min(m, top));
+      if (band == 0) {
+        pstart = m;
+        t0 = l;
+        t1 = lb;
+        G0 = (GT)Gl;
+        if (lb != EDT_NO_SITE) {
+          A = (GT)(Gl - Glb);
+          Bb = H::idiff(l, lb);
+        }
+      } else {
+        pstart = top - (m + 1);
+        t0 = top - r;
+        t1 = rb == EDT_NO_SITE ? EDT_NO_SITE : top - rb;
+        G0 = (GT)(Gr - r * r + t0 * t0);
+        if (rb != EDT_NO_SITE) {
+          A = (GT)((int32_t)G0 - (Grb - rb * rb + t1 * t1));
+          Bb = H::idiff(t0, t1);
+        }
+      }
+      if (pstart < 0) return;
+    }
+  }
+  float* __restrict__ out_f = reinterpret_cast<float*>(a.out) + base + (StepT)pstart * stp;
+  int32_t* __restrict__ out_i = reinterpret_cast<int32_t*>(a.out) + base + (StepT)pstart * stp;
+  int32_t* __restrict__ out_sq = a.out_sq + base + (StepT)pstart * stp;
   if (t0 == EDT_NO_SITE) {  // no site on this line
 #pragma unroll 1
-    for (int p = L - 1; p >= 0; --p, out_i -= st, out_f -= st, out_sq -= st) {
+    for (int p = pstart; p >= 0; --p, out_i -= stp, out_f -= stp, out_sq -= stp) {
       if (OUT == EDT_OUT_I32) *out_i = EDT_INF_I32;
       if (OUT == EDT_OUT_F32 || (OUT == EDT_OUT_DIST && SQ != 2)) *out_f = INFINITY;
       if (OUT == EDT_OUT_DIST && SQ != 0) *out_sq = EDT_INF_I32;
@@ -439,11 +540,11 @@ __global__ void __launch_bounds__(ENV_THREADS, ENV_BATCH == ENV_BATCH_LONG ? 1 :
   WT D = 1, Dstep = 0, Gdiff = 1;
   int32_t val = 0, e = 0;
   double Fcur = 0.0, curd = 0.0;
-  double pd = u2d((uint32_t)(L - 1));
+  double pd = u2d((uint32_t)pstart);
   // float64 arithmetic decides which site owns p; the DISTANCE itself (EDT_OUT_DIST) is then evaluated
   // in float32 -- three roundings of 6e-8 before the square root and 1.2e-7 in it (MUFU), well inside
   // the 1e-6 contract of the anisotropic transform
-  float Fcurf = 0.f, curf = 0.f, pf = (float)(L - 1);
+  float Fcurf = 0.f, curf = 0.f, pf = (float)pstart;
   const float w2f = (float)w2;
   auto enter = [&](int p, GT Aa, BT Ba) {  // pair (prev, cur) at p;  Aa = Gcur - Gprev, Ba = cur - prev
     if (INT) {
@@ -469,9 +570,9 @@ __global__ void __launch_bounds__(ENV_THREADS, ENV_BATCH == ENV_BATCH_LONG ? 1 :
       }
     }
   };
-  enter(L - 1, A, Bb);
+  enter(pstart, A, Bb);
 #pragma unroll 4
-  for (int p = L - 1; p >= 0; --p, out_i -= st, out_f -= st, out_sq -= st) {
+  for (int p = pstart; p >= 0; --p, out_i -= stp, out_f -= stp, out_sq -= stp) {
     if (!INT) D = (WT)fma(pd, (double)Dstep, (double)Gdiff);
     if (D <= (WT)0) {
       do {  // move down the hull (D > 0 whenever prev does not exist)
@@ -546,21 +647,49 @@ static int launch_env(const TIn* in, void* link, void* out, int32_t* out_sq, int
   a.w2 = w2;
   a.out_scale = out_scale;
   a.out_mul = (float)sqrt(out_scale);
-  int64_t bx = (a.inner + ENV_THREADS - 1) / ENV_THREADS;
+  const bool small_idx = nz * nx * ny < (1ll << 32);
+  // two threads per line (BANDS of the kernel) where one per line leaves the machine under-filled: the all-integer
+  // x pass of a z-slab of a wide mosaic (16384 x 2048 x 25 per rank, 51 200 lines: 5.19 -> 3.79 ms measured; the
+  // 204 800 lines of a 2048 x 2048 x 100 stack fill the SMs already and measure the same either way, 1.39 / 1.40 ms).
+  // MFISH_EDT_BANDS=1 never / =2 wherever the instance exists (tests, A/B timing).
+  bool banded = false;
+  if constexpr (INT && std::is_same<TIn, uint16_t>::value) {
+    const int forced = [] {
+      const char* e = getenv("MFISH_EDT_BANDS");
+      return e ? atoi(e) : 0;
+    }();
+    const int64_t lines = a.inner * nouter;
+    banded = forced == 2 ? a.L >= 2 : (forced != 1 && a.L >= 512 && lines <= (int64_t)num_sms() * 1024);
+  }
+  const int lines_per_block = banded ? ENV_THREADS / 2 : ENV_THREADS;
+  int64_t bx = (a.inner + lines_per_block - 1) / lines_per_block;
   MFISH_REQUIRE(bx < (1ll << 31) && nouter < 65536, "edt: grid too large");
   dim3 grid((unsigned)bx, (unsigned)nouter);
   ProfScope prof(axis == MFISH_AXIS_Z ? "edt_envelope_z" : "edt_envelope_x", st);
-  const bool small_idx = nz * nx * ny < (1ll << 32);
-  if (a.L <= 256) {
+  if (banded) {
+    if constexpr (INT && std::is_same<TIn, uint16_t>::value) {
+      if (a.L <= 256) {
+        if (small_idx)
+          edt_envelope_kernel<TIn, LinkT, OUT, SQ, INT, uint32_t, ENV_BATCH_SHORT, 2><<<grid, ENV_THREADS, 0, st>>>(a);
+        else
+          edt_envelope_kernel<TIn, LinkT, OUT, SQ, INT, int64_t, ENV_BATCH_SHORT, 2><<<grid, ENV_THREADS, 0, st>>>(a);
+      } else {
+        if (small_idx)
+          edt_envelope_kernel<TIn, LinkT, OUT, SQ, INT, uint32_t, ENV_BATCH_LONG, 2><<<grid, ENV_THREADS, 0, st>>>(a);
+        else
+          edt_envelope_kernel<TIn, LinkT, OUT, SQ, INT, int64_t, ENV_BATCH_LONG, 2><<<grid, ENV_THREADS, 0, st>>>(a);
+      }
+    }
+  } else if (a.L <= 256) {
     if (small_idx)
-      edt_envelope_kernel<TIn, LinkT, OUT, SQ, INT, uint32_t, ENV_BATCH_SHORT><<<grid, ENV_THREADS, 0, st>>>(a);
+      edt_envelope_kernel<TIn, LinkT, OUT, SQ, INT, uint32_t, ENV_BATCH_SHORT, 1><<<grid, ENV_THREADS, 0, st>>>(a);
     else
-      edt_envelope_kernel<TIn, LinkT, OUT, SQ, INT, int64_t, ENV_BATCH_SHORT><<<grid, ENV_THREADS, 0, st>>>(a);
+      edt_envelope_kernel<TIn, LinkT, OUT, SQ, INT, int64_t, ENV_BATCH_SHORT, 1><<<grid, ENV_THREADS, 0, st>>>(a);
   } else {
     if (small_idx)
-      edt_envelope_kernel<TIn, LinkT, OUT, SQ, INT, uint32_t, ENV_BATCH_LONG><<<grid, ENV_THREADS, 0, st>>>(a);
+      edt_envelope_kernel<TIn, LinkT, OUT, SQ, INT, uint32_t, ENV_BATCH_LONG, 1><<<grid, ENV_THREADS, 0, st>>>(a);
     else
-      edt_envelope_kernel<TIn, LinkT, OUT, SQ, INT, int64_t, ENV_BATCH_LONG><<<grid, ENV_THREADS, 0, st>>>(a);
+      edt_envelope_kernel<TIn, LinkT, OUT, SQ, INT, int64_t, ENV_BATCH_LONG, 1><<<grid, ENV_THREADS, 0, st>>>(a);
   }
   count_launch(1);
   return check_launch("edt_envelope");

@@ -144,3 +144,74 @@ def test_golden_edt(golden):
     np.testing.assert_array_equal(sq, golden["edt_iso_sq"])
     dist = _edt_gpu(np.logical_not(nuc), ANISO)
     np.testing.assert_allclose(dist, golden["edt_aniso"], rtol=1e-6)
+
+
+def _inplane_sq(mask_xyz, bands):
+    """squared in-plane distances (passes 1 + 2) with the x pass on one / two threads per line (MFISH_EDT_BANDS)"""
+    import ctypes as C
+    import os
+    import torch
+    from muscle_fish_b200 import _lib as L, device as D
+    m = D.ingest(mask_xyz, as_mask=True)
+    nz, nx, ny = m.shape
+    ws = torch.empty(int(L.lib().mfish_edt_workspace_bytes(nz, nx, ny)), dtype=torch.uint8, device="cuda")
+    f2 = torch.empty((nz, nx, ny), dtype=torch.int32, device="cuda")
+    kind = C.c_int(-1)
+    old = os.environ.get("MFISH_EDT_BANDS")
+    os.environ["MFISH_EDT_BANDS"] = str(bands)
+    try:
+        L.check(L.lib().mfish_edt_inplane_u8(m.data_ptr(), nz, nx, ny, None, f2.data_ptr(), C.byref(kind),
+                                             ws.data_ptr(), D._stream()))
+        torch.cuda.synchronize()
+    finally:
+        if old is None:
+            del os.environ["MFISH_EDT_BANDS"]
+        else:
+            os.environ["MFISH_EDT_BANDS"] = old
+    assert kind.value == 0  # MFISH_EDT_F2_I32
+    return f2.permute(1, 2, 0).cpu().numpy()
+
+
+def _inplane_bruteforce(mask_xyz):
+    out = np.empty(mask_xyz.shape, np.int64)
+    for z in range(mask_xyz.shape[2]):
+        plane = mask_xyz[:, :, z]
+        out[:, :, z] = oracle.edt_bruteforce_sq(plane[:, :, None])[:, :, 0] if (plane == 0).any() else 2 ** 31 - 1
+    return out
+
+
+@pytest.mark.parametrize("nx", [2, 3, 4, 5, 9, 16, 33, 64, 130])
+@pytest.mark.parametrize("p_zero", [0.3, 0.02, 0.001])
+def test_banded_x_pass_equals_single_thread_lines_and_bruteforce(nx, p_zero):
+    """two threads per x line joined by the lower common tangent of their hulls (edt.cu, BANDS = 2)"""
+    mask = _random_mask((nx, 70, 3), p_zero, seed=nx * 7 + int(p_zero * 1000))
+    one = _inplane_sq(mask, 1)
+    two = _inplane_sq(mask, 2)
+    np.testing.assert_array_equal(two, one)
+    np.testing.assert_array_equal(two, _inplane_bruteforce(mask))
+
+
+def test_banded_x_pass_empty_bands_blobs_and_the_default_policy():
+    rng = np.random.default_rng(5)
+    # sites only in the lower / only in the upper half of x, none at all in one plane, one full plane
+    mask = np.ones((90, 40, 5), np.uint8)
+    mask[:40, :, 0] = rng.random((40, 40)) > 0.05
+    mask[50:, :, 1] = rng.random((40, 40)) > 0.05
+    mask[44:46, 10:12, 2] = 0
+    mask[:, :, 4] = 0
+    one = _inplane_sq(mask, 1)
+    two = _inplane_sq(mask, 2)
+    np.testing.assert_array_equal(two, one)
+    np.testing.assert_array_equal(two, _inplane_bruteforce(mask))
+    # smooth blobs (long pop runs, sparse hulls) on lines long enough for the default to pick the banded kernel
+    from muscle_fish_b200 import synth
+    st = synth.make_stack(shape=(1100, 96, 4), n_spots=5, n_nuclei=14, seed=11, nuc_semi=(60.0, 20.0, 3.0))
+    not_nuc = (st["nuc_mask"] == 0).astype(np.uint8)
+    one = _inplane_sq(not_nuc, 1)
+    two = _inplane_sq(not_nuc, 2)
+    dflt = _inplane_sq(not_nuc, 0)
+    np.testing.assert_array_equal(two, one)
+    np.testing.assert_array_equal(dflt, one)
+    # and the full transform (default policy) against scipy
+    ref = oracle.distance_transform_edt(not_nuc, sampling=ANISO)
+    np.testing.assert_allclose(_edt_gpu(not_nuc, ANISO), ref, rtol=1e-6)
