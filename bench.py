@@ -310,8 +310,16 @@ def bench_e2e(ctx, args, img, fiber, nuc, shape, nvox):
 
     steps = max(1, min(args.steps, args.e2e_steps))
     warm = max(1, min(args.warmup, 3))
-    dt, res = ctx.timed(fused, steps, warm)
-    h2d = int(h_img.numel() * 4 + h_fib.numel() + h_nuc.numel())
+    from muscle_fish_b200 import device as D
+
+    def counted(fn, nsteps, nwarm):
+        """ctx.timed + the bytes host_to_device_many queued per call (masks cross PCIe as bits: device.PackedMask)"""
+        b0 = D.H2D_BYTES
+        dt_, res_ = ctx.timed(fn, nsteps, nwarm)
+        return dt_, res_, int((D.H2D_BYTES - b0) // (nsteps + nwarm))
+
+    dt, res, h2d = counted(fused, steps, warm)
+    h2d_bytes_whole = int(h_img.numel() * 4 + h_fib.numel() + h_nuc.numel())
     # the ceiling the host side sets: the same three pinned buffers copied to the device and nothing else, every
     # rank at once (with N ranks on one host they share its memory system and PCIe root complexes)
     d_img = torch.empty(shape, dtype=torch.float32, device="cuda")
@@ -329,16 +337,19 @@ def bench_e2e(ctx, args, img, fiber, nuc, shape, nvox):
     h2d_only_ms = dtc / 3 * 1e3
     e2e = {"value": ctx.world * nvox * steps / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h_bytes(res), "steps": steps, "ms_per_step": dt / steps * 1e3,
-           "pcie_floor_ms": h2d / 55e9 * 1e3,
-           "h2d_only_ms_all_ranks_at_once": h2d_only_ms, "h2d_only_gbs_per_gpu": h2d / h2d_only_ms / 1e6,
+           "pcie_floor_ms": h2d / 55e9 * 1e3, "masks": "bit-packed by host threads inside the timed region"
+           if D.PACK_MASKS else "whole bytes",
+           "h2d_bytes_whole_byte_masks": h2d_bytes_whole,
+           "h2d_only_ms_all_ranks_at_once": h2d_only_ms,
+           "h2d_only_gbs_per_gpu": h2d_bytes_whole / h2d_only_ms / 1e6,
            "api": "muscle_fish.find_spots_snrfilter_with_distances (= find_spots_snrfilter + the EDT/interpn pair of "
                   "nocodazole/fish_analysis_noco.py:218-221,297-298 in one call): pinned host float32 (x,y,z) image "
                   "+ uint8 masks in, host float64 spots / table / distances out"}
     variants = {}
     vsteps = max(1, min(steps, 3))
-    dt2, res2 = ctx.timed(two_calls, vsteps, 1)
+    dt2, res2, hb2 = counted(two_calls, vsteps, 1)
     variants["two_reference_calls_f32_pinned"] = {
-        "value": ctx.world * nvox * vsteps / dt2 / 1e9, "ms_per_step": dt2 / vsteps * 1e3, "h2d_bytes_per_step": h2d,
+        "value": ctx.world * nvox * vsteps / dt2 / 1e9, "ms_per_step": dt2 / vsteps * 1e3, "h2d_bytes_per_step": hb2,
         "api": "muscle_fish.find_spots_snrfilter, then ndimage.spot_distances (round-1 e2e)",
         "same_spots_as_fused": bool(np.array_equal(res2[0], res[0]) and np.array_equal(res2[2], res[2]))}
     if not args.quick:
@@ -347,8 +358,7 @@ def bench_e2e(ctx, args, img, fiber, nuc, shape, nvox):
         u_img.copy_((img.permute(1, 2, 0) * 16.0).round().clamp(0, 65535).to(torch.uint16))
         torch.cuda.synchronize()
         au = u_img.numpy()
-        dt3, res3 = ctx.timed(lambda: fused(au), vsteps, 1)
-        hb = int(u_img.numel() * 2 + h_fib.numel() + h_nuc.numel())
+        dt3, res3, hb = counted(lambda: fused(au), vsteps, 1)
         variants["uint16_pinned"] = {"value": ctx.world * nvox * vsteps / dt3 / 1e9, "ms_per_step": dt3 / vsteps * 1e3,
                                      "h2d_bytes_per_step": hb, "pcie_floor_ms": hb / 55e9 * 1e3,
                                      "found_spots": int(len(res3[0])),
@@ -359,8 +369,7 @@ def bench_e2e(ctx, args, img, fiber, nuc, shape, nvox):
         p_img = a_img.astype(np.float64)
         p_fib = a_fib.astype(np.int64)
         p_nuc = a_nuc.astype(np.int64)
-        dt4, res4 = ctx.timed(lambda: fused(p_img, p_fib, p_nuc), 2, 1)
-        hb = int(p_img.nbytes + p_fib.nbytes + p_nuc.nbytes)
+        dt4, res4, hb = counted(lambda: fused(p_img, p_fib, p_nuc), 2, 1)
         variants["float64_int64_pageable"] = {
             "value": ctx.world * nvox * 2 / dt4 / 1e9, "ms_per_step": dt4 / 2 * 1e3, "h2d_bytes_per_step": hb,
             "same_spots_as_fused": bool(np.array_equal(res4[0], res[0])),

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MFISH_ABI_VERSION 5
+#define MFISH_ABI_VERSION 6
 
 #define MFISH_OK 0
 #define MFISH_ERR_INVALID (-1)
@@ -86,6 +86,21 @@ int64_t mfish_profile_collect(char* buf, int64_t cap);
  * the converted values into minmax_dev[0..1] (float).                      */
 int mfish_ingest(const void* src_dev, int src_dtype, int src_layout, int64_t nx, int64_t ny,
                  int64_t nz, void* dst_dev, int dst_kind, float* minmax_dev, void* stream);
+
+/* Masks over PCIe as bits.  The masks the reference passes (`mask=` of find_spots*, modules/muscle_fish.py:281,
+ * 631; the nucleus mask of nocodazole/fish_analysis_noco.py:218) carry one bit per voxel; the host-buffer path
+ * packs them on the host and expands them on the device instead of moving whole bytes.
+ *  mfish_mask_bits_bytes   size of the bit stream of n voxels (whole 32-bit words + one pad word)
+ *  mfish_host_pack_mask    HOST code (no CUDA call; thread-safe on disjoint ranges): bit i (LSB first inside a
+ *                          byte) of bits_host = (src_host[i] != 0) != negate, for n elements of src_dtype.
+ *                          Worker threads split a mask at multiples of 8 elements.
+ *  mfish_ingest_mask_bits  the packed stream of a C-ordered array in src_layout -> uint8 mask [nz][nx][ny]
+ *                          (dst_kind MFISH_DST_NONZERO / MFISH_DST_ISZERO), i.e. what mfish_ingest gives for
+ *                          the unpacked array.  bits_dev: 4-byte aligned, mfish_mask_bits_bytes long.        */
+int64_t mfish_mask_bits_bytes(int64_t n);
+int mfish_host_pack_mask(const void* src_host, int src_dtype, int64_t n, uint8_t* bits_host, int negate);
+int mfish_ingest_mask_bits(const void* bits_dev, int src_layout, int64_t nx, int64_t ny, int64_t nz,
+                           uint8_t* dst_dev, int dst_kind, void* stream);
 
 /* global min / max (np.min, np.max inside np.interp, scope_utils3.py:386) */
 int mfish_minmax_f32(const float* vol_dev, int64_t n, float* minmax_dev, void* stream);

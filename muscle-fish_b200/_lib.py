@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MFISH_LIB") or os.path.join(_HERE, "libmfish_sm100.so")
 
 # constants mirrored from include/mfish.h
-ABI_VERSION = 5
+ABI_VERSION = 6
 OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 U8, U16, I16, I32, I64, F32, F64 = range(7)
 LAYOUT_XYZ, LAYOUT_ZXY = 0, 1
@@ -43,6 +43,9 @@ SIGNATURES = {
     "mfish_profile_enable": (None, [_i]),
     "mfish_profile_collect": (_i64, [C.c_char_p, _i64]),
     "mfish_ingest": (_i, [_p, _i, _i, _i64, _i64, _i64, _p, _i, _p, _p]),
+    "mfish_mask_bits_bytes": (_i64, [_i64]),
+    "mfish_host_pack_mask": (_i, [_p, _i, _i64, _p, _i]),
+    "mfish_ingest_mask_bits": (_i, [_p, _i, _i64, _i64, _i64, _p, _i, _p]),
     "mfish_minmax_f32": (_i, [_p, _i64, _p, _p]),
     "mfish_normalize_f64": (_i, [_p, _i, _i64, _d, _d, _p, _p, _p]),
     "mfish_sepconv_f32": (_i, [_p, _p, _p, _p, _i64, _i64, _i64, _i, _p, _p, _i, _i, _i, _f, _p, _p]),

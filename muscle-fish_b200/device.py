@@ -119,11 +119,68 @@ def _stage_resources():
             ncpu = len(os.sched_getaffinity(0))
         except AttributeError:
             ncpu = os.cpu_count() or 1
-        nthreads = max(1, min(8, ncpu // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
+        nthreads = max(1, min(16, ncpu // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
         depth = nthreads + 2
         ring = [torch.empty(_STAGE_CHUNK_ELEMS * 4, dtype=torch.uint8).pin_memory() for _ in range(depth)]
         ent = _STAGE["pool"] = (ThreadPoolExecutor(nthreads), ring, [None] * depth)
     return ent
+
+
+# ---- masks as bits: a mask is one bit of information per voxel, and two whole-byte masks are a third of the PCIe
+# bytes of a float32 stack.  Worker threads pack "voxel != 0" (mfish_host_pack_mask, plain C in the library, the
+# GIL released) into pinned memory while the image is crossing PCIe; the device expands the bits straight into the
+# uint8 [z][x][y] layout (mfish_ingest_mask_bits).  MFISH_PACK_MASKS=0 sends whole bytes as before.
+PACK_MASKS = os.environ.get("MFISH_PACK_MASKS", "1") != "0"
+_PACK_MIN_ELEMS = 16 << 20
+_PACK_CHUNK_ELEMS = 4 << 20  # a multiple of 64
+_PACK_RING = 4
+_SPLIT_MIN_BYTES = 64 << 20  # a pinned array this large is sent in two halves around a pending packed mask
+H2D_BYTES = 0  # bytes queued for upload by host_to_device_many since import (bench.py reads differences)
+
+
+@dataclass
+class PackedMask:
+    """a mask on the device as the bit stream of its C-ordered host array (``ingest`` expands it)"""
+    bits: torch.Tensor  # uint8, mfish_mask_bits_bytes(n) long
+    shape: tuple
+
+
+def _packable(arr):
+    if isinstance(arr, torch.Tensor):
+        if arr.is_cuda or not arr.is_contiguous():
+            return None
+        arr = arr.view(torch.uint8).numpy() if arr.dtype == torch.bool else arr.numpy()
+    a = np.asarray(arr)
+    if a.dtype == np.bool_:
+        a = a.view(np.uint8)
+    if a.ndim != 3 or a.size < _PACK_MIN_ELEMS or not a.flags.c_contiguous or a.dtype not in _DTYPES:
+        return None
+    return a
+
+
+def _start_pack(a: np.ndarray):
+    """queue the packing of ``a`` on the worker threads -> (futures, pinned bits tensor, ring slot)"""
+    pool = _stage_resources()[0]
+    nbytes = int(L.lib().mfish_mask_bits_bytes(a.size))
+    ring = _STAGE.setdefault(("bits", nbytes), {"bufs": [], "events": [], "next": 0})
+    if len(ring["bufs"]) < _PACK_RING:
+        ring["bufs"].append(torch.zeros(nbytes, dtype=torch.uint8).pin_memory())
+        ring["events"].append(None)
+        slot = len(ring["bufs"]) - 1
+    else:
+        slot = ring["next"] % _PACK_RING
+        ring["next"] += 1
+        if ring["events"][slot] is not None:
+            ring["events"][slot].synchronize()  # the previous DMA out of this buffer has finished
+    buf = ring["bufs"][slot]
+    src, dst, code, esz = a.ctypes.data, buf.data_ptr(), _DTYPES[a.dtype], a.dtype.itemsize
+    fn = L.lib().mfish_host_pack_mask
+
+    def job(i0, n):
+        L.check(fn(src + i0 * esz, code, n, dst + i0 // 8, 0))
+
+    futs = [pool.submit(job, i0, min(_PACK_CHUNK_ELEMS, a.size - i0)) for i0 in range(0, a.size, _PACK_CHUNK_ELEMS)]
+    return futs, buf, (ring, slot), a
 
 
 def _upload_staged(a: np.ndarray, kind: str, cs, cur):
@@ -179,25 +236,65 @@ def _upload_staged(a: np.ndarray, kind: str, cs, cur):
     return dst, ev
 
 
-def host_to_device_many(arrs, kinds=None):
+def host_to_device_many(arrs, kinds=None, pack_masks=False):
     """Queue the H2D copies of several host arrays back to back on a side stream and return
     [(device tensor, ready event)], so that work on the first array overlaps the later copies
     (PCIe is the slow link of the host-buffer path).  Device / non-array inputs pass through.
     ``kinds`` (per array: "image" / "mask" / None) tells what the array is FOR: large pageable arrays of a known
     kind are narrowed on the host (float32 / 0-1 uint8: exactly what ``ingest`` makes of them) while they are
-    staged through pinned memory."""
+    staged through pinned memory.
+    ``pack_masks``: the caller hands every "mask" result to ``ingest`` (which expands a ``PackedMask``), so large
+    masks travel as bits.  All masks are packed by the worker threads from the start; a mask listed BEFORE a large
+    pinned array is sent between the two halves of that array (by then it is packed, and PCIe has not been idle),
+    the others after it."""
+    global H2D_BYTES
     _require_cuda()
     dev = torch.cuda.current_device()
     cur = torch.cuda.current_stream()
     cs = _COPY_STREAMS.get(dev)
     if cs is None:
         cs = _COPY_STREAMS[dev] = torch.cuda.Stream()
-    out = []
-    started = False
     kinds = list(kinds) if kinds is not None else [None] * len(arrs)
-    for arr, kind in zip(arrs, kinds):
+    out = [None] * len(arrs)
+    started = False
+
+    def start():
+        nonlocal started
+        if not started:
+            cs.wait_stream(cur)  # the blocks may have been in use by earlier compute work
+            started = True
+
+    jobs = {}
+    if pack_masks and PACK_MASKS:
+        for i, (arr, kind) in enumerate(zip(arrs, kinds)):
+            a = _packable(arr) if (kind == "mask" and arr is not None) else None
+            if a is not None:
+                jobs[i] = _start_pack(a)
+    pending = []
+
+    def flush():
+        global H2D_BYTES
+        for i in pending:
+            futs, buf, (ring, slot), a = jobs[i]
+            for f in futs:
+                f.result()
+            start()
+            dst = torch.empty(buf.shape, dtype=torch.uint8, device="cuda")
+            with torch.cuda.stream(cs):
+                dst.copy_(buf, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(cs)
+            ring["events"][slot] = ev
+            H2D_BYTES += buf.numel()
+            out[i] = (PackedMask(dst, tuple(a.shape)), ev)
+        pending.clear()
+
+    for i, (arr, kind) in enumerate(zip(arrs, kinds)):
+        if i in jobs:
+            pending.append(i)
+            continue
         if arr is None:
-            out.append((None, None))
+            out[i] = (None, None)
             continue
         if isinstance(arr, torch.Tensor):
             src = arr if arr.is_cuda else arr.contiguous()
@@ -205,10 +302,12 @@ def host_to_device_many(arrs, kinds=None):
             a = np.asarray(arr)
             if (kind in ("image", "mask") and a.ndim == 3 and a.nbytes >= _STAGE_MIN_BYTES and a.dtype in _DTYPES
                     and STAGED_UPLOADS and not _is_pinned(a)):
+                flush()
+                start()
                 staged = _upload_staged(a, kind, cs, cur)
                 if staged is not None:
-                    started = True
-                    out.append(staged)
+                    H2D_BYTES += staged[0].numel() * staged[0].element_size()
+                    out[i] = staged
                     continue
             if a.dtype == np.bool_:
                 a = a.view(np.uint8)
@@ -222,21 +321,31 @@ def host_to_device_many(arrs, kinds=None):
         if src.dtype == torch.bool:
             src = src.view(torch.uint8)
         if src.is_cuda:
-            out.append((src.contiguous(), None))
+            out[i] = (src.contiguous(), None)
             continue
+        H2D_BYTES += src.numel() * src.element_size()
         if not src.is_pinned():
             # pageable memory: the driver stages the copy synchronously anyway
-            out.append((src.to("cuda"), None))
+            flush()
+            out[i] = (src.to("cuda"), None)
             continue
         dst = torch.empty(src.shape, dtype=src.dtype, device="cuda")  # owned by the compute stream
-        if not started:
-            cs.wait_stream(cur)  # the block may have been in use by earlier compute work
-            started = True
+        start()
+        half = src.shape[0] // 2 if (pending and src.dim() >= 1 and src.numel() * src.element_size() >= _SPLIT_MIN_BYTES) else 0
         with torch.cuda.stream(cs):
-            dst.copy_(src, non_blocking=True)
+            if half:
+                dst[:half].copy_(src[:half], non_blocking=True)
+            else:
+                dst.copy_(src, non_blocking=True)
+        if half:
+            flush()  # waits for the packing (a few ms; the first half keeps PCIe busy), queues the bits
+            with torch.cuda.stream(cs):
+                dst[half:].copy_(src[half:], non_blocking=True)
+        with torch.cuda.stream(cs):
             ev = torch.cuda.Event()
             ev.record(cs)
-        out.append((dst, ev))
+        out[i] = (dst, ev)
+    flush()
     return out
 
 
@@ -268,6 +377,22 @@ def ingest(src, z_first=False, as_mask=False, want_minmax=True, negate=False, re
     """Host/device array in reference order (x,y,z) [or (z,x,y) when ``z_first``]
     -> device layout.  Returns ``Volume`` (float32 + minmax) or a uint8 mask tensor.
     ``ready``: event of an asynchronous copy of ``src`` (see ``host_to_device_many``)."""
+    if isinstance(src, PackedMask):
+        if not as_mask:
+            raise TypeError("a bit-packed array is a mask: ingest(..., as_mask=True)")
+        if ready is not None:
+            torch.cuda.current_stream().wait_event(ready)
+            src.bits.record_stream(torch.cuda.current_stream())
+        if len(src.shape) != 3:
+            raise ValueError("expected a 3-D volume, got shape %r" % (tuple(src.shape),))
+        if z_first:
+            nz, nx, ny = src.shape
+        else:
+            nx, ny, nz = src.shape
+        out = torch.empty((nz, nx, ny), dtype=torch.uint8, device=src.bits.device)
+        L.check(L.lib().mfish_ingest_mask_bits(src.bits.data_ptr(), L.LAYOUT_ZXY if z_first else L.LAYOUT_XYZ, nx, ny, nz,
+                                               out.data_ptr(), L.DST_ISZERO if negate else L.DST_NONZERO, _stream()))
+        return out
     t = host_to_device(src)
     if ready is not None:
         torch.cuda.current_stream().wait_event(ready)
@@ -1170,7 +1295,7 @@ def analyze_host(img_fish, fiber_mask, region_nuc, sigma=2.0, t_spot=0.025, samp
     t = timer or _NoTimer()
     fiber_dev = MASK_HANDOFF.lookup(fiber_mask, z_first)  # a mask this package returned: already on the device
     (tn, en), (ti, ei), (tf, ef) = host_to_device_many([region_nuc, img_fish, None if fiber_dev is not None else fiber_mask],
-                                                       kinds=("mask", "image", "mask"))
+                                                       kinds=("mask", "image", "mask"), pack_masks=True)
     main = torch.cuda.current_stream()
     side = _side_stream()
     side.wait_stream(main)

@@ -42,9 +42,9 @@ def _prep(img_fish, mask, z_first):
     mdev = D.MASK_HANDOFF.lookup(mask, z_first)  # the same for a mask (threshold_fiber's result)
     up_mask = None if mdev is not None else mask
     if vol is not None:
-        (tm, em), = D.host_to_device_many([up_mask], kinds=("mask",))
+        (tm, em), = D.host_to_device_many([up_mask], kinds=("mask",), pack_masks=True)
     else:
-        (ti, ei), (tm, em) = D.host_to_device_many([img_fish, up_mask], kinds=("image", "mask"))
+        (ti, ei), (tm, em) = D.host_to_device_many([img_fish, up_mask], kinds=("image", "mask"), pack_masks=True)
         vol = D.ingest(ti, z_first=z_first, ready=ei)
     m = _Lazy(tm, em, z_first, vol.data.shape, ready=mdev) if mask is not None else None
     return vol, m

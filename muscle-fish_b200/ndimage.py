@@ -49,7 +49,8 @@ def spot_distances(region_nuc, spots, dims_xyz):
     ``distance_transform_edt(np.logical_not(region_nuc), sampling=dims)`` + ``interpn`` pair of
     nocodazole/fish_analysis_noco.py:218-221,297-298 without the dense map leaving the GPU."""
     a = np.asarray(region_nuc)
-    not_nuc = D.ingest(a, as_mask=True, negate=True)
+    (tn, en), = D.host_to_device_many([a], kinds=("mask",), pack_masks=True)  # a large mask crosses PCIe as bits
+    not_nuc = D.ingest(tn, as_mask=True, negate=True, ready=en)
     dist = D.edt(not_nuc, _sampling3(dims_xyz))
     return D.gather(dist, np.asarray(spots)).astype(np.float64)
 

@@ -226,3 +226,52 @@ def test_mask_handoff_from_threshold_fiber():
     n2 = sg.threshold_nuclei(st["img"], fiber_mask=plain)
     np.testing.assert_array_equal(n1, n2)
     assert D.MASK_HANDOFF.hits >= h0 + 4
+
+
+def test_masks_as_bits_equal_whole_byte_masks(monkeypatch):
+    """mfish_host_pack_mask + mfish_ingest_mask_bits against mfish_ingest on the whole-byte mask (every dtype the
+    reference's callers pass, both layouts, both polarities, ragged sizes), and the host-buffer entry with packed
+    masks against the same call with MFISH_PACK_MASKS off."""
+    import torch
+    from muscle_fish_b200 import device as D, muscle_fish as mf, synth
+    monkeypatch.setattr(D, "_PACK_MIN_ELEMS", 0)
+    monkeypatch.setattr(D, "_PACK_CHUNK_ELEMS", 1 << 12)
+    monkeypatch.setattr(D, "_SPLIT_MIN_BYTES", 0)
+    rng = np.random.default_rng(8)
+    for shape in [(40, 36, 21), (33, 17, 100), (8, 64, 32), (5, 3, 1), (64, 8, 77)]:
+        for dt in (np.uint8, np.bool_, np.int64, np.float64, np.uint16):
+            m = (rng.random(shape) < 0.3).astype(dt)
+            if dt not in (np.bool_,):
+                m = m * 3
+            for z_first in (False, True):
+                for negate in (False, True):
+                    (t, e), = D.host_to_device_many([m], kinds=("mask",), pack_masks=True)
+                    assert isinstance(t, D.PackedMask) and e is not None
+                    got = D.ingest(t, z_first=z_first, as_mask=True, negate=negate, ready=e)
+                    ref = D.ingest(m, z_first=z_first, as_mask=True, negate=negate)
+                    assert torch.equal(got, ref), (shape, dt, z_first, negate)
+    # two masks and a pinned image in one call: the first mask is sent between the halves of the image
+    img = torch.from_numpy(rng.random((64, 48, 20)).astype(np.float32)).pin_memory()
+    m1 = (rng.random((64, 48, 20)) < 0.5).astype(np.uint8)
+    m2 = (rng.random((64, 48, 20)) < 0.5).astype(np.uint8)
+    (a, ea), (b, eb), (c, ec) = D.host_to_device_many([m1, img.numpy(), m2], kinds=("mask", "image", "mask"),
+                                                      pack_masks=True)
+    for e in (ea, eb, ec):
+        torch.cuda.current_stream().wait_event(e)
+    assert torch.equal(b.cpu(), img)
+    assert torch.equal(D.ingest(a, as_mask=True), D.ingest(m1, as_mask=True))
+    assert torch.equal(D.ingest(c, as_mask=True), D.ingest(m2, as_mask=True))
+    st = synth.make_config("small")
+    args = (st["img"], st["nuc_mask"], ANISO)
+    kw = dict(sigma=2.0, t_spot=0.025, mask=st["fiber_mask"])
+    before = D.H2D_BYTES
+    a = mf.find_spots_snrfilter_with_distances(*args, **kw)
+    packed_bytes = D.H2D_BYTES - before
+    monkeypatch.setattr(D, "PACK_MASKS", False)
+    before = D.H2D_BYTES
+    b = mf.find_spots_snrfilter_with_distances(*args, **kw)
+    assert packed_bytes < D.H2D_BYTES - before
+    np.testing.assert_array_equal(a[0], b[0])
+    assert a[1] == b[1]
+    np.testing.assert_array_equal(a[2], b[2])
+    assert len(a[0]) > 20

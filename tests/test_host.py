@@ -196,3 +196,30 @@ def test_slab_generators_draw_the_voxels_of_the_whole_stack():
             assert torch.equal(part[k], full[k][:, x0:x1]), (k, x0)
     again = synth.make_stack_device(shape, ns, nn, seed, device="cpu")
     assert torch.equal(again["img"], full["img"])
+
+
+def test_host_mask_packer_equals_numpy_packbits():
+    """mfish_host_pack_mask is plain host code (no CUDA call): every dtype, ragged lengths, both polarities, and
+    the split into chunks the worker threads use"""
+    from muscle_fish_b200 import _lib
+    lib = _lib.lib()
+    rng = np.random.default_rng(0)
+    for dt, code in ((np.uint8, _lib.U8), (np.uint16, _lib.U16), (np.int16, _lib.I16), (np.int32, _lib.I32),
+                     (np.int64, _lib.I64), (np.float32, _lib.F32), (np.float64, _lib.F64)):
+        for n in (0, 1, 7, 8, 63, 64, 65, 1000, 4099):
+            a = (rng.random(n) < 0.3).astype(dt) * 3
+            nb = int(lib.mfish_mask_bits_bytes(n))
+            assert nb == (0 if n == 0 else ((n + 31) // 32 + 1) * 4)
+            out = np.full(max(nb, 1), 0xAA, np.uint8)
+            for neg in (0, 1):
+                _lib.check(lib.mfish_host_pack_mask(a.ctypes.data, code, n, out.ctypes.data, neg))
+                ref = np.packbits((a != 0) != bool(neg), bitorder="little")
+                np.testing.assert_array_equal(out[:len(ref)], ref)
+    a = (rng.random(100_000) < 0.5).astype(np.uint8)
+    out = np.zeros(int(lib.mfish_mask_bits_bytes(a.size)), np.uint8)
+    for i0 in range(0, a.size, 4096):  # chunk starts are multiples of 8 elements
+        n = min(4096, a.size - i0)
+        _lib.check(lib.mfish_host_pack_mask(a.ctypes.data + i0, _lib.U8, n, out.ctypes.data + i0 // 8, 0))
+    np.testing.assert_array_equal(out[:a.size // 8], np.packbits(a, bitorder="little"))
+    assert lib.mfish_host_pack_mask(None, _lib.U8, 8, out.ctypes.data, 0) == _lib.ERR_INVALID
+    assert lib.mfish_host_pack_mask(a.ctypes.data, 99, 8, out.ctypes.data, 0) == _lib.ERR_UNSUPPORTED
