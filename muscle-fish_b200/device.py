@@ -145,7 +145,7 @@ class PackedMask:
     shape: tuple
 
 
-def _packable(arr):
+def _packable(arr, min_elems=None):
     if isinstance(arr, torch.Tensor):
         if arr.is_cuda or not arr.is_contiguous():
             return None
@@ -153,14 +153,32 @@ def _packable(arr):
     a = np.asarray(arr)
     if a.dtype == np.bool_:
         a = a.view(np.uint8)
-    if a.ndim != 3 or a.size < _PACK_MIN_ELEMS or not a.flags.c_contiguous or a.dtype not in _DTYPES:
+    if a.ndim != 3 or a.size < (_PACK_MIN_ELEMS if min_elems is None else min_elems) or not a.flags.c_contiguous \
+            or a.dtype not in _DTYPES:
         return None
     return a
 
 
+def _packable_any_size(arr):
+    """``_packable`` without the size threshold (run_batch packs every stack's masks)"""
+    return _packable(arr, min_elems=0)
+
+
+def pack_into(a: np.ndarray, bits: torch.Tensor):
+    """queue the packing of the C-contiguous mask ``a`` into the (pinned) uint8 tensor ``bits`` on the worker
+    threads -> futures"""
+    pool = _stage_resources()[0]
+    src, dst, code, esz = a.ctypes.data, bits.data_ptr(), _DTYPES[a.dtype], a.dtype.itemsize
+    fn = L.lib().mfish_host_pack_mask
+
+    def job(i0, n):
+        L.check(fn(src + i0 * esz, code, n, dst + i0 // 8, 0))
+
+    return [pool.submit(job, i0, min(_PACK_CHUNK_ELEMS, a.size - i0)) for i0 in range(0, a.size, _PACK_CHUNK_ELEMS)]
+
+
 def _start_pack(a: np.ndarray):
     """queue the packing of ``a`` on the worker threads -> (futures, pinned bits tensor, ring slot)"""
-    pool = _stage_resources()[0]
     nbytes = int(L.lib().mfish_mask_bits_bytes(a.size))
     ring = _STAGE.setdefault(("bits", nbytes), {"bufs": [], "events": [], "next": 0})
     if len(ring["bufs"]) < _PACK_RING:
@@ -173,14 +191,7 @@ def _start_pack(a: np.ndarray):
         if ring["events"][slot] is not None:
             ring["events"][slot].synchronize()  # the previous DMA out of this buffer has finished
     buf = ring["bufs"][slot]
-    src, dst, code, esz = a.ctypes.data, buf.data_ptr(), _DTYPES[a.dtype], a.dtype.itemsize
-    fn = L.lib().mfish_host_pack_mask
-
-    def job(i0, n):
-        L.check(fn(src + i0 * esz, code, n, dst + i0 // 8, 0))
-
-    futs = [pool.submit(job, i0, min(_PACK_CHUNK_ELEMS, a.size - i0)) for i0 in range(0, a.size, _PACK_CHUNK_ELEMS)]
-    return futs, buf, (ring, slot), a
+    return pack_into(a, buf), buf, (ring, slot), a
 
 
 def _upload_staged(a: np.ndarray, kind: str, cs, cur):
@@ -295,6 +306,9 @@ def host_to_device_many(arrs, kinds=None, pack_masks=False):
             continue
         if arr is None:
             out[i] = (None, None)
+            continue
+        if isinstance(arr, PackedMask):  # already on the device as bits (parallel.run_batch)
+            out[i] = (arr, None)
             continue
         if isinstance(arr, torch.Tensor):
             src = arr if arr.is_cuda else arr.contiguous()

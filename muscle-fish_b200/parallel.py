@@ -191,6 +191,14 @@ class _StagingSlot:
         self.nuc_d = torch.empty(shape_xyz, dtype=torch.uint8, device=device)
         self.copied = torch.cuda.Event()
         self.bytes = sum(t.numel() * t.element_size() for t in (self.img_h, self.fib_h, self.nuc_h))
+        # the masks cross PCIe as bits (device.PackedMask): pinned bit streams + their landing buffers
+        from . import _lib as L
+        nbits = int(L.lib().mfish_mask_bits_bytes(int(np.prod(shape_xyz))))
+        self.fib_bits_h = torch.zeros(nbits, dtype=torch.uint8).pin_memory()
+        self.nuc_bits_h = torch.zeros(nbits, dtype=torch.uint8).pin_memory()
+        self.fib_bits_d = torch.empty(nbits, dtype=torch.uint8, device=device)
+        self.nuc_bits_d = torch.empty(nbits, dtype=torch.uint8, device=device)
+        self.packed = False
 
     def host_views(self):
         return self.img_h.numpy(), self.fib_h.numpy(), self.nuc_h.numpy()
@@ -233,6 +241,19 @@ def run_batch(n_stacks: int, loader, shape_xyz, img_dtype=torch.uint16, sigma=2.
             # filling the staging views; those buffers are then uploaded as they are
             slot.src = (slot.img_h, slot.fib_h, slot.nuc_h) if ret is None else tuple(
                 t if isinstance(t, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(t)) for t in ret)
+            # one bit per mask voxel over PCIe: packed here, by the worker threads of the upload path, while the
+            # previous stack is crossing PCIe / being analysed
+            slot.packed = False
+            if D.PACK_MASKS:
+                pairs = [(slot.src[1], slot.fib_bits_h), (slot.src[2], slot.nuc_bits_h)]
+                arrs = [D._packable_any_size(m) for m, _ in pairs]
+                if all(a is not None and a.size == slot.fib_h.numel() for a in arrs):
+                    futs = []
+                    for a, (_, bits) in zip(arrs, pairs):
+                        futs += D.pack_into(a, bits)
+                    for f in futs:
+                        f.result()
+                    slot.packed = True
         except BaseException as e:  # surfaced in the main thread
             errors.append(e)
 
@@ -247,9 +268,15 @@ def run_batch(n_stacks: int, loader, shape_xyz, img_dtype=torch.uint16, sigma=2.
         copy_stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(copy_stream):
             img_h, fib_h, nuc_h = s.src
-            s.nuc_d.copy_(nuc_h, non_blocking=True)  # the distance transform starts first
-            s.img_d.copy_(img_h, non_blocking=True)
-            s.fib_d.copy_(fib_h, non_blocking=True)
+            if s.packed:
+                s.nuc_bits_d.copy_(s.nuc_bits_h, non_blocking=True)  # the distance transform starts first
+                s.img_d.copy_(img_h, non_blocking=True)
+                s.fib_bits_d.copy_(s.fib_bits_h, non_blocking=True)
+            else:
+                s.nuc_d.copy_(nuc_h, non_blocking=True)
+                s.img_d.copy_(img_h, non_blocking=True)
+                s.fib_d.copy_(fib_h, non_blocking=True)
+            s.uploaded_packed = s.packed
             s.copied.record(copy_stream)
 
     results = []
@@ -271,7 +298,12 @@ def run_batch(n_stacks: int, loader, shape_xyz, img_dtype=torch.uint16, sigma=2.
             pending = start_fill(k + 2)
         s = slots[k % 2]
         torch.cuda.current_stream().wait_event(s.copied)
-        res = D.analyze_host(s.img_d, s.fib_d, s.nuc_d, sigma=sigma, t_spot=t_spot, sampling_xyz=sampling_xyz,
+        if s.uploaded_packed:
+            fib_in = D.PackedMask(s.fib_bits_d, tuple(shape_xyz))
+            nuc_in = D.PackedMask(s.nuc_bits_d, tuple(shape_xyz))
+        else:
+            fib_in, nuc_in = s.fib_d, s.nuc_d
+        res = D.analyze_host(s.img_d, fib_in, nuc_in, sigma=sigma, t_spot=t_spot, sampling_xyz=sampling_xyz,
                              snr=snr)
         res.pop("dist", None)  # the dense map stays a per-stack temporary
         results.append((index, res))
