@@ -409,10 +409,11 @@ def bench_batch(ctx, args):
     dt, res = ctx.timed(once, 1, 1)
     nvox = float(np.prod(shape))
     from muscle_fish_b200 import _lib as L, device as D
-    per_stack = int(nvox) * 2 + (2 * int(L.lib().mfish_mask_bits_bytes(int(nvox))) if D.PACK_MASKS else 2 * int(nvox))
+    packed = D.PACK_MASKS
+    per_stack = int(nvox) * 2 + (2 * int(L.lib().mfish_mask_bits_bytes(int(nvox))) if packed else 2 * int(nvox))
     return {"workload": f"configs[2]: {n_stacks} stacks {shape[0]}x{shape[1]}x{shape[2]} (uint16 image + two uint8 masks "
-                        f"per stack in pinned host memory; the masks cross PCIe as bits, packed by host threads inside the "
-                        f"timed region), every {ctx.world}-th stack per GPU, parallel.run_batch",
+                        f"per stack in pinned host memory{'; the masks cross PCIe as bits, packed by host threads inside the timed region' if packed else ''}), "
+                        f"every {ctx.world}-th stack per GPU, parallel.run_batch",
             "n_stacks": n_stacks, "stacks_this_rank": len(res), "value": n_stacks * nvox / dt / 1e9, "unit": UNIT,
             "ms_total": dt * 1e3, "ms_per_stack_per_gpu": dt * 1e3 / max(1, len(res)),
             "h2d_bytes_per_stack": per_stack, "pcie_floor_ms_per_stack": per_stack / 55e9 * 1e3,

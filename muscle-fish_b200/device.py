@@ -129,12 +129,19 @@ def _stage_resources():
 # ---- masks as bits: a mask is one bit of information per voxel, and two whole-byte masks are a third of the PCIe
 # bytes of a float32 stack.  Worker threads pack "voxel != 0" (mfish_host_pack_mask, plain C in the library, the
 # GIL released) into pinned memory while the image is crossing PCIe; the device expands the bits straight into the
-# uint8 [z][x][y] layout (mfish_ingest_mask_bits).  MFISH_PACK_MASKS=0 sends whole bytes as before.
-PACK_MASKS = os.environ.get("MFISH_PACK_MASKS", "1") != "0"
+# uint8 [z][x][y] layout (mfish_ingest_mask_bits).  This pays where PCIe is the limit: one or two processes on the
+# host (C2 host-buffer step 52.8 -> 44.3 ms).  With four or eight ranks the host's memory system is the limit
+# (8 x 2.5 GB of pinned copies at once run at 23 GB/s per GPU), and the packing threads' reads
+# of the masks add to its load: measured at 4 ranks, 66.9 ms against ~57 ms expected from whole-byte copies, the
+# batch 7.22 against 6.83 ms per stack.  Default: bits with at most two ranks per host, whole bytes beyond;
+# MFISH_PACK_MASKS=1 / 0 forces either.
+_pack_env = os.environ.get("MFISH_PACK_MASKS")
+PACK_MASKS = (_pack_env != "0") if _pack_env is not None else int(os.environ.get("LOCAL_WORLD_SIZE", "1")) <= 2
 _PACK_MIN_ELEMS = 16 << 20
 _PACK_CHUNK_ELEMS = 4 << 20  # a multiple of 64
 _PACK_RING = 4
-_SPLIT_MIN_BYTES = 64 << 20  # a pinned array this large is sent in two halves around a pending packed mask
+_SPLIT_MIN_BYTES = 64 << 20  # a pinned array this large is sent in pieces, a pending packed mask between them
+_SPLIT_PIECES = 4
 H2D_BYTES = 0  # bytes queued for upload by host_to_device_many since import (bench.py reads differences)
 
 
@@ -256,7 +263,7 @@ def host_to_device_many(arrs, kinds=None, pack_masks=False):
     staged through pinned memory.
     ``pack_masks``: the caller hands every "mask" result to ``ingest`` (which expands a ``PackedMask``), so large
     masks travel as bits.  All masks are packed by the worker threads from the start; a mask listed BEFORE a large
-    pinned array is sent between the two halves of that array (by then it is packed, and PCIe has not been idle),
+    pinned array is sent between the pieces of that array, as soon as it is packed (PCIe is never left idle),
     the others after it."""
     global H2D_BYTES
     _require_cuda()
@@ -283,10 +290,12 @@ def host_to_device_many(arrs, kinds=None, pack_masks=False):
                 jobs[i] = _start_pack(a)
     pending = []
 
-    def flush():
+    def flush(only_finished=False):
         global H2D_BYTES
-        for i in pending:
+        for i in list(pending):
             futs, buf, (ring, slot), a = jobs[i]
+            if only_finished and not all(f.done() for f in futs):
+                break  # masks keep their order
             for f in futs:
                 f.result()
             start()
@@ -298,7 +307,7 @@ def host_to_device_many(arrs, kinds=None, pack_masks=False):
             ring["events"][slot] = ev
             H2D_BYTES += buf.numel()
             out[i] = (PackedMask(dst, tuple(a.shape)), ev)
-        pending.clear()
+            pending.remove(i)
 
     for i, (arr, kind) in enumerate(zip(arrs, kinds)):
         if i in jobs:
@@ -345,16 +354,36 @@ def host_to_device_many(arrs, kinds=None, pack_masks=False):
             continue
         dst = torch.empty(src.shape, dtype=src.dtype, device="cuda")  # owned by the compute stream
         start()
-        half = src.shape[0] // 2 if (pending and src.dim() >= 1 and src.numel() * src.element_size() >= _SPLIT_MIN_BYTES) else 0
-        with torch.cuda.stream(cs):
-            if half:
-                dst[:half].copy_(src[:half], non_blocking=True)
-            else:
-                dst.copy_(src, non_blocking=True)
-        if half:
-            flush()  # waits for the packing (a few ms; the first half keeps PCIe busy), queues the bits
+        pieces = _SPLIT_PIECES if (pending and src.dim() >= 1 and src.shape[0] >= _SPLIT_PIECES
+                                   and src.numel() * src.element_size() >= _SPLIT_MIN_BYTES) else 1
+        if pieces == 1:
             with torch.cuda.stream(cs):
-                dst[half:].copy_(src[half:], non_blocking=True)
+                dst.copy_(src, non_blocking=True)
+        else:
+            # The array goes in pieces, one piece queued ahead of the one in flight, so PCIe never idles; a mask
+            # listed before it is queued the moment its packing is finished (checked while waiting for the DMA
+            # to move on), i.e. behind at most two pieces -- its consumer (the distance transform) then runs
+            # under the rest of the upload.  A mask that is still being packed when the last piece is queued
+            # (a host whose memory system is shared by eight ranks) follows the array instead of stalling it.
+            import time
+            bounds = [src.shape[0] * k // pieces for k in range(pieces + 1)]
+            done_ev = []
+
+            def queue_piece(k):
+                with torch.cuda.stream(cs):
+                    dst[bounds[k]:bounds[k + 1]].copy_(src[bounds[k]:bounds[k + 1]], non_blocking=True)
+                    e = torch.cuda.Event()
+                    e.record(cs)
+                done_ev.append(e)
+
+            queue_piece(0)
+            queue_piece(1)
+            for k in range(2, pieces):
+                while not done_ev[k - 2].query():
+                    flush(only_finished=True)
+                    time.sleep(1e-4)
+                flush(only_finished=True)
+                queue_piece(k)
         with torch.cuda.stream(cs):
             ev = torch.cuda.Event()
             ev.record(cs)

@@ -232,6 +232,7 @@ def run_batch(n_stacks: int, loader, shape_xyz, img_dtype=torch.uint16, sigma=2.
         slots = _STAGING[skey] = [_StagingSlot(tuple(shape_xyz), img_dtype, dev) for _ in range(2)]
     copy_stream = _STAGING.setdefault(("stream", str(dev)), torch.cuda.Stream())
     errors = []
+    pack_masks = D.PACK_MASKS  # bits with at most two ranks per host, whole bytes beyond (see device.PACK_MASKS)
 
     def fill(slot, index):
         try:
@@ -244,7 +245,7 @@ def run_batch(n_stacks: int, loader, shape_xyz, img_dtype=torch.uint16, sigma=2.
             # one bit per mask voxel over PCIe: packed here, by the worker threads of the upload path, while the
             # previous stack is crossing PCIe / being analysed
             slot.packed = False
-            if D.PACK_MASKS:
+            if pack_masks:
                 pairs = [(slot.src[1], slot.fib_bits_h), (slot.src[2], slot.nuc_bits_h)]
                 arrs = [D._packable_any_size(m) for m, _ in pairs]
                 if all(a is not None and a.size == slot.fib_h.numel() for a in arrs):
