@@ -258,3 +258,27 @@ def test_oracle_label_and_fade_reproduce_golden():
     np.testing.assert_array_equal(lab2, nuc_lab)
     for i in range(n2):
         np.testing.assert_allclose(ref_fade.nucleus_fade(nuc_lab, i), g[f"fade_{i}"], rtol=0, atol=1e-7)
+
+
+def test_two_band_envelope_model_equals_bruteforce():
+    """the specification of the banded x pass of the EDT (oracle.ref_edt.two_band_envelope; csrc/edt.cu BANDS = 2):
+    mirrored bands joined by the lower common tangent give the plain lower envelope, on random, sparse, dense,
+    one-sided and empty lines"""
+    import random
+    from oracle.ref_edt import two_band_envelope
+    rnd = random.Random(3)
+    for _ in range(3000):
+        L = rnd.choice([1, 2, 3, 4, 5, 7, 8, 16, 33, 64, 100])
+        dens = rnd.choice([0.0, 0.05, 0.3, 0.9, 1.0])
+        mx = rnd.choice([1, 3, 10, 50, 2000])
+        mode = rnd.randrange(4)
+        F = []
+        for u in range(L):
+            if rnd.random() < dens and not (mode == 3 and u >= L // 2):
+                d = rnd.randrange(mx) if mode in (0, 3) else (abs(u - L // 3) * 2 if mode == 1 else rnd.choice([0, mx]))
+                F.append(d * d)
+            else:
+                F.append(None)
+        sites = [(u, f) for u, f in enumerate(F) if f is not None]
+        want = [min(f + (p - u) ** 2 for u, f in sites) for p in range(L)] if sites else [None] * L
+        assert two_band_envelope(F) == want, F
