@@ -140,6 +140,7 @@ PACK_MASKS = (_pack_env != "0") if _pack_env is not None else int(os.environ.get
 _PACK_MIN_ELEMS = 16 << 20
 _PACK_CHUNK_ELEMS = 4 << 20  # a multiple of 64
 _PACK_RING = 4
+_PACK_SIZES_KEPT = 3
 _SPLIT_MIN_BYTES = 64 << 20  # a pinned array this large is sent in pieces, a pending packed mask between them
 _SPLIT_PIECES = 4
 H2D_BYTES = 0  # bytes queued for upload by host_to_device_many since import (bench.py reads differences)
@@ -187,7 +188,19 @@ def pack_into(a: np.ndarray, bits: torch.Tensor):
 def _start_pack(a: np.ndarray):
     """queue the packing of ``a`` on the worker threads -> (futures, pinned bits tensor, ring slot)"""
     nbytes = int(L.lib().mfish_mask_bits_bytes(a.size))
-    ring = _STAGE.setdefault(("bits", nbytes), {"bufs": [], "events": [], "next": 0})
+    key = ("bits", nbytes)
+    ring = _STAGE.get(key)
+    if ring is None:
+        ring = _STAGE[key] = {"bufs": [], "events": [], "next": 0}
+        # pinned rings are kept for the few most recent stack sizes only (a long-running caller with stacks of many
+        # shapes must not accumulate page-locked memory)
+        sizes = _STAGE.setdefault("bits_sizes", [])
+        sizes.append(key)
+        while len(sizes) > _PACK_SIZES_KEPT:
+            old = _STAGE.pop(sizes.pop(0), None)
+            for ev in (old or {}).get("events", []):
+                if ev is not None:
+                    ev.synchronize()
     if len(ring["bufs"]) < _PACK_RING:
         ring["bufs"].append(torch.zeros(nbytes, dtype=torch.uint8).pin_memory())
         ring["events"].append(None)
