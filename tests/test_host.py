@@ -223,3 +223,26 @@ def test_host_mask_packer_equals_numpy_packbits():
     np.testing.assert_array_equal(out[:a.size // 8], np.packbits(a, bitorder="little"))
     assert lib.mfish_host_pack_mask(None, _lib.U8, 8, out.ctypes.data, 0) == _lib.ERR_INVALID
     assert lib.mfish_host_pack_mask(a.ctypes.data, 99, 8, out.ctypes.data, 0) == _lib.ERR_UNSUPPORTED
+
+
+def test_which_masks_travel_as_bits():
+    """device._packable: C-contiguous 3-D arrays of the ingest dtypes above the size threshold (bool as uint8);
+    everything else takes the whole-byte path.  No CUDA call involved."""
+    import torch
+    from muscle_fish_b200 import device as D
+    big = np.zeros((64, 64, 8), np.uint8)
+    assert D._packable(big) is None  # below the threshold
+    assert D._packable(big, min_elems=0) is big
+    assert D._packable_any_size(big.astype(np.bool_)).dtype == np.uint8
+    assert D._packable_any_size(big.astype(np.int64)).dtype == np.int64
+    assert D._packable_any_size(np.asfortranarray(big)) is None  # not C-contiguous
+    assert D._packable_any_size(big[:, :, ::2]) is None
+    assert D._packable_any_size(big[0]) is None  # not 3-D
+    assert D._packable_any_size(big.astype(np.complex64)) is None  # not an ingest dtype
+    t = torch.zeros((4, 4, 4), dtype=torch.bool)
+    a = D._packable_any_size(t)
+    assert a is not None and a.dtype == np.uint8 and a.shape == (4, 4, 4)
+    assert D._packable_any_size(t.permute(2, 0, 1)) is None
+    # the default follows the number of ranks per host (DESIGN.md section 6)
+    assert D.PACK_MASKS == (int(os.environ.get("LOCAL_WORLD_SIZE", "1")) <= 2
+                            if os.environ.get("MFISH_PACK_MASKS") is None else os.environ["MFISH_PACK_MASKS"] != "0")
